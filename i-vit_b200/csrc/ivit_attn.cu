@@ -1,0 +1,306 @@
+// Fused integer attention and the generic batched integer matmul (sm_100a).
+//
+// ivit_attention_i8:  one CTA per (sequence, head).  S = Q K^T -> dyadic requant to int8
+// (qact_attn1) -> Shiftmax (IntSoftmax, LUT over d = q - max in [-255, 0]) -> P V -> dyadic
+// requant to int8 (attn.qact2).  Scores and probabilities never leave the SM: S lives in the
+// accumulator registers of the integer tensor-core MMA (mma.sync m16n8k32 s8), P is re-used
+// in place as the A operand of the second MMA (16-bit P split into an unsigned high and low
+// byte plane, two u8 x s8 MMAs, recombined (hi << 8) + lo).
+// Reference call order: vit_quant.py:59-83 (DeiT), swin_quant.py:121-164 (Swin).
+//
+// ivit_bmm_i32: QuantMatMul.forward's contraction (quant_modules.py:223-228) for the
+// operator-level API (raw int32 result, strided batched views, int8 or int16 A).
+#include "ivit_common.cuh"
+#include "ivit_internal.h"
+
+namespace ivit {
+
+IVIT_DEVINL void mma_s8s8(int32_t (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k32.row.col.s32.s8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+r"(d[0]), "+r"(d[1]), "+r"(d[2]), "+r"(d[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+IVIT_DEVINL void mma_u8s8(int32_t (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k32.row.col.s32.u8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+r"(d[0]), "+r"(d[1]), "+r"(d[2]), "+r"(d[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+struct AttnArgs {
+    int n_seq, n_tok, H;
+    ivit_dyadic_t me_s;
+    int32_t x0;
+    float inv_x0;
+    int n;
+    int p_shift;                  // 31 - p_bits + 1  (16 for 16-bit P, 24 for 8-bit P)
+    int p_bits;
+    ivit_dyadic_t me_o;
+    const int8_t* relbias;        // [H, n_tok, n_tok] or null
+    ivit_dyadic_t me_s2, me_b;
+    const int32_t* mask;          // [n_win, n_tok, n_tok] or null
+    int n_win;
+};
+
+constexpr int ATT_WARPS = 7;
+constexpr int PAD_MARK = -100000;  // marks key columns >= n_tok
+
+// D: head dim (32 | 64).  KT: number of 32-token chunks (n_tok <= 32*KT).
+template <int D, int KT>
+__global__ void __launch_bounds__(ATT_WARPS * 32, 1)
+attention_kernel(const int8_t* __restrict__ qkv, const AttnArgs p, int8_t* __restrict__ out) {
+    constexpr int NT = KT * 4;             // 8-column score tiles
+    constexpr int KSTR = D + 16;           // bytes; (KSTR/4) mod 32 spreads the 8 fragment rows over distinct banks
+    constexpr int VSTR = KT * 32 + 16;
+    constexpr int KK = D / 32;             // k-steps of Q K^T
+    constexpr int ND = D / 8;              // 8-column output tiles
+    __shared__ __align__(16) int8_t sK[KT * 32 * KSTR];
+    __shared__ __align__(16) int8_t sVt[D * VSTR];
+    __shared__ int32_t sE[257];              // [256] = saturated value (d <= n*x0), used by masked entries
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, q4 = lane & 3;
+    const int b = blockIdx.x / p.H, h = blockIdx.x % p.H;
+    const int n_tok = p.n_tok;
+    const long long ld = 3LL * p.H * D;
+    const int8_t* qb = qkv + (long long)b * n_tok * ld + h * D;
+    const int8_t* kb = qb + p.H * D;
+    const int8_t* vb = qb + 2 * p.H * D;
+
+    // ---- K tile -> smem (zero padded) ----
+    for (int idx = tid; idx < KT * 32 * (D / 16); idx += ATT_WARPS * 32) {
+        const int j = idx / (D / 16), v = idx % (D / 16);
+        uint4 val = make_uint4(0, 0, 0, 0);
+        if (j < n_tok) val = *reinterpret_cast<const uint4*>(kb + (long long)j * ld + 16 * v);
+        *reinterpret_cast<uint4*>(sK + j * KSTR + 16 * v) = val;
+    }
+    // ---- V -> smem transposed [d][token slot], token slots permuted inside each 32-chunk so that
+    //      the P accumulator fragment of the first MMA is directly the A fragment of the second:
+    //      token jj = 8a + 2c + b (a<4, c<4, b<2)  ->  slot = (a<2 ? 0 : 16) + 4c + 2(a&1) + b
+    for (int idx = tid; idx < KT * 16 * (D / 4); idx += ATT_WARPS * 32) {
+        const int jp = idx / (D / 4), db = idx % (D / 4);     // token pair, group of 4 d
+        const int j = 2 * jp;
+        uint32_t r0 = 0, r1 = 0;
+        if (j < n_tok) r0 = *reinterpret_cast<const uint32_t*>(vb + (long long)j * ld + 4 * db);
+        if (j + 1 < n_tok) r1 = *reinterpret_cast<const uint32_t*>(vb + (long long)(j + 1) * ld + 4 * db);
+        const int jj = j & 31, chunk = j >> 5;
+        const int a = jj >> 3, c = (jj & 7) >> 1;
+        const int slot = ((a < 2) ? 0 : 16) + 4 * c + 2 * (a & 1);
+#pragma unroll
+        for (int dd = 0; dd < 4; ++dd) {
+            const uint16_t pr = (uint16_t)(((r0 >> (8 * dd)) & 0xff) | (((r1 >> (8 * dd)) & 0xff) << 8));
+            *reinterpret_cast<uint16_t*>(sVt + (4 * db + dd) * VSTR + chunk * 32 + slot) = pr;
+        }
+    }
+    // ---- Shiftmax exponent LUT: sE[k] = int_exp_shift(-k), k = max - q in [0, 255] ----
+    for (int k = tid; k < 257; k += ATT_WARPS * 32)
+        sE[k] = (int32_t)shiftexp(k < 256 ? -k : -(1 << 20), p.x0, p.inv_x0, p.n);
+    __syncthreads();
+
+    const int n_row_tiles = (n_tok + 15) / 16;
+    for (int rt = warp; rt < n_row_tiles; rt += ATT_WARPS) {
+        const int r0 = rt * 16 + g, r1 = r0 + 8;
+        // ---- Q fragments straight from global ----
+        uint32_t aq[KK][4];
+#pragma unroll
+        for (int kk = 0; kk < KK; ++kk) {
+            aq[kk][0] = (r0 < n_tok) ? *reinterpret_cast<const uint32_t*>(qb + (long long)r0 * ld + 32 * kk + 4 * q4) : 0u;
+            aq[kk][1] = (r1 < n_tok) ? *reinterpret_cast<const uint32_t*>(qb + (long long)r1 * ld + 32 * kk + 4 * q4) : 0u;
+            aq[kk][2] = (r0 < n_tok) ? *reinterpret_cast<const uint32_t*>(qb + (long long)r0 * ld + 32 * kk + 16 + 4 * q4) : 0u;
+            aq[kk][3] = (r1 < n_tok) ? *reinterpret_cast<const uint32_t*>(qb + (long long)r1 * ld + 32 * kk + 16 + 4 * q4) : 0u;
+        }
+        // ---- S = Q K^T ----
+        int32_t s[NT][4];
+#pragma unroll
+        for (int t = 0; t < NT; ++t) {
+            s[t][0] = s[t][1] = s[t][2] = s[t][3] = 0;
+#pragma unroll
+            for (int kk = 0; kk < KK; ++kk) {
+                const uint32_t b0 = *reinterpret_cast<const uint32_t*>(sK + (8 * t + g) * KSTR + 32 * kk + 4 * q4);
+                const uint32_t b1 = *reinterpret_cast<const uint32_t*>(sK + (8 * t + g) * KSTR + 32 * kk + 16 + 4 * q4);
+                mma_s8s8(s[t], aq[kk], b0, b1);
+            }
+        }
+        // ---- requant to int8 (qact_attn1), optional rel-pos bias / mask (Swin), row max ----
+        int32_t mx0 = INT32_MIN, mx1 = INT32_MIN;
+#pragma unroll
+        for (int t = 0; t < NT; ++t) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const int col = 8 * t + 2 * q4 + (c & 1);
+                const int row = (c < 2) ? r0 : r1;
+                int32_t v = clamp_bits<8>(requant32(s[t][c], p.me_s.m, p.me_s.e));
+                if (p.relbias != nullptr && col < n_tok && row < n_tok) {
+                    const int32_t bq = (int32_t)p.relbias[((long long)h * n_tok + row) * n_tok + col];
+                    long long t2 = requant64((long long)v, p.me_s2.m, p.me_s2.e) + requant64((long long)bq, p.me_b.m, p.me_b.e);
+                    v = clamp_i64_bits(t2, 8);
+                }
+                if (p.mask != nullptr && col < n_tok && row < n_tok)
+                    v += p.mask[((long long)(b % p.n_win) * n_tok + row) * n_tok + col];
+                if (col >= n_tok) v = PAD_MARK;
+                s[t][c] = v;
+                if (c < 2) mx0 = v > mx0 ? v : mx0; else mx1 = v > mx1 ? v : mx1;
+            }
+        }
+        mx0 = max(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = max(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+        mx1 = max(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = max(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+        // ---- exponentials (LUT) and row sums ----
+        unsigned long long sum0 = 0, sum1 = 0;
+#pragma unroll
+        for (int t = 0; t < NT; ++t) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const int32_t v = s[t][c];
+                int32_t E = 0;
+                if (v != PAD_MARK) {
+                    int k = ((c < 2) ? mx0 : mx1) - v;
+                    // k > 255 only for masked Swin entries (addend RNE(-100/s)); those are always past the
+                    // saturation point t <= n*x0 when s < 0.35, checked by the caller
+                    k = k > 255 ? 256 : k;
+                    E = sE[k];
+                }
+                s[t][c] = E;
+                if (c < 2) sum0 += (uint32_t)E; else sum1 += (uint32_t)E;
+            }
+        }
+        sum0 += __shfl_xor_sync(0xffffffffu, sum0, 1); sum0 += __shfl_xor_sync(0xffffffffu, sum0, 2);
+        sum1 += __shfl_xor_sync(0xffffffffu, sum1, 1); sum1 += __shfl_xor_sync(0xffffffffu, sum1, 2);
+        const uint32_t S0 = sum0 > 2147483647ULL ? 2147483647u : (uint32_t)sum0;   // clamp_max_(2**31-1)
+        const uint32_t S1 = sum1 > 2147483647ULL ? 2147483647u : (uint32_t)sum1;
+        const uint32_t F0 = 2147483647u / (S0 ? S0 : 1u);
+        const uint32_t F1 = 2147483647u / (S1 ? S1 : 1u);
+
+        // ---- O = P V with P = (E * F) >> p_shift, hi/lo byte planes ----
+        int32_t ohi[ND][4], olo[ND][4];
+#pragma unroll
+        for (int nd = 0; nd < ND; ++nd) {
+            ohi[nd][0] = ohi[nd][1] = ohi[nd][2] = ohi[nd][3] = 0;
+            olo[nd][0] = olo[nd][1] = olo[nd][2] = olo[nd][3] = 0;
+        }
+        const bool two_plane = p.p_bits > 8;
+#pragma unroll
+        for (int kc = 0; kc < KT; ++kc) {
+            uint32_t alo[4], ahi[4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                // fragment register r: rows (r&1 ? r1 : r0), tiles (4kc + (r>>1)*2 + {0,1}), columns {0,1} of each
+                const int tA = 4 * kc + (r >> 1) * 2;
+                const int cb = (r & 1) * 2;
+                const uint32_t F = (r & 1) ? F1 : F0;
+                uint32_t lo = 0, hi = 0;
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const uint32_t E = (uint32_t)s[tA + (e >> 1)][cb + (e & 1)];
+                    const uint32_t P = (uint32_t)(((unsigned long long)E * (unsigned long long)F) >> p.p_shift);
+                    lo |= (P & 0xffu) << (8 * e);
+                    hi |= ((P >> 8) & 0xffu) << (8 * e);
+                }
+                alo[r] = lo; ahi[r] = hi;
+            }
+#pragma unroll
+            for (int nd = 0; nd < ND; ++nd) {
+                const uint32_t b0 = *reinterpret_cast<const uint32_t*>(sVt + (8 * nd + g) * VSTR + 32 * kc + 4 * q4);
+                const uint32_t b1 = *reinterpret_cast<const uint32_t*>(sVt + (8 * nd + g) * VSTR + 32 * kc + 16 + 4 * q4);
+                mma_u8s8(olo[nd], alo, b0, b1);
+                if (two_plane) mma_u8s8(ohi[nd], ahi, b0, b1);
+            }
+        }
+        // ---- requant (attn.qact2) and store ----
+#pragma unroll
+        for (int nd = 0; nd < ND; ++nd) {
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                const int row = half ? r1 : r0;
+                if (row < n_tok) {
+                    const int32_t v0 = (ohi[nd][2 * half] << 8) + olo[nd][2 * half];
+                    const int32_t v1 = (ohi[nd][2 * half + 1] << 8) + olo[nd][2 * half + 1];
+                    const int32_t o0 = clamp_bits<8>(requant32(v0, p.me_o.m, p.me_o.e));
+                    const int32_t o1 = clamp_bits<8>(requant32(v1, p.me_o.m, p.me_o.e));
+                    int8_t* dst = out + ((long long)b * n_tok + row) * (long long)(p.H * D) + h * D + 8 * nd + 2 * q4;
+                    *reinterpret_cast<uint16_t*>(dst) = (uint16_t)((o0 & 0xff) | ((o1 & 0xff) << 8));
+                }
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// generic strided batched integer matmul, raw int32 result (operator-level QuantMatMul)
+// ------------------------------------------------------------------------------------
+template <typename TA>
+__global__ void bmm_i32_kernel(const TA* __restrict__ A, long long lda, long long sa,
+                               const int8_t* __restrict__ B, long long ldb, long long sb, int trans_b,
+                               int M, int N, int K, int32_t* __restrict__ C, long long ldc, long long sc) {
+    __shared__ int32_t tA[16][17], tB[16][17];
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const long long bi = blockIdx.z;
+    const TA* Ab = A + bi * sa;
+    const int8_t* Bb = B + bi * sb;
+    const int row = blockIdx.y * 16 + ty, col = blockIdx.x * 16 + tx;
+    int32_t acc = 0;
+    for (int k0 = 0; k0 < K; k0 += 16) {
+        tA[ty][tx] = (row < M && k0 + tx < K) ? (int32_t)Ab[(long long)row * lda + k0 + tx] : 0;
+        const int bn = blockIdx.x * 16 + ty;               // B tile stored [n][k]
+        int32_t bv = 0;
+        if (bn < N && k0 + tx < K)
+            bv = trans_b ? (int32_t)Bb[(long long)bn * ldb + k0 + tx] : (int32_t)Bb[(long long)(k0 + tx) * ldb + bn];
+        tB[ty][tx] = bv;
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < 16; ++k) acc += tA[ty][k] * tB[tx][k];
+        __syncthreads();
+    }
+    if (row < M && col < N) C[bi * sc + (long long)row * ldc + col] = acc;
+}
+
+}  // namespace ivit
+
+using namespace ivit;
+
+extern "C" int ivit_attention_i8(ivit_ctx* ctx, const int8_t* qkv, const ivit_attn_params* ap, int8_t* out,
+                                 ivit_stream stream) {
+    IVIT_REQUIRE(ctx && qkv && ap && out, "ivit_attention_i8: null pointer");
+    IVIT_REQUIRE(ap->n_seq > 0 && ap->n_tok > 0 && ap->n_heads > 0, "ivit_attention_i8: bad shape");
+    IVIT_REQUIRE(ap->head_dim == 64 || ap->head_dim == 32, "ivit_attention_i8: head_dim must be 32 or 64");
+    IVIT_REQUIRE(ap->p_bits == 16 || ap->p_bits == 8, "ivit_attention_i8: p_bits must be 8 or 16");
+    IVIT_REQUIRE(ap->n >= 1 && ap->n <= 16, "ivit_attention_i8: n must be in [1,16] (int32 exponent LUT)");
+    IVIT_REQUIRE(((uintptr_t)qkv % 16) == 0 && ((uintptr_t)out % 2) == 0, "ivit_attention_i8: qkv must be 16-byte aligned");
+    if (!(ap->x0 <= -1 && ap->x0 >= -65535))
+        return fail(IVIT_ENOTSUP, "ivit_attention_i8: x0=%d outside [-65535, -1]", ap->x0);
+    if (ap->mask) IVIT_REQUIRE(ap->n_win > 0 && ap->n_seq % ap->n_win == 0, "ivit_attention_i8: n_seq must be a multiple of n_win");
+    AttnArgs a;
+    a.n_seq = ap->n_seq; a.n_tok = ap->n_tok; a.H = ap->n_heads;
+    a.me_s = ap->me_s; a.x0 = ap->x0; a.inv_x0 = 1.0f / (float)ap->x0; a.n = ap->n;
+    a.p_bits = ap->p_bits; a.p_shift = 31 - ap->p_bits + 1;
+    a.me_o = ap->me_o; a.relbias = ap->relbias; a.me_s2 = ap->me_s2; a.me_b = ap->me_b;
+    a.mask = ap->mask; a.n_win = ap->n_win > 0 ? ap->n_win : 1;
+    const int grid = ap->n_seq * ap->n_heads;
+    cudaStream_t s = st(stream);
+    if (ap->head_dim == 64) {
+        if (ap->n_tok <= 64) attention_kernel<64, 2><<<grid, ATT_WARPS * 32, 0, s>>>(qkv, a, out);
+        else if (ap->n_tok <= 224) attention_kernel<64, 7><<<grid, ATT_WARPS * 32, 0, s>>>(qkv, a, out);
+        else return fail(IVIT_ENOTSUP, "ivit_attention_i8: n_tok=%d > 224 not supported", ap->n_tok);
+    } else {
+        if (ap->n_tok <= 64) attention_kernel<32, 2><<<grid, ATT_WARPS * 32, 0, s>>>(qkv, a, out);
+        else if (ap->n_tok <= 224) attention_kernel<32, 7><<<grid, ATT_WARPS * 32, 0, s>>>(qkv, a, out);
+        else return fail(IVIT_ENOTSUP, "ivit_attention_i8: n_tok=%d > 224 not supported", ap->n_tok);
+    }
+    IVIT_LAUNCH_OK("attention_kernel");
+    return IVIT_OK;
+}
+
+extern "C" int ivit_bmm_i32(ivit_ctx* ctx, const void* A, int a_dtype, int64_t lda, int64_t sa, const int8_t* B,
+                            int64_t ldb, int64_t sb, int trans_b, int64_t batch, int M, int N, int K,
+                            int32_t* C, int64_t ldc, int64_t sc, ivit_stream stream) {
+    IVIT_REQUIRE(ctx && A && B && C && batch > 0 && M > 0 && N > 0 && K > 0, "ivit_bmm_i32: bad arguments");
+    IVIT_REQUIRE(a_dtype == IVIT_I8 || a_dtype == IVIT_I16, "ivit_bmm_i32: a_dtype must be I8 or I16");
+    IVIT_REQUIRE(batch <= 65535, "ivit_bmm_i32: batch > 65535");
+    dim3 grid((N + 15) / 16, (M + 15) / 16, (unsigned)batch);
+    if (a_dtype == IVIT_I8)
+        bmm_i32_kernel<int8_t><<<grid, 256, 0, st(stream)>>>((const int8_t*)A, lda, sa, B, ldb, sb, trans_b, M, N, K, C, ldc, sc);
+    else
+        bmm_i32_kernel<int16_t><<<grid, 256, 0, st(stream)>>>((const int16_t*)A, lda, sa, B, ldb, sb, trans_b, M, N, K, C, ldc, sc);
+    IVIT_LAUNCH_OK("bmm_i32_kernel");
+    return IVIT_OK;
+}

@@ -1,0 +1,155 @@
+// Shared device helpers for the I-ViT sm_100a kernels: exact dyadic requantisation,
+// shift-exponential, saturating packs, warp reductions, vector load/store.
+//
+// Integer semantics follow SURVEY.md Appendix A (restating the reference's
+// models/quantization_utils/quant_utils.py and quant_modules.py, cited per function).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/ivit_b200.h"
+
+#define IVIT_DEVINL __device__ __forceinline__
+
+namespace ivit {
+
+// ------------------------------------------------------------------------------------
+// Dyadic requant   out = RNE(z * m / 2^e)      fixedpoint_mul.forward, quant_utils.py:229-230
+//   m : int32 (|m| in [2^30, 2^31), sign = sign of the scale ratio; 2^31 normalised away)
+//   e : clamped to [-1, 63] by the host/dyadic kernel (e >= 63 => 0, e <= -1 saturates)
+// Exact 64-bit product; result saturated to int32 (callers clamp further to 8/16 bits).
+// ------------------------------------------------------------------------------------
+IVIT_DEVINL int32_t sat_i64_to_i32(long long v) {
+    v = v > 2147483647LL ? 2147483647LL : v;
+    v = v < -2147483648LL ? -2147483648LL : v;
+    return (int32_t)v;
+}
+
+IVIT_DEVINL long long requant64(long long z, int32_t m, int32_t e) {
+    // general form used by the row kernels (z may exceed 32 bits after LayerNorm)
+    if (e >= 63) return 0;
+    // |z| < 2^32 guaranteed by callers => |z*m| < 2^63
+    long long p = z * (long long)m;
+    if (e <= 0) {
+        // e == 0 : p ; e == -1 : 2p  (saturating)
+        if (e < 0) {
+            if (p > (1LL << 61)) return (1LL << 62);
+            if (p < -(1LL << 61)) return -(1LL << 62);
+            p *= 2;
+        }
+        return p;
+    }
+    const long long half = 1LL << (e - 1);
+    const long long t = p + half;                    // |p| <= 2^62, half <= 2^61: no overflow
+    long long q = t >> e;                            // floor((p + half) / 2^e)  == round half up
+    const bool tie = (t & ((1ULL << e) - 1ULL)) == 0ULL;
+    q -= (long long)(tie & (q & 1LL));               // exact .5 -> even
+    return q;
+}
+
+IVIT_DEVINL int32_t requant32(int32_t z, int32_t m, int32_t e) {
+    return sat_i64_to_i32(requant64((long long)z, m, e));
+}
+
+// Fast path for 32 <= e <= 62 when the caller knows ties are impossible or handled:
+// p = z*m + half, q = hi32(p) >> (e-32).  Used by the GEMM epilogue (see ivit_gemm.cu).
+IVIT_DEVINL int32_t requant32_e32(int32_t z, int32_t m, int32_t e) {
+    const long long half = 1LL << (e - 1);
+    const long long t = (long long)z * (long long)m + half;
+    const int32_t hi = (int32_t)(t >> 32);
+    const uint32_t lo = (uint32_t)t;
+    const int sh = e - 32;
+    int32_t q = hi >> sh;
+    const bool tie = (lo == 0u) && ((hi & ((1 << sh) - 1)) == 0);
+    q -= (int32_t)(tie & (q & 1));
+    return q;
+}
+
+template <int BITS>
+IVIT_DEVINL int32_t clamp_bits(int32_t v) {
+    constexpr int32_t hi = (BITS >= 32) ? 2147483647 : ((1 << (BITS - 1)) - 1);
+    constexpr int32_t lo = -hi - 1;
+    return v < lo ? lo : (v > hi ? hi : v);
+}
+IVIT_DEVINL int32_t clamp_bits_rt(int32_t v, int bits) {
+    if (bits >= 32) return v;
+    const int32_t hi = (1 << (bits - 1)) - 1;
+    const int32_t lo = -hi - 1;
+    return v < lo ? lo : (v > hi ? hi : v);
+}
+IVIT_DEVINL int32_t clamp_i64_bits(long long v, int bits) {
+    const long long hi = (bits >= 32) ? 2147483647LL : ((1LL << (bits - 1)) - 1);
+    const long long lo = -hi - 1;
+    return (int32_t)(v < lo ? lo : (v > hi ? hi : v));
+}
+
+// ------------------------------------------------------------------------------------
+// int_exp_shift   quant_modules.py:410-423 (IntGELU) / :469-481 (IntSoftmax)
+//   t = d + floor(d/2) - floor(d/16); t = max(t, n*x0); k = floor(t/x0); r = t - x0*k
+//   E = max(floor((r/2 - x0) * 2^(n-k)), 0) = ((r - 2*x0) << (n-k)) >> 1
+// x0 < 0.  inv_x0 = 1.0f / x0 (host supplied) seeds the floor division; two exact
+// corrections make it an exact floor for |t| < 2^24.
+// Domain (checked at freeze): 8 <= -x0 <= 2^15, |d| <= 256  => result < 2^62.
+// ------------------------------------------------------------------------------------
+IVIT_DEVINL long long shiftexp(int32_t d, int32_t x0, float inv_x0, int n) {
+    int32_t t = d + (d >> 1) - (d >> 4);
+    const int32_t lim = n * x0;
+    t = t < lim ? lim : t;
+    int32_t k = __float2int_rd(__int2float_rn(t) * inv_x0);
+    int32_t r = t - x0 * k;                          // want x0 < r <= 0
+    if (r > 0) { k -= 1; r += x0; }
+    if (r <= x0) { k += 1; r -= x0; }
+    const int32_t base = r - 2 * x0;                 // in (|x0|, 2|x0|]
+    const int sh = n - k - 1;
+    long long E = (sh >= 0) ? ((long long)base << (sh > 46 ? 46 : sh)) : (long long)(base >> 1);
+    return E;
+}
+
+// floor((2^31-1) / S) for 1 <= S <= 2^31-1     quant_modules.py:438, 492
+IVIT_DEVINL uint32_t recip_factor(uint32_t S) { return 2147483647u / S; }
+
+// ------------------------------------------------------------------------------------
+// Warp reductions
+// ------------------------------------------------------------------------------------
+IVIT_DEVINL int32_t warp_max_i32(int32_t v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { int32_t t = __shfl_xor_sync(0xffffffffu, v, o); v = t > v ? t : v; }
+    return v;
+}
+IVIT_DEVINL long long warp_sum_i64(long long v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+IVIT_DEVINL int32_t warp_sum_i32(int32_t v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// ------------------------------------------------------------------------------------
+// Typed element access (op kernels are templated on the integer storage type)
+// ------------------------------------------------------------------------------------
+template <typename T> struct DType;
+template <> struct DType<int8_t>  { static constexpr int id = IVIT_I8;  static constexpr int bits = 8; };
+template <> struct DType<int16_t> { static constexpr int id = IVIT_I16; static constexpr int bits = 16; };
+template <> struct DType<int32_t> { static constexpr int id = IVIT_I32; static constexpr int bits = 32; };
+
+IVIT_DEVINL int32_t load_int(const void* p, int dtype, long long i) {
+    switch (dtype) {
+        case IVIT_I8:  return (int32_t)((const int8_t*)p)[i];
+        case IVIT_U8:  return (int32_t)((const uint8_t*)p)[i];
+        case IVIT_I16: return (int32_t)((const int16_t*)p)[i];
+        default:       return ((const int32_t*)p)[i];
+    }
+}
+IVIT_DEVINL void store_int(void* p, int dtype, long long i, int32_t v) {
+    switch (dtype) {
+        case IVIT_I8:  ((int8_t*)p)[i] = (int8_t)v; break;
+        case IVIT_U8:  ((uint8_t*)p)[i] = (uint8_t)v; break;
+        case IVIT_I16: ((int16_t*)p)[i] = (int16_t)v; break;
+        default:       ((int32_t*)p)[i] = v; break;
+    }
+}
+
+}  // namespace ivit

@@ -1,0 +1,518 @@
+// INT8 GEMM on the 5th-generation tensor cores (tcgen05.mma kind::i8, sm_100a) with the dyadic
+// requantisation of the following QuantAct fused into the epilogue.
+//
+//   acc[i,j] = sum_k A[i,k] * W[j,k] (+ bias[j])              QuantLinear.forward, quant_modules.py:93-97
+//   out[i,j] = clamp(RNE(acc * m[j] / 2^e[j]) ...)            QuantAct / fixedpoint_mul, quant_utils.py:192-253
+//
+// Structure (one persistent CTA per SM, 192 threads):
+//   warp 0      TMA producer: A tile [128 x 128 B] and W tile [BN x 128 B] per k-block into a
+//               STAGES-deep shared-memory ring (128-byte swizzle), mbarrier full/empty pairs
+//   warp 1      TMEM allocator + MMA issuer: one thread issues 4 x tcgen05.mma (K = 32 each) per
+//               k-block into one of two TMEM accumulators (128 lanes x BN int32 columns each)
+//   warps 2-5   epilogue: tcgen05.ld 32 columns at a time -> bias + per-channel dyadic requant
+//               (+ residual) in registers -> 16-byte stores.  Runs concurrently with the MMAs of
+//               the next tile (double-buffered accumulator).
+// Both operands are K-major (row-major A [M,K], row-major W [N,K]), so no transposes anywhere.
+#include <stdio.h>
+#include <stdlib.h>
+
+#include "ivit_common.cuh"
+#include "ivit_internal.h"
+#include "ivit_ptx.cuh"
+
+namespace ivit {
+
+constexpr int GEMM_BM = 128;
+constexpr int GEMM_BK = 128;          // bytes == int8 elements per k-block (one 128 B swizzle row)
+constexpr int GEMM_UMMA_K = 32;       // K per tcgen05.mma for 8-bit operands
+constexpr int GEMM_THREADS = 192;
+
+enum GemmMode { GM_RAW_I32 = 0, GM_CARRIER = 1, GM_RQ_I8 = 2, GM_RQ_I16 = 3 };
+
+struct GemmArgs {
+    int M, N, K;
+    int mode_bits;                    // clamp bits for requant modes
+    const int32_t* bias;
+    const ivit_dyadic_t* me;
+    const void* residual;             // int16 [M, res_ld] (GM_RQ_I16 only)
+    long long res_ld;
+    ivit_dyadic_t res_me;
+    int two_stage;
+    ivit_dyadic_t me2;
+    const float* scale;
+    void* out;
+    long long out_ld;
+};
+
+struct alignas(16) ColParam {         // per output column, staged in shared memory per tile
+    int32_t bias;
+    int32_t m;
+    int32_t e;
+    float scale;
+};
+
+template <int BN, int STAGES>
+struct GemmSmem {
+    static constexpr int A_BYTES = GEMM_BM * GEMM_BK;
+    static constexpr int B_BYTES = BN * GEMM_BK;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int PARAM_BYTES = 2 * BN * (int)sizeof(ColParam);
+    static constexpr int BAR_BYTES = 256;
+    static constexpr int TOTAL = STAGES * STAGE_BYTES + PARAM_BYTES + BAR_BYTES + 1024;  // +1024 alignment slack
+};
+
+template <int BN, int STAGES, int MODE>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_i8_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                       const GemmArgs args) {
+    using S = GemmSmem<BN, STAGES>;
+    constexpr uint32_t TMEM_COLS = 2 * BN;            // double-buffered accumulator (256 or 512)
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* smem = smem_raw + (smem_base - ptx::smem_u32(smem_raw));
+
+    const uint32_t stage_base = smem_base;
+    ColParam* col_params = reinterpret_cast<ColParam*>(smem + STAGES * S::STAGE_BYTES);
+    const uint32_t bar_base = smem_base + STAGES * S::STAGE_BYTES + S::PARAM_BYTES;
+    // barrier layout (8 B each): full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], then tmem ptr + flags
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+    auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + s); };
+    auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + 2 + s); };
+    volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + STAGES * S::STAGE_BYTES + S::PARAM_BYTES + 8 * (2 * STAGES + 4));
+    int* fast_flag = reinterpret_cast<int*>(const_cast<uint32_t*>(tmem_ptr_smem) + 2);   // [2] one per accumulator stage
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    const int tiles_m = (args.M + GEMM_BM - 1) / GEMM_BM;
+    const int tiles_n = (args.N + BN - 1) / BN;
+    const int num_tiles = tiles_m * tiles_n;
+    const int num_kb = (args.K + GEMM_BK - 1) / GEMM_BK;
+
+    if (warp == 0 && lane == 0) {
+        ptx::prefetch_tensormap(&tmap_a);
+        ptx::prefetch_tensormap(&tmap_b);
+        for (int s = 0; s < STAGES; ++s) {
+            ptx::mbar_init(full_bar(s), 1);
+            ptx::mbar_init(empty_bar(s), 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            ptx::mbar_init(tfull_bar(s), 1);
+            ptx::mbar_init(tempty_bar(s), 4);          // one arrive per epilogue warp
+        }
+        ptx::fence_barrier_init();
+    }
+    if (warp == 1) {
+        ptx::tmem_alloc(ptx::smem_u32(const_cast<uint32_t*>(tmem_ptr_smem)), TMEM_COLS);
+        ptx::tmem_relinquish();
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+
+    if (warp == 0) {
+        // ================= TMA producer =================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int m0 = (tile / tiles_n) * GEMM_BM;
+                const int n0 = (tile % tiles_n) * BN;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
+                    ptx::mbar_arrive_expect_tx(full_bar(stage), S::STAGE_BYTES);
+                    const uint32_t a_dst = stage_base + stage * S::STAGE_BYTES;
+                    const uint32_t b_dst = a_dst + S::A_BYTES;
+                    ptx::tma_load_2d(a_dst, &tmap_a, full_bar(stage), kb * GEMM_BK, m0);
+                    ptx::tma_load_2d(b_dst, &tmap_b, full_bar(stage), kb * GEMM_BK, n0);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer =================
+        if (lane == 0) {
+            constexpr uint32_t idesc = ptx::umma_idesc_i8(GEMM_BM, BN, 1, 1);
+            int stage = 0;
+            uint32_t phase = 0;
+            int as = 0;
+            uint32_t aphase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                ptx::mbar_wait(tempty_bar(as), aphase ^ 1u);
+                ptx::tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    ptx::mbar_wait(full_bar(stage), phase);
+                    ptx::tc_fence_after();
+                    const uint32_t a_addr = stage_base + stage * S::STAGE_BYTES;
+                    const uint32_t b_addr = a_addr + S::A_BYTES;
+                    const uint64_t a_desc = ptx::umma_desc_k_sw128(a_addr);
+                    const uint64_t b_desc = ptx::umma_desc_k_sw128(b_addr);
+#pragma unroll
+                    for (int k = 0; k < GEMM_BK / GEMM_UMMA_K; ++k) {
+                        // advance along K inside the 128 B swizzle row: +32 B == +2 in the (addr >> 4) field
+                        ptx::mma_i8_ss(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc,
+                                       (kb | k) != 0 ? 1u : 0u);
+                    }
+                    ptx::mma_commit(empty_bar(stage));             // frees the smem slot when the MMAs retire
+                    if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+                }
+                ptx::mma_commit(tfull_bar(as));                    // accumulator complete -> epilogue
+                if (++as == 2) { as = 0; aphase ^= 1u; }
+            }
+        }
+    } else {
+        // ================= epilogue (warps 2..5) =================
+        const int ew = warp - 2;                      // 0..3
+        const int lane_group = warp & 3;              // TMEM lanes [32*lane_group, +32) are accessible to this warp
+        const int et = ew * 32 + lane;                // 0..127 thread index inside the epilogue group
+        int as = 0;
+        uint32_t aphase = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            const int m0 = (tile / tiles_n) * GEMM_BM;
+            const int n0 = (tile % tiles_n) * BN;
+            ColParam* cp = col_params + as * BN;
+            // stage the per-column constants of this tile (coalesced global reads)
+            if (et == 0) fast_flag[as] = 1;
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            {
+                int ok = 1;
+                for (int c = et; c < BN; c += 128) {
+                    const int n = n0 + c;
+                    ColParam p;
+                    p.bias = 0; p.m = 0; p.e = 63; p.scale = 0.f;
+                    if (n < args.N) {
+                        if (args.bias) p.bias = args.bias[n];
+                        if (MODE == GM_RQ_I8 || MODE == GM_RQ_I16) {
+                            const ivit_dyadic_t d = args.me[n];
+                            p.m = d.m; p.e = d.e;
+                            ok &= (d.e >= 32 && d.e <= 62);
+                        }
+                        if (MODE == GM_CARRIER) p.scale = args.scale[n];
+                    }
+                    cp[c] = p;
+                }
+                if (!ok) atomicAnd(&fast_flag[as], 0);
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            const bool fast = fast_flag[as] != 0;
+
+            ptx::mbar_wait(tfull_bar(as), aphase);
+            ptx::tc_fence_after();
+
+            const int row = m0 + lane_group * 32 + lane;
+            const bool row_ok = row < args.M;
+            const uint32_t t_row = tmem_base + ((uint32_t)(lane_group * 32) << 16) + (uint32_t)(as * BN);
+#pragma unroll 1
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                uint32_t r[32];
+                ptx::tmem_ld_32x32b_x32(t_row + (uint32_t)c0, r);
+                ptx::tmem_ld_wait();
+                const int ncol0 = n0 + c0;
+                if (ncol0 >= args.N) break;            // uniform: whole chunk out of range
+                const bool full_chunk = (ncol0 + 32 <= args.N);
+
+                if (MODE == GM_RAW_I32 || MODE == GM_CARRIER) {
+                    uint32_t o[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const ColParam p = cp[c0 + j];
+                        const int32_t v = (int32_t)r[j] + p.bias;
+                        o[j] = (MODE == GM_RAW_I32) ? (uint32_t)v : __float_as_uint(__fmul_rn(__int2float_rn(v), p.scale));
+                    }
+                    if (row_ok) {
+                        uint32_t* dst = reinterpret_cast<uint32_t*>(args.out) + (long long)row * args.out_ld + ncol0;
+                        if (full_chunk && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+#pragma unroll
+                            for (int j = 0; j < 32; j += 4)
+                                *reinterpret_cast<uint4*>(dst + j) = make_uint4(o[j], o[j + 1], o[j + 2], o[j + 3]);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j)
+                                if (ncol0 + j < args.N) dst[j] = o[j];
+                        }
+                    }
+                } else {
+                    int32_t q[32];
+                    if (fast) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const ColParam p = cp[c0 + j];
+                            q[j] = requant32_e32((int32_t)r[j] + p.bias, p.m, p.e);
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const ColParam p = cp[c0 + j];
+                            q[j] = requant32((int32_t)r[j] + p.bias, p.m, p.e);
+                        }
+                    }
+                    if (MODE == GM_RQ_I8) {
+                        if (row_ok) {
+                            int8_t* dst = reinterpret_cast<int8_t*>(args.out) + (long long)row * args.out_ld + ncol0;
+                            if (full_chunk && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+                                uint32_t w[8];
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) {
+                                    const uint32_t b0 = (uint32_t)(clamp_bits<8>(q[4 * j + 0]) & 0xff);
+                                    const uint32_t b1 = (uint32_t)(clamp_bits<8>(q[4 * j + 1]) & 0xff);
+                                    const uint32_t b2 = (uint32_t)(clamp_bits<8>(q[4 * j + 2]) & 0xff);
+                                    const uint32_t b3 = (uint32_t)(clamp_bits<8>(q[4 * j + 3]) & 0xff);
+                                    w[j] = b0 | (b1 << 8) | (b2 << 16) | (b3 << 24);
+                                }
+                                *reinterpret_cast<uint4*>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
+                                *reinterpret_cast<uint4*>(dst + 16) = make_uint4(w[4], w[5], w[6], w[7]);
+                            } else {
+#pragma unroll
+                                for (int j = 0; j < 32; ++j)
+                                    if (ncol0 + j < args.N) dst[j] = (int8_t)clamp_bits<8>(q[j]);
+                            }
+                        }
+                    } else {  // GM_RQ_I16 (+ optional residual / two-stage)
+                        if (row_ok) {
+                            int16_t* dst = reinterpret_cast<int16_t*>(args.out) + (long long)row * args.out_ld + ncol0;
+                            const int16_t* res = args.residual
+                                ? reinterpret_cast<const int16_t*>(args.residual) + (long long)row * args.res_ld + ncol0 : nullptr;
+                            const bool vec = full_chunk && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) &&
+                                             (!res || ((reinterpret_cast<uintptr_t>(res) & 15) == 0));
+                            int32_t rv[32];
+                            if (res) {
+                                if (vec) {
+#pragma unroll
+                                    for (int j = 0; j < 32; j += 8) {
+                                        const uint4 t = *reinterpret_cast<const uint4*>(res + j);
+                                        const uint32_t tw[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+                                        for (int u = 0; u < 4; ++u) {
+                                            rv[j + 2 * u] = (int32_t)(int16_t)(tw[u] & 0xffff);
+                                            rv[j + 2 * u + 1] = (int32_t)(int16_t)(tw[u] >> 16);
+                                        }
+                                    }
+                                } else {
+#pragma unroll
+                                    for (int j = 0; j < 32; ++j) rv[j] = (ncol0 + j < args.N) ? (int32_t)res[j] : 0;
+                                }
+                            }
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) {
+                                int32_t v = clamp_bits_rt(q[j], args.mode_bits);
+                                if (args.two_stage) v = requant32(v, args.me2.m, args.me2.e);
+                                if (res) {
+                                    long long s = (long long)v + requant64((long long)rv[j], args.res_me.m, args.res_me.e);
+                                    v = clamp_i64_bits(s, args.mode_bits);
+                                } else if (args.two_stage) {
+                                    v = clamp_bits_rt(v, args.mode_bits);
+                                }
+                                q[j] = v;
+                            }
+                            if (vec) {
+#pragma unroll
+                                for (int j = 0; j < 32; j += 8) {
+                                    uint32_t w[4];
+#pragma unroll
+                                    for (int u = 0; u < 4; ++u)
+                                        w[u] = ((uint32_t)q[j + 2 * u] & 0xffffu) | ((uint32_t)q[j + 2 * u + 1] << 16);
+                                    *reinterpret_cast<uint4*>(dst + j) = make_uint4(w[0], w[1], w[2], w[3]);
+                                }
+                            } else {
+#pragma unroll
+                                for (int j = 0; j < 32; ++j)
+                                    if (ncol0 + j < args.N) dst[j] = (int16_t)q[j];
+                            }
+                        }
+                    }
+                }
+            }
+            // release the accumulator back to the MMA warp
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(tempty_bar(as));
+            if (++as == 2) { as = 0; aphase ^= 1u; }
+        }
+    }
+
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// Debug-only SIMT implementation (dp4a), selected by IVIT_GEMM_IMPL=simt.  It exists so that
+// the tensor-core kernel can be cross-checked ON THE GPU at full problem sizes (the CPU oracle
+// is too slow there); it is never the default path.
+// ------------------------------------------------------------------------------------
+__global__ void gemm_i8_simt_raw(const int8_t* __restrict__ A, long long lda, const int8_t* __restrict__ W,
+                                 int M, int N, int K, int32_t* __restrict__ C, long long ldc) {
+    __shared__ int32_t sa[32][9], sb[32][9];          // 32 rows x 32 bytes (+pad)
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 32 threads
+    const int row = blockIdx.y * 32 + ty, col = blockIdx.x * 32 + tx;
+    int32_t acc = 0;
+    for (int k0 = 0; k0 < K; k0 += 32) {
+        // each thread loads one byte-quad for A and B tiles
+        if (tx < 8) {
+            const int r = blockIdx.y * 32 + ty;
+            int32_t v = 0;
+            if (r < M) {
+                const int kk = k0 + tx * 4;
+                const int8_t* p = A + (long long)r * lda + kk;
+                uint32_t b = 0;
+                for (int u = 0; u < 4; ++u) if (kk + u < K) b |= ((uint32_t)(uint8_t)p[u]) << (8 * u);
+                v = (int32_t)b;
+            }
+            sa[ty][tx] = v;
+        } else if (tx < 16) {
+            const int t = tx - 8;
+            const int r = blockIdx.x * 32 + ty;
+            int32_t v = 0;
+            if (r < N) {
+                const int kk = k0 + t * 4;
+                const int8_t* p = W + (long long)r * K + kk;
+                uint32_t b = 0;
+                for (int u = 0; u < 4; ++u) if (kk + u < K) b |= ((uint32_t)(uint8_t)p[u]) << (8 * u);
+                v = (int32_t)b;
+            }
+            sb[ty][t] = v;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int t = 0; t < 8; ++t) acc = __dp4a(sa[ty][t], sb[tx][t], acc);
+        __syncthreads();
+    }
+    if (row < M && col < N) C[(long long)row * ldc + col] = acc;
+}
+
+__global__ void gemm_simt_epilogue(const int32_t* __restrict__ acc, GemmArgs a, int mode) {
+    const long long n = (long long)a.M * a.N;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int r = (int)(i / a.N), c = (int)(i % a.N);
+        const int32_t v = acc[i] + (a.bias ? a.bias[c] : 0);
+        if (mode == GM_RAW_I32) { reinterpret_cast<int32_t*>(a.out)[(long long)r * a.out_ld + c] = v; continue; }
+        if (mode == GM_CARRIER) { reinterpret_cast<float*>(a.out)[(long long)r * a.out_ld + c] = __fmul_rn(__int2float_rn(v), a.scale[c]); continue; }
+        const ivit_dyadic_t d = a.me[c];
+        int32_t q = clamp_bits_rt(requant32(v, d.m, d.e), a.mode_bits);
+        if (mode == GM_RQ_I8) { reinterpret_cast<int8_t*>(a.out)[(long long)r * a.out_ld + c] = (int8_t)q; continue; }
+        if (a.two_stage) q = requant32(q, a.me2.m, a.me2.e);
+        long long s = q;
+        if (a.residual) s += requant64((long long)reinterpret_cast<const int16_t*>(a.residual)[(long long)r * a.res_ld + c], a.res_me.m, a.res_me.e);
+        reinterpret_cast<int16_t*>(a.out)[(long long)r * a.out_ld + c] = (int16_t)clamp_i64_bits(s, a.mode_bits);
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// 2D uint8 tensor map: dims {inner = K bytes, outer = rows}, row pitch ld bytes, box {128, box_rows}, SWIZZLE_128B.
+int make_tmap_2d_u8(ivit_ctx* ctx, CUtensorMap* tm, const void* base, uint64_t inner, uint64_t outer, uint64_t ld_bytes,
+                    uint32_t box_inner, uint32_t box_outer) {
+    if (!ctx->encode_tiled) return fail(IVIT_ECUDA, "cuTensorMapEncodeTiled entry point unavailable");
+    cuuint64_t gdim[2] = {inner, outer};
+    cuuint64_t gstride[1] = {ld_bytes};
+    cuuint32_t box[2] = {box_inner, box_outer};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = reinterpret_cast<EncodeTiledFn>(ctx->encode_tiled)(
+        tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(IVIT_ECUDA, "cuTensorMapEncodeTiled failed (CUresult %d): inner=%llu outer=%llu ld=%llu",
+                                       (int)r, (unsigned long long)inner, (unsigned long long)outer, (unsigned long long)ld_bytes);
+    return IVIT_OK;
+}
+
+template <int BN, int STAGES, int MODE>
+static int launch_gemm(ivit_ctx* ctx, const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& ga, cudaStream_t s) {
+    using S = GemmSmem<BN, STAGES>;
+    auto kern = gemm_i8_tcgen05_kernel<BN, STAGES, MODE>;
+    static bool attr_set = false;                     // per instantiation
+    if (!attr_set) {
+        IVIT_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
+        attr_set = true;
+    }
+    const int tiles = ((ga.M + GEMM_BM - 1) / GEMM_BM) * ((ga.N + BN - 1) / BN);
+    const int grid = tiles < ctx->num_sms ? tiles : ctx->num_sms;
+    kern<<<grid, GEMM_THREADS, S::TOTAL, s>>>(ta, tb, ga);
+    IVIT_LAUNCH_OK("gemm_i8_tcgen05_kernel");
+    return IVIT_OK;
+}
+
+template <int MODE>
+static int dispatch_bn(ivit_ctx* ctx, const int8_t* A, int64_t lda, const int8_t* W, const GemmArgs& ga, cudaStream_t s) {
+    // wide tiles when N is large enough to fill them; 128-wide otherwise (less padding waste)
+    const bool wide = (ga.N % 256 == 0) || ga.N >= 1024;
+    CUtensorMap ta, tb;
+    int rc = make_tmap_2d_u8(ctx, &ta, A, (uint64_t)ga.K, (uint64_t)ga.M, (uint64_t)lda, GEMM_BK, GEMM_BM);
+    if (rc) return rc;
+    rc = make_tmap_2d_u8(ctx, &tb, W, (uint64_t)ga.K, (uint64_t)ga.N, (uint64_t)ga.K, GEMM_BK, wide ? 256 : 128);
+    if (rc) return rc;
+    if (wide) return launch_gemm<256, 4, MODE>(ctx, ta, tb, ga, s);
+    return launch_gemm<128, 6, MODE>(ctx, ta, tb, ga, s);
+}
+
+}  // namespace ivit
+
+using namespace ivit;
+
+extern "C" int ivit_gemm_i8(ivit_ctx* ctx, const int8_t* A, int64_t lda, const int8_t* W, int64_t M, int64_t N,
+                            int64_t K, const ivit_gemm_epilogue* epi, void* out, ivit_stream stream) {
+    IVIT_REQUIRE(ctx && A && W && epi && out, "ivit_gemm_i8: null pointer");
+    IVIT_REQUIRE(M > 0 && N > 0 && K > 0 && M < (1LL << 31) && N < (1LL << 31) && K < (1LL << 31), "ivit_gemm_i8: bad shape");
+    IVIT_REQUIRE(K % 16 == 0 && lda % 16 == 0 && lda >= K, "ivit_gemm_i8: K and lda must be multiples of 16 (TMA row pitch), lda >= K");
+    IVIT_REQUIRE(((uintptr_t)A % 16) == 0 && ((uintptr_t)W % 16) == 0, "ivit_gemm_i8: A and W must be 16-byte aligned");
+    IVIT_REQUIRE(epi->out_ld >= N, "ivit_gemm_i8: out_ld < N");
+    GemmArgs ga;
+    ga.M = (int)M; ga.N = (int)N; ga.K = (int)K;
+    ga.mode_bits = epi->bits;
+    ga.bias = epi->bias; ga.me = epi->me;
+    ga.residual = epi->residual; ga.res_ld = epi->res_ld; ga.res_me = epi->res_me;
+    ga.two_stage = epi->two_stage; ga.me2 = epi->me2;
+    ga.scale = epi->scale; ga.out = out; ga.out_ld = epi->out_ld;
+    int mode;
+    switch (epi->mode) {
+        case IVIT_EPI_RAW_I32:
+            IVIT_REQUIRE(epi->out_dtype == IVIT_I32, "ivit_gemm_i8: RAW epilogue writes int32");
+            mode = GM_RAW_I32; break;
+        case IVIT_EPI_CARRIER:
+            IVIT_REQUIRE(epi->out_dtype == IVIT_F32 && epi->scale, "ivit_gemm_i8: CARRIER epilogue needs scale[] and fp32 out");
+            mode = GM_CARRIER; break;
+        case IVIT_EPI_REQUANT:
+            IVIT_REQUIRE(epi->me != nullptr, "ivit_gemm_i8: REQUANT epilogue needs me[N]");
+            if (epi->bits == 8) {
+                IVIT_REQUIRE(epi->out_dtype == IVIT_I8 && !epi->residual && !epi->two_stage,
+                             "ivit_gemm_i8: 8-bit requant writes int8, no residual");
+                mode = GM_RQ_I8;
+            } else {
+                IVIT_REQUIRE(epi->bits == 16 && epi->out_dtype == IVIT_I16, "ivit_gemm_i8: requant bits must be 8 or 16 (int8/int16 out)");
+                IVIT_REQUIRE(!epi->residual || (epi->res_dtype == IVIT_I16 && epi->res_ld >= N), "ivit_gemm_i8: residual must be int16 with res_ld >= N");
+                mode = GM_RQ_I16;
+            }
+            break;
+        default:
+            return fail(IVIT_EINVAL, "ivit_gemm_i8: unknown epilogue mode %d", epi->mode);
+    }
+    cudaStream_t s = st(stream);
+    static const char* impl = getenv("IVIT_GEMM_IMPL");
+    if (impl && impl[0] == 's') {                      // debug cross-check path, see gemm_i8_simt_raw
+        int32_t* tmp = nullptr;
+        IVIT_CUDA_OK(cudaMallocAsync(&tmp, sizeof(int32_t) * (size_t)M * (size_t)N, s));
+        dim3 g((unsigned)((N + 31) / 32), (unsigned)((M + 31) / 32));
+        gemm_i8_simt_raw<<<g, 1024, 0, s>>>(A, lda, W, (int)M, (int)N, (int)K, tmp, N);
+        gemm_simt_epilogue<<<ctx->num_sms * 4, 256, 0, s>>>(tmp, ga, mode);
+        IVIT_LAUNCH_OK("gemm_i8_simt");
+        IVIT_CUDA_OK(cudaFreeAsync(tmp, s));
+        return IVIT_OK;
+    }
+    switch (mode) {
+        case GM_RAW_I32: return dispatch_bn<GM_RAW_I32>(ctx, A, lda, W, ga, s);
+        case GM_CARRIER: return dispatch_bn<GM_CARRIER>(ctx, A, lda, W, ga, s);
+        case GM_RQ_I8:   return dispatch_bn<GM_RQ_I8>(ctx, A, lda, W, ga, s);
+        default:         return dispatch_bn<GM_RQ_I16>(ctx, A, lda, W, ga, s);
+    }
+}

@@ -1,0 +1,46 @@
+// Host-side internals shared by the translation units of libivit_b200.so.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+
+#include "../../include/ivit_b200.h"
+
+struct ivit_ctx {
+    int device = 0;
+    int num_sms = 0;
+    int cc_major = 0, cc_minor = 0;
+    size_t smem_optin = 0;
+    void* encode_tiled = nullptr;   // cuTensorMapEncodeTiled (driver entry point)
+};
+
+namespace ivit {
+int fail(int code, const char* fmt, ...);
+int fail_cuda(cudaError_t e, const char* what);
+inline cudaStream_t st(ivit_stream s) { return reinterpret_cast<cudaStream_t>(s); }
+inline int dtype_size(int dt) {
+    switch (dt) {
+        case IVIT_I8: case IVIT_U8: return 1;
+        case IVIT_I16: return 2;
+        case IVIT_I32: case IVIT_F32: return 4;
+        default: return 0;
+    }
+}
+}  // namespace ivit
+
+#define IVIT_REQUIRE(cond, ...)                                   \
+    do {                                                          \
+        if (!(cond)) return ivit::fail(IVIT_EINVAL, __VA_ARGS__); \
+    } while (0)
+#define IVIT_CUDA_OK(expr)                                        \
+    do {                                                          \
+        cudaError_t _e = (expr);                                  \
+        if (_e != cudaSuccess) return ivit::fail_cuda(_e, #expr); \
+    } while (0)
+#define IVIT_LAUNCH_OK(name)                                       \
+    do {                                                           \
+        cudaError_t _e = cudaPeekAtLastError();                    \
+        if (_e != cudaSuccess) return ivit::fail_cuda(_e, name);   \
+    } while (0)

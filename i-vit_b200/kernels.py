@@ -1,0 +1,205 @@
+"""Tensor-level wrappers over the C ABI (``_lib.py``): allocate outputs, check shapes, launch on
+torch's current stream.  Everything here runs on the GPU through libivit_b200.so; there is no
+torch / CPU fallback for any operator."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import F32, I8, I16, I32, TORCH2IVIT, Dyadic, call, context, ptr
+
+_BITS_DTYPE = {8: torch.int8, 16: torch.int16, 32: torch.int32}
+
+
+def dyadic_host(s_in, s_out):
+    """Host version of batch_frexp on fp64(s_in)/fp64(fp32(s_out)) (reference quant_utils.py:150-175,
+    221-228) for STATIC tables: returns int32 arrays (m, e), m normalised to fit int32, e clamped
+    to [-1, 63] (identical to the device kernel ``ivit_dyadic``)."""
+    s = np.asarray(s_in, dtype=np.float32).reshape(-1).astype(np.float64)
+    r = s / np.float64(np.float32(s_out))
+    mant, ex = np.frexp(r)
+    sc = mant * 2147483648.0
+    m = np.where(sc >= 0, np.floor(sc + 0.5), -np.floor(-sc + 0.5)).astype(np.int64)   # half away from zero
+    e = 31 - ex.astype(np.int64)
+    big = np.abs(m) == 2 ** 31
+    m = np.where(big, m // 2, m)
+    e = np.where(big, e - 1, e)
+    e = np.where(m == 0, 63, e)
+    e = np.clip(e, -1, 63)
+    return m.astype(np.int32), e.astype(np.int32)
+
+
+def dyadic_table(m, e, device) -> torch.Tensor:
+    """Pack (m, e) arrays into the device layout of ``ivit_dyadic_t[]`` (int32 [n, 2])."""
+    t = np.stack([np.asarray(m, np.int32).reshape(-1), np.asarray(e, np.int32).reshape(-1)], axis=1)
+    return torch.from_numpy(np.ascontiguousarray(t)).to(device)
+
+
+def dyadic_device(s_in: torch.Tensor, s_out: torch.Tensor) -> torch.Tensor:
+    """ivit_dyadic: device-side batch_frexp, no host sync.  Returns int32 [n, 2]."""
+    s_in = s_in.reshape(-1).contiguous().float()
+    s_out = s_out.reshape(-1)[:1].contiguous().float()
+    out = torch.empty((s_in.numel(), 2), dtype=torch.int32, device=s_in.device)
+    call("ivit_dyadic", context(s_in.device), ptr(s_in), s_in.numel(), ptr(s_out), ptr(out))
+    return out
+
+
+def quantize_f32(x: torch.Tensor, scale: torch.Tensor, bits: int, per_row: bool = False, out_dtype=None):
+    x = x.contiguous().float()
+    scale = scale.reshape(-1).contiguous().float()
+    out_dtype = out_dtype or _BITS_DTYPE[8 if bits <= 8 else (16 if bits <= 16 else 32)]
+    out = torch.empty(x.shape, dtype=out_dtype, device=x.device)
+    inner = int(np.prod(x.shape[1:])) if per_row else 1
+    call("ivit_quantize_f32", context(x.device), ptr(x), x.numel(), ptr(scale), scale.numel(),
+         max(inner, 1), bits, TORCH2IVIT[out_dtype], ptr(out))
+    return out
+
+
+def carrier_to_int(x: torch.Tensor, s: torch.Tensor, out_dtype=torch.int32):
+    x = x.contiguous().float()
+    s = s.reshape(-1).contiguous().float()
+    cols = x.shape[-1]
+    out = torch.empty(x.shape, dtype=out_dtype, device=x.device)
+    call("ivit_carrier_to_int", context(x.device), ptr(x), x.numel() // cols, cols, ptr(s), s.numel(),
+         TORCH2IVIT[out_dtype], ptr(out))
+    return out
+
+
+def int_to_carrier(q: torch.Tensor, s: torch.Tensor):
+    q = q.contiguous()
+    s = s.reshape(-1).contiguous().float()
+    cols = q.shape[-1]
+    out = torch.empty(q.shape, dtype=torch.float32, device=q.device)
+    call("ivit_int_to_carrier", context(q.device), ptr(q), TORCH2IVIT[q.dtype], q.numel() // cols, cols,
+         ptr(s), s.numel(), ptr(out))
+    return out
+
+
+def requant(z: torch.Tensor, me: torch.Tensor, bits: int, w: torch.Tensor = None, me1: torch.Tensor = None,
+            out_dtype=None):
+    z = z.contiguous()
+    cols = z.shape[-1]
+    rows = z.numel() // cols
+    out_dtype = out_dtype or _BITS_DTYPE[8 if bits <= 8 else (16 if bits <= 16 else 32)]
+    out = torch.empty(z.shape, dtype=out_dtype, device=z.device)
+    if w is not None:
+        w = w.contiguous()
+        w_rows = w.numel() // cols
+        call("ivit_requant", context(z.device), ptr(z), TORCH2IVIT[z.dtype], rows, cols, ptr(me), me.shape[0],
+             ptr(w), TORCH2IVIT[w.dtype], w_rows, ptr(me1), me1.shape[0], bits, TORCH2IVIT[out_dtype], ptr(out))
+    else:
+        call("ivit_requant", context(z.device), ptr(z), TORCH2IVIT[z.dtype], rows, cols, ptr(me), me.shape[0],
+             None, 0, 0, None, 0, bits, TORCH2IVIT[out_dtype], ptr(out))
+    return out
+
+
+def gemm_i8(a: torch.Tensor, w: torch.Tensor, *, bias=None, mode="raw", me=None, bits=8, residual=None,
+            res_me=(0, 63), two_stage=False, me2=(0, 63), scale=None, out=None):
+    """acc = a @ w.T (+bias) on the tcgen05 int8 path, with the fused epilogue selected by ``mode``:
+    'raw' -> int32, 'carrier' -> fp32 acc*scale[n], 'requant' -> int8/int16 (per-channel ``me``)."""
+    assert a.dtype == torch.int8 and w.dtype == torch.int8 and a.dim() == 2 and w.dim() == 2
+    M, K = a.shape
+    N = w.shape[0]
+    assert w.shape[1] == K and a.stride(1) == 1 and w.is_contiguous()
+    epi = _lib.GemmEpilogue()
+    epi.bias = ptr(bias)
+    if mode == "raw":
+        epi.mode, odt = _lib.EPI_RAW_I32, torch.int32
+    elif mode == "carrier":
+        epi.mode, odt = _lib.EPI_CARRIER, torch.float32
+        epi.scale = ptr(scale)
+    elif mode == "requant":
+        epi.mode, odt = _lib.EPI_REQUANT, _BITS_DTYPE[bits]
+        epi.me = ptr(me)
+        epi.bits = bits
+        if residual is not None:
+            assert residual.dtype == torch.int16 and residual.stride(-1) == 1
+            epi.residual = ptr(residual)
+            epi.res_dtype = I16
+            epi.res_ld = residual.stride(0)
+            epi.res_me = Dyadic(int(res_me[0]), int(res_me[1]))
+        epi.two_stage = 1 if two_stage else 0
+        epi.me2 = Dyadic(int(me2[0]), int(me2[1]))
+    else:
+        raise ValueError(mode)
+    if out is None:
+        out = torch.empty((M, N), dtype=odt, device=a.device)
+    assert out.dtype == odt and out.stride(-1) == 1
+    epi.out_dtype = TORCH2IVIT[odt]
+    epi.out_ld = out.stride(0)
+    call("ivit_gemm_i8", context(a.device), ptr(a), a.stride(0), ptr(w), M, N, K, C.byref(epi), ptr(out))
+    return out
+
+
+def bmm_i32(a: torch.Tensor, b: torch.Tensor, trans_b: bool):
+    """Batched raw int32 matmul on strided [batch, M, K] views (last dim contiguous).
+    trans_b: b is [batch, N, K]; else [batch, K, N]."""
+    assert a.dim() == 3 and b.dim() == 3 and a.stride(2) == 1 and b.stride(2) == 1
+    batch, M, K = a.shape
+    N = b.shape[1] if trans_b else b.shape[2]
+    c = torch.empty((batch, M, N), dtype=torch.int32, device=a.device)
+    call("ivit_bmm_i32", context(a.device), ptr(a), TORCH2IVIT[a.dtype], a.stride(1), a.stride(0),
+         ptr(b), b.stride(1), b.stride(0), 1 if trans_b else 0, batch, M, N, K, ptr(c), N, M * N)
+    return c
+
+
+def layernorm(x: torch.Tensor, bias_int: torch.Tensor, me: torch.Tensor = None, bits: int = 8, out_dtype=None):
+    x = x.contiguous()
+    Cc = x.shape[-1]
+    out_dtype = out_dtype or (torch.int32 if me is None else _BITS_DTYPE[bits])
+    out = torch.empty(x.shape, dtype=out_dtype, device=x.device)
+    call("ivit_layernorm", context(x.device), ptr(x), TORCH2IVIT[x.dtype], x.numel() // Cc, Cc, ptr(bias_int),
+         ptr(me), bits, TORCH2IVIT[out_dtype], ptr(out))
+    return out
+
+
+def shiftmax(q: torch.Tensor, x0: int, out_bits: int, n: int = 15, out_dtype=None):
+    q = q.contiguous()
+    cols = q.shape[-1]
+    out_dtype = out_dtype or (torch.int16 if out_bits == 16 else torch.int8)
+    out = torch.empty(q.shape, dtype=out_dtype, device=q.device)
+    call("ivit_shiftmax", context(q.device), ptr(q), TORCH2IVIT[q.dtype], q.numel() // cols, cols, int(x0), n,
+         out_bits, TORCH2IVIT[out_dtype], ptr(out))
+    return out
+
+
+def shiftgelu(q: torch.Tensor, x0: int, me: torch.Tensor = None, bits: int = 8, n: int = 23, out_dtype=None):
+    q = q.contiguous()
+    cols = q.shape[-1]
+    out_dtype = out_dtype or (torch.int16 if me is None else _BITS_DTYPE[bits])
+    out = torch.empty(q.shape, dtype=out_dtype, device=q.device)
+    call("ivit_shiftgelu", context(q.device), ptr(q), TORCH2IVIT[q.dtype], q.numel() // cols, cols, int(x0), n,
+         ptr(me), bits, TORCH2IVIT[out_dtype], ptr(out))
+    return out
+
+
+def attention_i8(qkv: torch.Tensor, n_seq: int, n_tok: int, n_heads: int, head_dim: int, me_s, x0: int,
+                 me_o, p_bits: int = 16, n: int = 15, relbias=None, me_s2=(0, 63), me_b=(0, 63), mask=None,
+                 n_win: int = 0, out=None):
+    assert qkv.dtype == torch.int8 and qkv.is_contiguous()
+    assert qkv.shape == (n_seq * n_tok, 3 * n_heads * head_dim)
+    if out is None:
+        out = torch.empty((n_seq * n_tok, n_heads * head_dim), dtype=torch.int8, device=qkv.device)
+    p = _lib.AttnParams()
+    p.n_seq, p.n_tok, p.n_heads, p.head_dim = n_seq, n_tok, n_heads, head_dim
+    p.me_s = Dyadic(int(me_s[0]), int(me_s[1]))
+    p.x0, p.n, p.p_bits = int(x0), n, p_bits
+    p.me_o = Dyadic(int(me_o[0]), int(me_o[1]))
+    p.relbias = ptr(relbias)
+    p.me_s2 = Dyadic(int(me_s2[0]), int(me_s2[1]))
+    p.me_b = Dyadic(int(me_b[0]), int(me_b[1]))
+    p.mask = ptr(mask)
+    p.n_win = n_win
+    call("ivit_attention_i8", context(qkv.device), ptr(qkv), C.byref(p), ptr(out))
+    return out
+
+
+def patchify_i8(x: torch.Tensor, patch: int):
+    assert x.dtype == torch.int8 and x.dim() == 4 and x.is_contiguous()
+    B, Cin, H, W = x.shape
+    out = torch.empty((B * (H // patch) * (W // patch), Cin * patch * patch), dtype=torch.int8, device=x.device)
+    call("ivit_patchify_i8", context(x.device), ptr(x), B, Cin, H, W, patch, ptr(out))
+    return out

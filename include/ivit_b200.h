@@ -1,0 +1,215 @@
+/*
+ * ivit_b200.h -- C ABI of the B200 (sm_100a) integer-only ViT operator library.
+ *
+ * This is the drop-in boundary for the hot path of zkkli/I-ViT: the forward of the
+ * seven operator classes exported by the reference's
+ *     models/quantization_utils/__init__.py:1
+ * (QuantLinear, QuantAct, QuantConv2d, QuantMatMul, IntLayerNorm, IntSoftmax, IntGELU)
+ * plus the primitives of models/quantization_utils/quant_utils.py they call.
+ * Each entry point below names the reference function it replaces (file:line, relative
+ * to the reference checkout).  The reference is pure Python/PyTorch, so the "FFI" a
+ * maintainer would add is a ctypes stub (shown in INTEGRATION.md; the one this repo
+ * ships is i-vit_b200/_lib.py).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless marked HOST
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*), takes the
+ *     context created by ivit_create(), returns 0 on success or a negative IVIT_E* code;
+ *     ivit_last_error() returns a thread-local message.  No exceptions cross the boundary.
+ *   - integer tensors are row-major [rows, cols] in their narrowest storage type
+ *     (IVIT_I8 / IVIT_I16 / IVIT_I32); "carrier" tensors are the reference's fp32
+ *     integer*scale representation (IVIT_F32)
+ *   - dyadic multipliers are ivit_dyadic_t {m, e}:  out = RNE(z * m / 2^e)
+ *     with m int32 (|m| in [2^30, 2^31)) and e in [-1, 63]; length 1 (scalar) or cols
+ *   - a thread may use one context at a time (thread-compatible, not thread-safe)
+ */
+#ifndef IVIT_B200_H
+#define IVIT_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define IVIT_API
+#else
+#define IVIT_API __attribute__((visibility("default")))
+#endif
+
+typedef struct ivit_ctx ivit_ctx;
+typedef void* ivit_stream;
+
+typedef struct ivit_dyadic_t {
+    int32_t m;
+    int32_t e;
+} ivit_dyadic_t;
+
+enum { IVIT_I8 = 0, IVIT_I16 = 1, IVIT_I32 = 2, IVIT_F32 = 3, IVIT_U8 = 4 };
+
+enum {
+    IVIT_OK = 0,
+    IVIT_EINVAL = -1,   /* bad argument (shape / dtype / alignment / null pointer)           */
+    IVIT_ECUDA = -2,    /* CUDA runtime / driver error (message has the CUDA error string)    */
+    IVIT_ENOTSUP = -3,  /* valid in the reference but outside this library's supported domain */
+    IVIT_ENODEV = -4    /* no sm_100 device                                                   */
+};
+
+/* ---- library / context ----------------------------------------------------------- */
+IVIT_API int ivit_version(void);
+IVIT_API const char* ivit_last_error(void);
+/* Creates a context on CUDA device `device` (must be compute capability 10.x). */
+IVIT_API int ivit_create(int device, ivit_ctx** out);
+IVIT_API int ivit_destroy(ivit_ctx* ctx);
+IVIT_API int ivit_num_sms(ivit_ctx* ctx);
+
+/* ---- quant_utils.py primitives ---------------------------------------------------- */
+
+/* batch_frexp (quant_utils.py:150-175) of fp64(s_in[i]) / fp64(fp32(*s_out))
+ * (the ratio formed in fixedpoint_mul.forward, quant_utils.py:221-228), on the device,
+ * no host round trip: m = round_half_away(mant * 2^31), e = 31 - exp, normalised so
+ * that m fits int32, e clamped to [-1, 63].  s_in: n floats; s_out: 1 float (device). */
+IVIT_API int ivit_dyadic(ivit_ctx*, const float* s_in, int n, const float* s_out,
+                         ivit_dyadic_t* out, ivit_stream stream);
+
+/* SymmetricQuantFunction.forward + linear_quantize (quant_utils.py:12-48, 77-96):
+ * q = clamp(RNE(fp32(1/s) * x), -2^(b-1), 2^(b-1)-1); out_dtype IVIT_I8 / IVIT_I16 / IVIT_I32.
+ * scale: device, ns entries; element i uses scale[(i / inner) % ns] (ns = 1: scalar;
+ * per-row weight scales: ns = rows, inner = row length). */
+IVIT_API int ivit_quantize_f32(ivit_ctx*, const float* x, int64_t n, const float* scale,
+                               int64_t ns, int64_t inner, int bits, int out_dtype, void* out,
+                               ivit_stream stream);
+
+/* Carrier -> integer: z = RNE(x / s[c]) (first line of fixedpoint_mul.forward,
+ * quant_utils.py:220; also the x / scaling_factor of quant_modules.py:94,224-225,359,426,484).
+ * x: [rows, cols] fp32; s: 1 or cols entries; saturates to out_dtype. */
+IVIT_API int ivit_carrier_to_int(ivit_ctx*, const float* x, int64_t rows, int cols,
+                                 const float* s, int s_len, int out_dtype, void* out,
+                                 ivit_stream stream);
+
+/* Integer -> carrier: x = float(q) * s[c] (the `* scaling_factor` on every operator's
+ * return, e.g. quant_modules.py:96-97,206,228,384,445,497). */
+IVIT_API int ivit_int_to_carrier(ivit_ctx*, const void* q, int q_dtype, int64_t rows, int cols,
+                                 const float* s, int s_len, float* out, ivit_stream stream);
+
+/* fixedpoint_mul.forward (quant_utils.py:192-253) on integers:
+ *   out = clamp( RNE(z*m/2^e) [+ RNE(w*m1/2^e1)], -2^(bits-1), 2^(bits-1)-1 )
+ * z: [rows, cols] (z_dtype); me: me_len (1|cols) entries; optional residual w
+ * (w_dtype, [w_rows, cols] with w_rows == rows or 1) with me1 (me1_len 1|cols).
+ * bits in {4, 8, 16, 32}; out_dtype must hold `bits`. */
+IVIT_API int ivit_requant(ivit_ctx*, const void* z, int z_dtype, int64_t rows, int cols,
+                          const ivit_dyadic_t* me, int me_len,
+                          const void* w, int w_dtype, int64_t w_rows,
+                          const ivit_dyadic_t* me1, int me1_len,
+                          int bits, int out_dtype, void* out, ivit_stream stream);
+
+/* ---- integer contractions --------------------------------------------------------- */
+
+/* Epilogue selector for ivit_gemm_i8. */
+enum {
+    IVIT_EPI_RAW_I32 = 0,   /* out int32 = acc + bias                                         */
+    IVIT_EPI_REQUANT = 1,   /* out = clamp(RNE((acc+bias)*m[n]/2^e[n]) [+ residual])  i8/i16 */
+    IVIT_EPI_CARRIER = 2    /* out fp32 = float(acc + bias) * scale[n]                        */
+};
+
+typedef struct ivit_gemm_epilogue {
+    int mode;                      /* IVIT_EPI_*                                              */
+    const int32_t* bias;           /* [N] or NULL                                             */
+    const ivit_dyadic_t* me;       /* [N] (per output channel) for IVIT_EPI_REQUANT           */
+    int bits;                      /* 8 or 16 for IVIT_EPI_REQUANT                            */
+    const void* residual;          /* optional [M, N] residual (res_dtype), IVIT_EPI_REQUANT  */
+    int res_dtype;
+    int64_t res_ld;                /* leading dimension (elements) of residual                */
+    ivit_dyadic_t res_me;          /* scalar dyadic of the residual                           */
+    int two_stage;                 /* != 0: q1 = clamp(RNE(z*me[n]), bits); out = clamp(RNE(q1*me2) + RNE(res*res_me), bits)
+                                      (a per-channel QuantAct followed by a residual QuantAct, vit_quant.py:85,135) */
+    ivit_dyadic_t me2;             /* scalar dyadic of the second stage                       */
+    const float* scale;            /* [N] for IVIT_EPI_CARRIER                                */
+    int out_dtype;                 /* IVIT_I8 / IVIT_I16 / IVIT_I32 / IVIT_F32                */
+    int64_t out_ld;                /* leading dimension (elements) of out, >= N               */
+} ivit_gemm_epilogue;
+
+/* QuantLinear.forward contraction (quant_modules.py:93-97), also QuantConv2d on unfolded
+ * patches (quant_modules.py:325-330):   acc[i,j] = sum_k A[i,k] * W[j,k]
+ * A: int8 [M, K] (lda elements between rows), W: int8 [N, K] (row-major, the
+ * `weight_integer` buffer), tcgen05 kind::i8 tensor-core path.  K % 16 == 0, lda % 16 == 0. */
+IVIT_API int ivit_gemm_i8(ivit_ctx*, const int8_t* A, int64_t lda, const int8_t* W,
+                          int64_t M, int64_t N, int64_t K, const ivit_gemm_epilogue* epi,
+                          void* out, ivit_stream stream);
+
+/* QuantMatMul.forward contraction (quant_modules.py:223-228), batched, raw int32 result:
+ *   C[b] = A[b] (a_dtype, [M,K], row stride lda, batch stride sa) x B[b]
+ * trans_b != 0: B[b] is [N,K] row-major (ldb) and C = A B^T; else B[b] is [K,N] (ldb).
+ * a_dtype IVIT_I8 or IVIT_I16 (DeiT's 16-bit softmax output, vit_quant.py:54,79);
+ * b_dtype IVIT_I8.  General strided form so that q/k/v views of the qkv buffer
+ * (vit_quant.py:63-71) need no copies. */
+IVIT_API int ivit_bmm_i32(ivit_ctx*, const void* A, int a_dtype, int64_t lda, int64_t sa,
+                          const int8_t* B, int64_t ldb, int64_t sb, int trans_b,
+                          int64_t batch, int M, int N, int K,
+                          int32_t* C, int64_t ldc, int64_t sc, ivit_stream stream);
+
+/* ---- row operators ----------------------------------------------------------------- */
+
+/* IntLayerNorm.forward (quant_modules.py:353-386), integer part:
+ *   mu = RNE(sum/C); y = q - mu; V = sum y^2; 10-step integer sqrt from 2^16;
+ *   F = floor((2^31-1)/std); out = floor(y*F/2) + bias_int[c]
+ * If `me` != NULL the following QuantAct (per-channel dyadic, `bits`) is fused:
+ *   out = clamp(RNE(out * m[c] / 2^e[c])).   x: [rows, C] (IVIT_I8/I16/I32). */
+IVIT_API int ivit_layernorm(ivit_ctx*, const void* x, int x_dtype, int64_t rows, int C,
+                            const int32_t* bias_int, const ivit_dyadic_t* me, int bits,
+                            int out_dtype, void* out, ivit_stream stream);
+
+/* IntSoftmax.forward (quant_modules.py:469-497), Shiftmax over the last dim.
+ * q: [rows, cols] IVIT_I8 (or IVIT_I32 with values in int8 range); x0 = floor(-1/s) (host,
+ * fp32 arithmetic), n = 15, out_bits 16 (out IVIT_I16) or 8 (out IVIT_I8). */
+IVIT_API int ivit_shiftmax(ivit_ctx*, const void* q, int q_dtype, int64_t rows, int cols,
+                           int32_t x0, int n, int out_bits, int out_dtype, void* out,
+                           ivit_stream stream);
+
+/* IntGELU.forward (quant_modules.py:410-445), ShiftGELU over the last dim (row max).
+ * q: [rows, cols] IVIT_I8; x0 = floor(-1/fp32(s*1.702)); n = 23; sigmoid bits 8.
+ * out = q * sigma (IVIT_I16 / IVIT_I32); if `me` != NULL the following scalar QuantAct is
+ * fused: out = clamp(RNE(q*sigma*m/2^e), bits) (out IVIT_I8). */
+IVIT_API int ivit_shiftgelu(ivit_ctx*, const void* q, int q_dtype, int64_t rows, int cols,
+                            int32_t x0, int n, const ivit_dyadic_t* me, int bits,
+                            int out_dtype, void* out, ivit_stream stream);
+
+/* Fused integer attention for one QuantLinear(qkv) output (vit_quant.py:63-83;
+ * swin_quant.py:128-164):
+ *   S = Q K^T -> qact_attn1 (scalar me_s, 8 bit) [-> + rel-pos bias (qact2) -> + mask]
+ *     -> Shiftmax (x0, n, p_bits) -> P V -> qact (scalar me_o, 8 bit)
+ * qkv: int8 [tokens_total, 3*H*D], token t of sequence b at row b*n_tok + t, column
+ * which*H*D + h*D + d.  out: int8 [tokens_total, H*D].  Scores never leave the chip.
+ * relbias: optional int8 [H, n_tok, n_tok] already requantised operand of qact2 with
+ * me_b (scalar) for the bias and me_s2 for the scores (swin_quant.py:149);
+ * mask: optional int32 [n_win, n_tok, n_tok] integer mask addend (RNE(-100/s), App. A.5),
+ * window index = b % n_win. */
+typedef struct ivit_attn_params {
+    int n_seq, n_tok, n_heads, head_dim;
+    ivit_dyadic_t me_s;        /* scores requant (qact_attn1)                                */
+    int32_t x0;                /* floor(-1/s_attn)                                           */
+    int n;                     /* 15                                                         */
+    int p_bits;                /* 16 (DeiT) or 8 (Swin)                                      */
+    ivit_dyadic_t me_o;        /* P.V requant (attn.qact2 / qact3)                           */
+    const int8_t* relbias;     /* optional                                                   */
+    ivit_dyadic_t me_s2, me_b; /* qact2(scores, bias)                                        */
+    const int32_t* mask;       /* optional                                                   */
+    int n_win;
+} ivit_attn_params;
+
+IVIT_API int ivit_attention_i8(ivit_ctx*, const int8_t* qkv, const ivit_attn_params* p,
+                               int8_t* out, ivit_stream stream);
+
+/* ---- data movement used by the DeiT stem/tail (graph glue, vit_quant.py:254-276) ---- */
+
+/* Unfold non-overlapping p x p patches of an int8 NCHW image into GEMM rows
+ * (QuantConv2d with kernel == stride, layers_quant.py:172-177,190-191):
+ * out[(b*Hp + i)*Wp + j, (c*p + u)*p + v] = x[b, c, i*p+u, j*p+v]. */
+IVIT_API int ivit_patchify_i8(ivit_ctx*, const int8_t* x, int B, int Cin, int H, int W, int p,
+                              int8_t* out, ivit_stream stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IVIT_B200_H */

@@ -1,0 +1,350 @@
+"""GPU parity tests: every entry point of the C ABI (include/ivit_b200.h) against the CPU oracle
+(oracle/, pinned to the reference by tests/test_oracle_golden.py) on identical seeded inputs.
+Bit-exact: all of this is integer arithmetic (the two fp32 outputs, carrier and logits, are a
+single IEEE fp32 multiply and must match bitwise too)."""
+import numpy as np
+import pytest
+import torch
+
+import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def K():
+    import ivit_b200.kernels as k
+    return k
+
+
+def dev(a, dtype=None):
+    t = torch.from_numpy(np.ascontiguousarray(a))
+    if dtype is not None:
+        t = t.to(dtype)
+    return t.cuda()
+
+
+def rand_me(rng, n, e_lo=32, e_hi=44, neg_every=0):
+    m = rng.integers(2 ** 30, 2 ** 31, n).astype(np.int64)
+    if neg_every:
+        m[::neg_every] *= -1
+    e = rng.integers(e_lo, e_hi + 1, n).astype(np.int64)
+    return m, e
+
+
+def me_dev(K, m, e):
+    return K.dyadic_table(m, e, "cuda")
+
+
+def assert_equal(got, want, what):
+    got = got.cpu().numpy().astype(np.int64) if isinstance(got, torch.Tensor) else np.asarray(got)
+    want = np.asarray(want).astype(np.int64)
+    if got.shape != want.shape:
+        got = got.reshape(want.shape)
+    bad = np.argwhere(got != want)
+    if len(bad):
+        i = tuple(bad[0])
+        pytest.fail("%s: %d / %d mismatches, first at %s: got %d want %d" %
+                    (what, len(bad), want.size, i, got[i], want[i]))
+
+
+# ------------------------------------------------------------------------------- primitives
+def test_dyadic_device_and_host(K, kat):
+    m_ref, e_ref = O.dyadic(kat["frexp_s_in"], kat["frexp_s_out"])
+    big = np.abs(m_ref) == 2 ** 31
+    m_n = np.where(big, m_ref // 2, m_ref)
+    e_n = np.clip(np.where(big, e_ref - 1, e_ref), -1, 63)
+    mh, eh = K.dyadic_host(kat["frexp_s_in"], kat["frexp_s_out"])
+    assert np.array_equal(mh, m_n) and np.array_equal(eh, e_n)
+    t = K.dyadic_device(dev(kat["frexp_s_in"]), dev(np.array([kat["frexp_s_out"]], np.float32))).cpu().numpy()
+    assert np.array_equal(t[:, 0], m_n) and np.array_equal(t[:, 1], e_n)
+
+
+@pytest.mark.parametrize("bits", [8, 16])
+def test_quantize_f32(K, kat, bits):
+    lo, hi = kat["qin%d_range" % bits]
+    s = O.sym_scale(bits, lo, hi)
+    q = K.quantize_f32(dev(kat["qin%d_x" % bits]), dev(np.array([s], np.float32)), bits)
+    assert_equal(q, kat["qin%d_q" % bits], "quantize_f32 b%d" % bits)
+    # large vectorised case
+    rng = np.random.default_rng(bits)
+    x = (rng.standard_normal((3, 3, 32, 32)) * 2).astype(np.float32)
+    s2 = np.float32(0.0173)
+    assert_equal(K.quantize_f32(dev(x), dev(np.array([s2])), 8), O.quantize_f32(x, s2, 8), "quantize_f32 vec")
+
+
+def test_quantize_weights_per_row(K, kat):
+    w = kat["lin_w"]
+    s_w = np.array([O.sym_scale(8, r.min(), r.max()) for r in w], np.float32)
+    q = K.quantize_f32(dev(w), dev(s_w), 8, per_row=True)
+    assert_equal(q, kat["lin_wq"], "weight quantisation")
+    s_b = (s_w * np.float32(kat["lin_s_a"])).astype(np.float32)
+    qb = K.quantize_f32(dev(kat["lin_b"]), dev(s_b), 32, per_row=True)
+    assert_equal(qb, kat["lin_bq"], "bias quantisation")
+
+
+def test_carrier_roundtrip(K):
+    rng = np.random.default_rng(3)
+    q = rng.integers(-30000, 30000, (37, 48)).astype(np.int32)
+    s = rng.uniform(1e-4, 1e-2, 48).astype(np.float32)
+    x = K.int_to_carrier(dev(q), dev(s))
+    assert np.array_equal(x.cpu().numpy(), (q.astype(np.float32) * s[None, :]).astype(np.float32))
+    assert_equal(K.carrier_to_int(x, dev(s), torch.int32), q, "carrier roundtrip per-channel")
+    x1 = K.int_to_carrier(dev(q.astype(np.int16)), dev(s[:1]))
+    assert_equal(K.carrier_to_int(x1, dev(s[:1]), torch.int16), q, "carrier roundtrip scalar")
+
+
+def test_requant_kat(K, kat):
+    for ci, bits, perch, resid in kat["rq_cases"]:
+        z, s_in, sf = kat["rq%d_z" % ci], kat["rq%d_s_in" % ci], kat["rq%d_sf" % ci].reshape(-1)[0]
+        m, e = K.dyadic_host(s_in, sf)
+        zt = dev(z.astype(np.int32))
+        if resid:
+            m1, e1 = K.dyadic_host(kat["rq%d_s_id" % ci], sf)
+            got = K.requant(zt, me_dev(K, m, e), int(bits), dev(kat["rq%d_w" % ci].astype(np.int16)), me_dev(K, m1, e1))
+        else:
+            got = K.requant(zt, me_dev(K, m, e), int(bits))
+        assert_equal(got, kat["rq%d_q" % ci], "requant KAT case %d" % ci)
+
+
+def test_requant_random_edges(K):
+    rng = np.random.default_rng(11)
+    rows, cols = 64, 96
+    z = rng.integers(-2 ** 31, 2 ** 31, (rows, cols)).astype(np.int64)
+    z[0, :8] = [0, 1, -1, 2 ** 31 - 1, -2 ** 31, 2 ** 30, -2 ** 30, 5]
+    m, e = rand_me(rng, cols, e_lo=-1, e_hi=63, neg_every=3)
+    m[:4] = [2 ** 30, -2 ** 30, 2 ** 31 - 1, -2 ** 31]
+    for bits, dt in [(8, np.int8), (16, np.int16), (32, np.int32)]:
+        want = O.requant(z, m, e, bits)
+        got = K.requant(dev(z.astype(np.int32)), me_dev(K, m, e), bits)
+        assert_equal(got, want, "requant edges b%d" % bits)
+    # broadcast residual row (pos_embed, vit_quant.py:265)
+    w = rng.integers(-32768, 32768, (1, cols)).astype(np.int64)
+    m1, e1 = rand_me(rng, 1, 28, 36)
+    z16 = rng.integers(-32768, 32768, (rows, cols)).astype(np.int64)
+    ms, es = rand_me(rng, 1, 28, 36)
+    want = O.requant(z16, ms, es, 16, w, m1, e1)
+    got = K.requant(dev(z16.astype(np.int16)), me_dev(K, ms, es), 16, dev(w.astype(np.int16)), me_dev(K, m1, e1))
+    assert_equal(got, want, "requant broadcast residual")
+
+
+# ------------------------------------------------------------------------------- row operators
+@pytest.mark.parametrize("tag", ["ln_a", "ln_b", "ln_c", "ln_d"])
+def test_layernorm_kat(K, kat, tag):
+    q, bq = kat[tag + "_q"], kat[tag + "_bq"]
+    got = K.layernorm(dev(q.astype(np.int16)), dev(bq.astype(np.int32)))
+    assert_equal(got, kat[tag + "_o"], "layernorm " + tag)
+    # fused per-channel QuantAct (8 bit), negative multipliers where gamma < 0
+    sf = kat[tag + "_sf"].reshape(-1)
+    s_out = np.float32(np.abs(kat[tag + "_o"].astype(np.float64) * sf.astype(np.float64)).max() / 127.0)
+    m, e = K.dyadic_host(sf, s_out)
+    want = O.requant(kat[tag + "_o"], m, e, 8)
+    got = K.layernorm(dev(q.astype(np.int16)), dev(bq.astype(np.int32)), me_dev(K, m, e), 8)
+    assert_equal(got, want, "layernorm+qact " + tag)
+
+
+def test_layernorm_random_widths(K):
+    rng = np.random.default_rng(5)
+    for C, dt, mag in [(96, np.int8, 127), (192, np.int16, 20000), (384, np.int16, 32767), (768, np.int16, 9000),
+                       (1536, np.int8, 127), (100, np.int16, 500)]:
+        q = rng.integers(-mag, mag + 1, (67, C)).astype(np.int64)
+        bq = rng.integers(-2 ** 24, 2 ** 24, C).astype(np.int64)
+        want = O.layernorm(q, bq)
+        got = K.layernorm(dev(q.astype(dt)), dev(bq.astype(np.int32)))
+        assert_equal(got, want, "layernorm C=%d" % C)
+
+
+@pytest.mark.parametrize("tag,bits", [("sm16", 16), ("sm8", 8), ("sm16b", 16), ("sm8b", 8)])
+def test_shiftmax_kat(K, kat, tag, bits):
+    x0 = O.x0_of(kat[tag + "_s"])
+    got = K.shiftmax(dev(kat[tag + "_q"].astype(np.int8)), x0, bits)
+    assert_equal(got, kat[tag + "_p"], "shiftmax " + tag)
+
+
+def test_shiftmax_random(K):
+    rng = np.random.default_rng(6)
+    for cols, s, bits in [(197, 0.02, 16), (49, 0.004, 8), (197, 0.11, 16), (64, 0.0007, 16), (300, 0.05, 8)]:
+        q = rng.integers(-128, 128, (50, cols)).astype(np.int64)
+        x0 = O.x0_of(np.float32(s))
+        assert_equal(K.shiftmax(dev(q.astype(np.int8)), x0, bits), O.shiftmax(q, x0, bits), "shiftmax cols=%d s=%g" % (cols, s))
+
+
+@pytest.mark.parametrize("tag", ["gelu_a", "gelu_b", "gelu_c"])
+def test_shiftgelu_kat(K, kat, tag):
+    s = kat[tag + "_s"]
+    x0 = O.x0_of(O.gelu_sig_scale(s))
+    got = K.shiftgelu(dev(kat[tag + "_q"].astype(np.int8)), x0)
+    assert_equal(got, kat[tag + "_o"], "shiftgelu " + tag)
+    # fused scalar QuantAct (mlp.qact1, layers_quant.py:148)
+    s_in = np.float32(s) * np.float32(1 / 128)
+    s_out = np.float32(np.abs(kat[tag + "_o"]).max() * float(s_in) / 127.0)
+    m, e = K.dyadic_host(np.array([s_in], np.float32), s_out)
+    want = O.requant(kat[tag + "_o"], m, e, 8)
+    got = K.shiftgelu(dev(kat[tag + "_q"].astype(np.int8)), x0, me_dev(K, m, e), 8)
+    assert_equal(got, want, "shiftgelu+qact " + tag)
+
+
+def test_shiftgelu_random(K):
+    rng = np.random.default_rng(8)
+    for cols, s in [(768, 0.03), (3072, 0.045), (384, 0.012), (1536, 0.07)]:
+        q = rng.integers(-128, 128, (33, cols)).astype(np.int64)
+        q[0] = rng.integers(-128, -1, cols)
+        x0 = O.x0_of(O.gelu_sig_scale(np.float32(s)))
+        assert_equal(K.shiftgelu(dev(q.astype(np.int8)), x0, out_dtype=torch.int32), O.shiftgelu(q, x0),
+                     "shiftgelu cols=%d" % cols)
+
+
+def test_unsupported_scales_fail_loudly(K):
+    from ivit_b200._lib import IvitError
+    q = torch.zeros((4, 64), dtype=torch.int8, device="cuda")
+    with pytest.raises(IvitError, match="x0"):
+        K.shiftgelu(q, -3)
+    with pytest.raises(IvitError, match="bits"):
+        K.requant(q.int(), me_dev(K, [2 ** 30], [31]), 7, out_dtype=torch.int32)
+
+
+def test_patchify(K):
+    rng = np.random.default_rng(9)
+    x = rng.integers(-128, 128, (3, 3, 32, 48)).astype(np.int8)
+    p = 16
+    got = K.patchify_i8(dev(x), p).cpu().numpy()
+    B, Cin, H, W = x.shape
+    want = x.reshape(B, Cin, H // p, p, W // p, p).transpose(0, 2, 4, 1, 3, 5).reshape(-1, Cin * p * p)
+    assert np.array_equal(got, want)
+
+
+# ------------------------------------------------------------------------------- GEMM (tcgen05)
+GEMM_SHAPES = [(128, 128, 128), (128, 256, 128), (256, 128, 256), (128, 256, 768), (197, 192, 192),
+               (394, 576, 192), (300, 768, 768), (130, 1000, 768), (2, 1000, 192), (640, 3072, 768),
+               (513, 768, 3072), (100, 96, 48), (1300, 2304, 768)]
+
+
+def gemm_inputs(rng, M, N, K_):
+    a = rng.integers(-128, 128, (M, K_)).astype(np.int8)
+    w = rng.integers(-128, 128, (N, K_)).astype(np.int8)
+    b = rng.integers(-2 ** 20, 2 ** 20, N).astype(np.int32)
+    return a, w, b
+
+
+def ref_acc(a, w, b):
+    return a.astype(np.int32) @ w.astype(np.int32).T + b.astype(np.int32)[None, :]
+
+
+@pytest.mark.parametrize("M,N,K_", GEMM_SHAPES)
+def test_gemm_raw_i32(K, M, N, K_):
+    rng = np.random.default_rng(M * 7 + N * 3 + K_)
+    a, w, b = gemm_inputs(rng, M, N, K_)
+    got = K.gemm_i8(dev(a), dev(w), bias=dev(b), mode="raw")
+    assert_equal(got, ref_acc(a, w, b), "gemm raw %dx%dx%d" % (M, N, K_))
+
+
+def test_gemm_matches_oracle_kat(K, kat):
+    # reference QuantLinear known answer (K=48 is not a multiple of 128: TMA zero fill)
+    a, wq, bq = kat["lin_a"], kat["lin_wq"], kat["lin_bq"]
+    got = K.gemm_i8(dev(a.astype(np.int8)), dev(wq.astype(np.int8)), bias=dev(bq.astype(np.int32)), mode="raw")
+    assert_equal(got, kat["lin_acc"], "QuantLinear KAT")
+    sf = kat["lin_sf"].reshape(-1)
+    got = K.gemm_i8(dev(a.astype(np.int8)), dev(wq.astype(np.int8)), bias=dev(bq.astype(np.int32)),
+                    mode="carrier", scale=dev(sf))
+    want = (kat["lin_acc"].astype(np.float32) * sf[None, :]).astype(np.float32)
+    assert np.array_equal(got.cpu().numpy(), want)
+
+
+@pytest.mark.parametrize("M,N,K_", [(197, 192, 192), (300, 768, 768), (256, 3072, 768), (130, 1000, 768)])
+@pytest.mark.parametrize("e_lo,e_hi", [(33, 44), (20, 50)])
+def test_gemm_requant_i8(K, M, N, K_, e_lo, e_hi):
+    rng = np.random.default_rng(M + N + K_ + e_lo)
+    a, w, b = gemm_inputs(rng, M, N, K_)
+    m, e = rand_me(rng, N, e_lo, e_hi, neg_every=5)
+    m[:3] = [2 ** 30, -2 ** 30, 2 ** 31 - 1]           # power-of-two multipliers produce exact ties
+    want = O.requant(ref_acc(a, w, b), m, e, 8)
+    got = K.gemm_i8(dev(a), dev(w), bias=dev(b), mode="requant", me=me_dev(K, m, e), bits=8)
+    assert_equal(got, want, "gemm rq8 %dx%dx%d e[%d,%d]" % (M, N, K_, e_lo, e_hi))
+
+
+@pytest.mark.parametrize("M,N,K_", [(197, 192, 768), (300, 768, 3072), (128, 256, 128)])
+@pytest.mark.parametrize("variant", ["plain", "residual", "two_stage"])
+def test_gemm_requant_i16(K, M, N, K_, variant):
+    rng = np.random.default_rng(M + N + K_ + len(variant))
+    a, w, b = gemm_inputs(rng, M, N, K_)
+    m, e = rand_me(rng, N, 33, 40, neg_every=4)
+    acc = ref_acc(a, w, b)
+    kw = {}
+    if variant == "plain":
+        want = O.requant(acc, m, e, 16)
+    else:
+        res = rng.integers(-32768, 32768, (M, N)).astype(np.int16)
+        m1, e1 = rand_me(rng, 1, 30, 33)
+        kw = dict(residual=dev(res), res_me=(m1[0], e1[0]))
+        if variant == "residual":
+            want = O.requant(acc, m, e, 16, res, m1, e1)
+        else:
+            m2, e2 = rand_me(rng, 1, 30, 33)
+            q1 = O.requant(acc, m, e, 16)
+            want = O.requant(q1, m2, e2, 16, res, m1, e1)
+            kw.update(two_stage=True, me2=(m2[0], e2[0]))
+    got = K.gemm_i8(dev(a), dev(w), bias=dev(b), mode="requant", me=me_dev(K, m, e), bits=16, **kw)
+    assert_equal(got, want, "gemm rq16 %s %dx%dx%d" % (variant, M, N, K_))
+
+
+def test_gemm_strided_a_and_out(K):
+    # A as a column slice of a wider buffer (lda > K), out into a wider buffer
+    rng = np.random.default_rng(77)
+    M, N, K_ = 200, 256, 256
+    big = rng.integers(-128, 128, (M, 512)).astype(np.int8)
+    w = rng.integers(-128, 128, (N, K_)).astype(np.int8)
+    A = dev(big)[:, 256:512]
+    out = torch.zeros((M, 512), dtype=torch.int32, device="cuda")
+    K.gemm_i8(A, dev(w), mode="raw", out=out[:, 128:128 + N])
+    want = big[:, 256:].astype(np.int32) @ w.astype(np.int32).T
+    assert_equal(out[:, 128:128 + N], want, "strided gemm")
+    assert int(out[:, :128].abs().sum()) == 0 and int(out[:, 128 + N:].abs().sum()) == 0
+
+
+# ------------------------------------------------------------------------------- batched matmul
+def test_bmm_kat(K, kat):
+    A, B = kat["mm_A"], kat["mm_B"]                    # [2,3,11,16] x [2,3,16,11]
+    a = dev(A.astype(np.int8)).reshape(6, 11, 16)
+    b = dev(B.astype(np.int8)).reshape(6, 16, 11)
+    assert_equal(K.bmm_i32(a, b, trans_b=False), kat["mm_acc"].reshape(6, 11, 11), "bmm QK KAT")
+    bt = b.transpose(1, 2).contiguous()
+    assert_equal(K.bmm_i32(a, bt, trans_b=True), kat["mm_acc"].reshape(6, 11, 11), "bmm QK^T KAT")
+    p = dev(kat["mm2_P"].astype(np.int16)).reshape(6, 11, 11)
+    v = dev(kat["mm2_V"].astype(np.int8)).reshape(6, 11, 16)
+    assert_equal(K.bmm_i32(p, v, trans_b=False), kat["mm2_acc"].reshape(6, 11, 16), "bmm PV KAT (int16 P)")
+
+
+# ------------------------------------------------------------------------------- fused attention
+def oracle_attention(qkv, n_seq, n_tok, H, D, me_s, x0, me_o, p_bits):
+    Cc = H * D
+    out = np.zeros((n_seq * n_tok, Cc), np.int64)
+    for b in range(n_seq):
+        blk = qkv[b * n_tok:(b + 1) * n_tok].astype(np.int64)
+        for h in range(H):
+            q = blk[:, h * D:(h + 1) * D]
+            k = blk[:, Cc + h * D:Cc + (h + 1) * D]
+            v = blk[:, 2 * Cc + h * D:2 * Cc + (h + 1) * D]
+            s = O.requant(q @ k.T, [me_s[0]], [me_s[1]], 8)
+            p = O.shiftmax(s, x0, p_bits)
+            o = O.requant(p @ v, [me_o[0]], [me_o[1]], 8)
+            out[b * n_tok:(b + 1) * n_tok, h * D:(h + 1) * D] = o
+    return out
+
+
+@pytest.mark.parametrize("n_seq,n_tok,H,D,p_bits", [(2, 197, 3, 64, 16), (3, 49, 3, 32, 8), (1, 197, 12, 64, 16),
+                                                    (2, 64, 2, 64, 16), (2, 50, 4, 32, 16), (1, 17, 1, 64, 8)])
+def test_attention(K, n_seq, n_tok, H, D, p_bits):
+    rng = np.random.default_rng(n_tok * 31 + H)
+    qkv = rng.integers(-128, 128, (n_seq * n_tok, 3 * H * D)).astype(np.int8)
+    # make some rows strongly peaked so the softmax is not flat
+    qkv[::7, :H * D] = np.clip(qkv[::7, :H * D].astype(np.int32) * 3, -128, 127).astype(np.int8)
+    s_attn = np.float32(0.031)
+    acc_scale = np.float32(127 * s_attn / (D * 127 * 40))       # scores use most of the int8 range
+    m_s, e_s = K.dyadic_host(np.array([acc_scale], np.float32), s_attn)
+    x0 = O.x0_of(s_attn)
+    m_o, e_o = K.dyadic_host(np.array([2.0 ** -(p_bits - 1) * 0.02], np.float32), np.float32(0.02 * 1.3))
+    me_s, me_o = (int(m_s[0]), int(e_s[0])), (int(m_o[0]), int(e_o[0]))
+    want = oracle_attention(qkv, n_seq, n_tok, H, D, me_s, x0, me_o, p_bits)
+    got = K.attention_i8(dev(qkv), n_seq, n_tok, H, D, me_s, x0, me_o, p_bits=p_bits)
+    assert np.abs(want).max() > 20, "test should produce non-trivial outputs"
+    assert_equal(got, want, "attention n_tok=%d H=%d D=%d P%d" % (n_tok, H, D, p_bits))
