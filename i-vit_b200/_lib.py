@@ -59,6 +59,7 @@ SIGNATURES = {
     "ivit_shiftgelu": [_vp, _vp, _int, _i64, _int, C.c_int32, _int, _vp, _int, _int, _vp, _vp],
     "ivit_attention_i8": [_vp, _vp, C.POINTER(AttnParams), _vp, _vp],
     "ivit_patchify_i8": [_vp, _vp, _int, _int, _int, _int, _int, _vp, _vp],
+    "ivit_embed_tokens": [_vp, _vp, _vp, _vp, _int, _int, _int, Dyadic, Dyadic, _int, _vp, _vp],
 }
 EXPORTS = ["ivit_version", "ivit_last_error", "ivit_create", "ivit_destroy", "ivit_num_sms"] + sorted(SIGNATURES)
 

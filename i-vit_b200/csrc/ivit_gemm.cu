@@ -297,15 +297,14 @@ gemm_i8_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
                             }
 #pragma unroll
                             for (int j = 0; j < 32; ++j) {
-                                int32_t v = clamp_bits_rt(q[j], args.mode_bits);
-                                if (args.two_stage) v = requant32(v, args.me2.m, args.me2.e);
-                                if (res) {
-                                    long long s = (long long)v + requant64((long long)rv[j], args.res_me.m, args.res_me.e);
-                                    v = clamp_i64_bits(s, args.mode_bits);
-                                } else if (args.two_stage) {
-                                    v = clamp_bits_rt(v, args.mode_bits);
-                                }
-                                q[j] = v;
+                                // single stage: clamp(RNE(z*me) + RNE(res*res_me)) -- one QuantAct with identity;
+                                // two stage: q1 = clamp(RNE(z*me)) is itself a QuantAct output, then a second
+                                // QuantAct adds the residual (vit_quant.py:85 then :135)
+                                int32_t v = q[j];
+                                if (args.two_stage) v = requant32(clamp_bits_rt(v, args.mode_bits), args.me2.m, args.me2.e);
+                                long long s = (long long)v;
+                                if (res) s += requant64((long long)rv[j], args.res_me.m, args.res_me.e);
+                                q[j] = clamp_i64_bits(s, args.mode_bits);
                             }
                             if (vec) {
 #pragma unroll
@@ -394,9 +393,9 @@ __global__ void gemm_simt_epilogue(const int32_t* __restrict__ acc, GemmArgs a, 
         if (mode == GM_RAW_I32) { reinterpret_cast<int32_t*>(a.out)[(long long)r * a.out_ld + c] = v; continue; }
         if (mode == GM_CARRIER) { reinterpret_cast<float*>(a.out)[(long long)r * a.out_ld + c] = __fmul_rn(__int2float_rn(v), a.scale[c]); continue; }
         const ivit_dyadic_t d = a.me[c];
-        int32_t q = clamp_bits_rt(requant32(v, d.m, d.e), a.mode_bits);
-        if (mode == GM_RQ_I8) { reinterpret_cast<int8_t*>(a.out)[(long long)r * a.out_ld + c] = (int8_t)q; continue; }
-        if (a.two_stage) q = requant32(q, a.me2.m, a.me2.e);
+        int32_t q = requant32(v, d.m, d.e);
+        if (mode == GM_RQ_I8) { reinterpret_cast<int8_t*>(a.out)[(long long)r * a.out_ld + c] = (int8_t)clamp_bits_rt(q, a.mode_bits); continue; }
+        if (a.two_stage) q = requant32(clamp_bits_rt(q, a.mode_bits), a.me2.m, a.me2.e);
         long long s = q;
         if (a.residual) s += requant64((long long)reinterpret_cast<const int16_t*>(a.residual)[(long long)r * a.res_ld + c], a.res_me.m, a.res_me.e);
         reinterpret_cast<int16_t*>(a.out)[(long long)r * a.out_ld + c] = (int16_t)clamp_i64_bits(s, a.mode_bits);

@@ -111,7 +111,7 @@ __global__ void requant_kernel(const void* __restrict__ z, int z_dtype, int64_t 
         long long o = requant64((long long)load_int(z, z_dtype, i), d.m, d.e);
         if (w != nullptr) {
             const ivit_dyadic_t d1 = me1[me1_len == 1 ? 0 : c];
-            const int64_t wi = (w_rows == 1) ? c : i;
+            const int64_t wi = (w_rows == rows) ? i : (i % (w_rows * (int64_t)cols));   // periodic broadcast
             o += requant64((long long)load_int(w, w_dtype, wi), d1.m, d1.e);
         }
         store_int(out, out_dtype, i, clamp_i64_bits(o, bits));
@@ -277,6 +277,26 @@ __global__ void patchify_kernel(const int8_t* __restrict__ x, int B, int Cin, in
     }
 }
 
+// ------------------------------------------------------------------------------------
+// DeiT stem glue: cls-token concatenation + position-embedding residual QuantAct
+//   vit_quant.py:259-265:  x = cat(cls, patches) ; x = qact1(x, sf, qact_pos(pos_embed), sf_pos)
+//   out[b,t,c] = clamp(RNE(z*m/2^e) + RNE(pos[t,c]*m1/2^e1)),  z = t == 0 ? cls[c] : pe[b,t-1,c]
+// ------------------------------------------------------------------------------------
+__global__ void embed_tokens_kernel(const int16_t* __restrict__ pe, const int32_t* __restrict__ cls,
+                                    const int16_t* __restrict__ pos, int B, int n_tok, int C,
+                                    ivit_dyadic_t me, ivit_dyadic_t me_res, int bits, int16_t* __restrict__ out) {
+    const int64_t n = (int64_t)B * n_tok * C;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C);
+        const int64_t r = i / C;
+        const int t = (int)(r % n_tok);
+        const int64_t b = r / n_tok;
+        const long long z = (t == 0) ? (long long)cls[c] : (long long)pe[(b * (n_tok - 1) + (t - 1)) * (int64_t)C + c];
+        const long long o = requant64(z, me.m, me.e) + requant64((long long)pos[(int64_t)t * C + c], me_res.m, me_res.e);
+        out[i] = (int16_t)clamp_i64_bits(o, bits);
+    }
+}
+
 }  // namespace ivit
 
 using namespace ivit;
@@ -346,8 +366,8 @@ int ivit_requant(ivit_ctx* ctx, const void* z, int z_dtype, int64_t rows, int co
     IVIT_REQUIRE((out_dtype == IVIT_I8 && bits <= 8) || (out_dtype == IVIT_I16 && bits <= 16) || out_dtype == IVIT_I32,
                  "ivit_requant: out_dtype cannot hold %d bits", bits);
     if (w != nullptr) {
-        IVIT_REQUIRE(me1 && (me1_len == 1 || me1_len == cols) && (w_rows == rows || w_rows == 1),
-                     "ivit_requant: residual needs me1 (len 1|cols) and w_rows in {rows, 1}");
+        IVIT_REQUIRE(me1 && (me1_len == 1 || me1_len == cols) && w_rows >= 1 && rows % w_rows == 0,
+                     "ivit_requant: residual needs me1 (len 1|cols) and w_rows dividing rows");
     }
     const int64_t n = rows * cols;
     requant_kernel<<<grid_for(n, 256, ctx->num_sms), 256, 0, st(stream)>>>(
@@ -440,6 +460,17 @@ int ivit_shiftgelu(ivit_ctx* ctx, const void* q, int q_dtype, int64_t rows, int 
     const int grid = grid_for(rows, wpb, ctx->num_sms, 16);
     shiftgelu_kernel<<<grid, wpb * 32, 0, st(stream)>>>(q, q_dtype, rows, cols, x0, inv_x0, n, me, bits, out_dtype, out);
     IVIT_LAUNCH_OK("shiftgelu_kernel");
+    return IVIT_OK;
+}
+
+int ivit_embed_tokens(ivit_ctx* ctx, const int16_t* pe, const int32_t* cls, const int16_t* pos, int B,
+                      int n_tok, int C, ivit_dyadic_t me, ivit_dyadic_t me_res, int bits, int16_t* out,
+                      ivit_stream stream) {
+    IVIT_REQUIRE(ctx && pe && cls && pos && out && B > 0 && n_tok > 1 && C > 0, "ivit_embed_tokens: bad arguments");
+    IVIT_REQUIRE(bits == 16 || bits == 8, "ivit_embed_tokens: bits must be 8 or 16");
+    const int64_t n = (int64_t)B * n_tok * C;
+    embed_tokens_kernel<<<grid_for(n, 256, ctx->num_sms), 256, 0, st(stream)>>>(pe, cls, pos, B, n_tok, C, me, me_res, bits, out);
+    IVIT_LAUNCH_OK("embed_tokens_kernel");
     return IVIT_OK;
 }
 

@@ -1,0 +1,192 @@
+"""Fused whole-model executor for a frozen DeiT/ViT parameter pack (the fast path).
+
+One forward = a fixed sequence of sm_100a kernel launches on int8/int16 tensors that stay on
+the device; every QuantAct of the reference graph is fused into the kernel that produces its
+input (dyadic requant in the GEMM epilogue / LayerNorm / ShiftGELU / attention), the residual
+adds ride in the proj / fc2 GEMM epilogues, scores and probabilities never leave the SM.
+Per block (reference call order vit_quant.py:130-143, 59-88; layers_quant.py:144-153):
+
+    norm1+qact1            ivit_layernorm  (int16 -> int8)
+    qkv+attn.qact1         ivit_gemm_i8    (tcgen05, int8 out)
+    matmul_1..attn.qact2   ivit_attention_i8
+    proj+qact3+Block.qact2 ivit_gemm_i8    (two-stage requant + residual, int16 out)
+    norm2+qact3            ivit_layernorm
+    fc1+qact_gelu          ivit_gemm_i8    (int8 out)
+    act+mlp.qact1          ivit_shiftgelu  (int8 -> int8)
+    fc2+qact2+Block.qact4  ivit_gemm_i8    (two-stage requant + residual, int16 out)
+
+The launch sequence is captured once into a CUDA graph per batch size and replayed.  Results
+are bit-identical to the operator-level path (``quantization_utils``) and to the CPU oracle.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import kernels as K
+from .pack import Pack, check_supported
+
+
+class Engine:
+    def __init__(self, pack: Pack, device="cuda", use_cuda_graph: bool = True):
+        if pack.meta.get("arch") != "deit":
+            raise NotImplementedError("Engine: arch %r" % pack.meta.get("arch"))
+        check_supported(pack)
+        self.meta = dict(pack.meta)
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("ivit_b200.Engine runs on a CUDA (sm_100a) device only")
+        K.context(self.device)                      # fails loudly without the extension / a Blackwell GPU
+        self.use_cuda_graph = use_cuda_graph
+        self.t = {k: torch.from_numpy(v).to(self.device) for k, v in pack.arrays.items()}
+        self.s = {k: (int(v[0, 0]), int(v[0, 1])) for k, v in pack.arrays.items()
+                  if (k.endswith(".me") or k.endswith(".me_res")) and v.shape[0] == 1}
+        self.x0 = {k: int(v[0]) for k, v in pack.arrays.items() if k.endswith(".x0")}
+        self._plans = {}
+        self.launches_per_forward = 0
+
+    # ------------------------------------------------------------------ parameter transport
+    def state_tensors(self):
+        """All device tensors of the frozen pack (for the one-time NCCL broadcast, dist.py)."""
+        return self.t
+
+    # ------------------------------------------------------------------ buffers
+    def _buffers(self, B: int):
+        m = self.meta
+        C, N, Hd = m["embed_dim"], m["n_tok"], m["mlp_hidden"]
+        M = B * N
+        dev = self.device
+        e = lambda *shape, dtype: torch.empty(shape, dtype=dtype, device=dev)
+        return dict(
+            img=e(B, m["in_chans"], m["img_size"], m["img_size"], dtype=torch.float32),
+            img_q=e(B, m["in_chans"], m["img_size"], m["img_size"], dtype=torch.int8),
+            patches=e(B * (N - 1), m["in_chans"] * m["patch"] ** 2, dtype=torch.int8),
+            pe16=e(B * (N - 1), C, dtype=torch.int16),
+            xa=e(M, C, dtype=torch.int16), xb=e(M, C, dtype=torch.int16),
+            ln8=e(M, C, dtype=torch.int8), qkv8=e(M, 3 * C, dtype=torch.int8), ao8=e(M, C, dtype=torch.int8),
+            h8=e(M, Hd, dtype=torch.int8), g8=e(M, Hd, dtype=torch.int8),
+            cls16=e(B, C, dtype=torch.int16), cls8=e(B, C, dtype=torch.int8),
+            logits=e(B, m["num_classes"], dtype=torch.float32))
+
+    # ------------------------------------------------------------------ the launch sequence
+    def _run(self, b, B: int, taps: dict = None):
+        m, t, s = self.meta, self.t, self.s
+        C, N, H, D = m["embed_dim"], m["n_tok"], m["num_heads"], m["head_dim"]
+        n = 0
+
+        def tap(name, tensor):
+            if taps is not None:
+                taps[name] = tensor.clone()
+
+        def lin(name, a, out, me_key, bits, residual=None, stage2=None):
+            kw = {}
+            if stage2 is not None:                                   # per-channel QuantAct, then residual QuantAct
+                kw = dict(two_stage=True, me2=s[stage2 + ".me"], residual=residual, res_me=s[stage2 + ".me_res"])
+            K.gemm_i8(a, t[name + ".weight_integer"], bias=t[name + ".bias_integer"], mode="requant",
+                      me=t[me_key + ".me"], bits=bits, out=out, **kw)
+
+        # input quantisation (vit_quant.py:257) -> patch unfold -> patch-embedding GEMM (+patch_embed.qact, 16 bit)
+        _quantize_into(b["img"], t["qact_input.scale"], b["img_q"]); n += 1
+        tap("qact_input", b["img_q"])
+        K.call("ivit_patchify_i8", K.context(self.device), K.ptr(b["img_q"]), B, m["in_chans"], m["img_size"],
+               m["img_size"], m["patch"], K.ptr(b["patches"])); n += 1
+        lin("patch_embed.proj", b["patches"], b["pe16"], "patch_embed.qact", 16); n += 1
+        tap("patch_embed.qact", b["pe16"])
+        # cls token + position embedding residual (vit_quant.py:259-265)
+        K.embed_tokens(b["pe16"], t["cls_token_integer"], t["pos_embed_integer"], B, N, C,
+                       s["qact1.me"], s["qact1.me_res"], 16, out=b["xa"]); n += 1
+        tap("qact1", b["xa"])
+        x, x2 = b["xa"], b["xb"]
+        for i in range(m["depth"]):
+            p = "blocks.%d." % i
+            _layernorm_into(x, t[p + "norm1.bias_integer"], t[p + "qact1.me"], b["ln8"]); n += 1
+            tap(p + "qact1", b["ln8"])
+            lin(p + "attn.qkv", b["ln8"], b["qkv8"], p + "attn.qact1", 8); n += 1
+            tap(p + "attn.qact1", b["qkv8"])
+            K.attention_i8(b["qkv8"], B, N, H, D, s[p + "attn.qact_attn1.me"], self.x0[p + "attn.int_softmax.x0"],
+                           s[p + "attn.qact2.me"], p_bits=m["softmax_bits"], out=b["ao8"]); n += 1
+            tap(p + "attn.qact2", b["ao8"])
+            lin(p + "attn.proj", b["ao8"], x2, p + "attn.qact3", 16, residual=x, stage2=p + "qact2"); n += 1
+            tap(p + "qact2", x2)
+            _layernorm_into(x2, t[p + "norm2.bias_integer"], t[p + "qact3.me"], b["ln8"]); n += 1
+            tap(p + "qact3", b["ln8"])
+            lin(p + "mlp.fc1", b["ln8"], b["h8"], p + "mlp.qact_gelu", 8); n += 1
+            tap(p + "mlp.qact_gelu", b["h8"])
+            _gelu_into(b["h8"], self.x0[p + "mlp.act.x0"], t[p + "mlp.qact1.me"], b["g8"]); n += 1
+            tap(p + "mlp.qact1", b["g8"])
+            lin(p + "mlp.fc2", b["g8"], x, p + "mlp.qact2", 16, residual=x2, stage2=p + "qact4"); n += 1
+            tap(p + "qact4", x)
+        # final norm on the cls rows only (LayerNorm is row-wise; vit_quant.py:271-273), then the head
+        b["cls16"].copy_(x.view(B, N, C)[:, 0]); n += 1
+        _layernorm_into(b["cls16"], t["norm.bias_integer"], t["qact2.me"], b["cls8"]); n += 1
+        tap("qact2", b["cls8"])
+        K.gemm_i8(b["cls8"], t["head.weight_integer"], bias=t["head.bias_integer"], mode="carrier",
+                  scale=t["head.out_scale"], out=b["logits"]); n += 1
+        self.launches_per_forward = n
+        return b["logits"]
+
+    # ------------------------------------------------------------------ public API
+    def _plan(self, B: int):
+        plan = self._plans.get(B)
+        if plan is None:
+            b = self._buffers(B)
+            plan = {"buf": b, "graph": None}
+            if self.use_cuda_graph:
+                side = torch.cuda.Stream(device=self.device)
+                side.wait_stream(torch.cuda.current_stream(self.device))
+                with torch.cuda.stream(side):
+                    self._run(b, B)                  # eager warm-up: sets func attributes, builds nothing lazily later
+                torch.cuda.current_stream(self.device).wait_stream(side)
+                torch.cuda.synchronize(self.device)
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._run(b, B)
+                plan["graph"] = g
+            self._plans[B] = plan
+        return plan
+
+    @torch.no_grad()
+    def forward(self, images: torch.Tensor) -> torch.Tensor:
+        """images: fp32 [B, 3, H, W] on this engine's device -> fp32 logits [B, classes]
+        (a view of an internal buffer, valid until the next call with the same batch size)."""
+        if images.device != self.device and not (images.is_cuda and self.device.index is None):
+            raise RuntimeError("Engine.forward: images on %s, engine on %s" % (images.device, self.device))
+        B = images.shape[0]
+        plan = self._plan(B)
+        plan["buf"]["img"].copy_(images, non_blocking=True)
+        if plan["graph"] is not None:
+            plan["graph"].replay()
+        else:
+            self._run(plan["buf"], B)
+        return plan["buf"]["logits"]
+
+    __call__ = forward
+
+    @torch.no_grad()
+    def forward_taps(self, images: torch.Tensor) -> dict:
+        """Eager forward that also returns the integer tensor at every fused-operator boundary
+        (keyed by the reference module name of the LAST operator fused into that kernel)."""
+        B = images.shape[0]
+        b = self._buffers(B)
+        b["img"].copy_(images)
+        taps = {}
+        logits = self._run(b, B, taps)
+        taps["logits"] = logits.clone()
+        return taps
+
+
+# thin "write into a preallocated buffer" helpers (CUDA-graph friendly: no allocation in the hot loop)
+def _quantize_into(x, scale, out):
+    K.call("ivit_quantize_f32", K.context(x.device), K.ptr(x), x.numel(), K.ptr(scale), 1, 1, 8,
+           K.TORCH2IVIT[out.dtype], K.ptr(out))
+
+
+def _layernorm_into(x, bias_int, me, out):
+    Cc = x.shape[-1]
+    K.call("ivit_layernorm", K.context(x.device), K.ptr(x), K.TORCH2IVIT[x.dtype], x.numel() // Cc, Cc,
+           K.ptr(bias_int), K.ptr(me), 8, K.TORCH2IVIT[out.dtype], K.ptr(out))
+
+
+def _gelu_into(q, x0, me, out):
+    cols = q.shape[-1]
+    K.call("ivit_shiftgelu", K.context(q.device), K.ptr(q), K.TORCH2IVIT[q.dtype], q.numel() // cols, cols,
+           int(x0), 23, K.ptr(me), 8, K.TORCH2IVIT[out.dtype], K.ptr(out))

@@ -203,3 +203,14 @@ def patchify_i8(x: torch.Tensor, patch: int):
     out = torch.empty((B * (H // patch) * (W // patch), Cin * patch * patch), dtype=torch.int8, device=x.device)
     call("ivit_patchify_i8", context(x.device), ptr(x), B, Cin, H, W, patch, ptr(out))
     return out
+
+
+def embed_tokens(pe16: torch.Tensor, cls32: torch.Tensor, pos16: torch.Tensor, B: int, n_tok: int, C: int,
+                 me, me_res, bits: int = 16, out=None):
+    """cls-token cat + position-embedding residual QuantAct (vit_quant.py:259-265)."""
+    assert pe16.dtype == torch.int16 and cls32.dtype == torch.int32 and pos16.dtype == torch.int16
+    if out is None:
+        out = torch.empty((B * n_tok, C), dtype=torch.int16, device=pe16.device)
+    call("ivit_embed_tokens", context(pe16.device), ptr(pe16), ptr(cls32), ptr(pos16), B, n_tok, C,
+         Dyadic(int(me[0]), int(me[1])), Dyadic(int(me_res[0]), int(me_res[1])), bits, ptr(out))
+    return out

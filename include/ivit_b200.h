@@ -96,7 +96,8 @@ IVIT_API int ivit_int_to_carrier(ivit_ctx*, const void* q, int q_dtype, int64_t 
 /* fixedpoint_mul.forward (quant_utils.py:192-253) on integers:
  *   out = clamp( RNE(z*m/2^e) [+ RNE(w*m1/2^e1)], -2^(bits-1), 2^(bits-1)-1 )
  * z: [rows, cols] (z_dtype); me: me_len (1|cols) entries; optional residual w
- * (w_dtype, [w_rows, cols] with w_rows == rows or 1) with me1 (me1_len 1|cols).
+ * (w_dtype, [w_rows, cols], w_rows divides rows: periodic broadcast, e.g. pos_embed over the
+ * batch, vit_quant.py:264-265) with me1 (me1_len 1|cols).
  * bits in {4, 8, 16, 32}; out_dtype must hold `bits`. */
 IVIT_API int ivit_requant(ivit_ctx*, const void* z, int z_dtype, int64_t rows, int cols,
                           const ivit_dyadic_t* me, int me_len,
@@ -208,6 +209,14 @@ IVIT_API int ivit_attention_i8(ivit_ctx*, const int8_t* qkv, const ivit_attn_par
  * out[(b*Hp + i)*Wp + j, (c*p + u)*p + v] = x[b, c, i*p+u, j*p+v]. */
 IVIT_API int ivit_patchify_i8(ivit_ctx*, const int8_t* x, int B, int Cin, int H, int W, int p,
                               int8_t* out, ivit_stream stream);
+
+/* DeiT stem glue: cls-token concatenation followed by the position-embedding residual QuantAct
+ * (vit_quant.py:259-265): out[b,t,:] = clamp(RNE(z*me) + RNE(pos[t,:]*me_res), bits) with
+ * z = cls (int32 [C], RNE(cls_token / s)) for t == 0 and pe[b, t-1, :] (int16 [B*(n_tok-1), C],
+ * the patch_embed.qact output) otherwise.  pos: int16 [n_tok, C] (qact_pos output).  out int16. */
+IVIT_API int ivit_embed_tokens(ivit_ctx*, const int16_t* pe, const int32_t* cls, const int16_t* pos,
+                               int B, int n_tok, int C, ivit_dyadic_t me, ivit_dyadic_t me_res,
+                               int bits, int16_t* out, ivit_stream stream);
 
 #ifdef __cplusplus
 }

@@ -108,7 +108,7 @@ def requant(z, m, e, bits: int, w=None, m1=None, e1=None, return_diff: bool = Fa
     if w is not None:
         w = _i64(w)
         wrows = w.size // cols
-        assert wrows in (1, rows)
+        assert rows % wrows == 0
         m1, e1 = _i64(m1).reshape(-1), _i64(e1).reshape(-1)
         lib().ivo_requant(_p(z), rows, cols, _p(m), _p(e), m.size, _p(w), wrows,
                           _p(m1), _p(e1), m1.size, bits, _p(out), C.byref(diff))

@@ -116,7 +116,8 @@ IVO_API void ivo_dyadic(const float* s_in, int64_t n, float s_out, int64_t* m, i
  *   out = clamp( RNE(z*m / 2^e) [+ RNE(w*m1 / 2^e1)] , -n-1, n )
  *   z:[rows, cols]; m/e have me_len (1 or cols) entries; the residual uses
  *   m1/e1 (me1_len entries) and w with wrows rows broadcast along rows
- *   (wrows == rows, or wrows == 1 e.g. pos_embed  vit_quant.py:265).
+ *   (wrows divides rows: wrows == rows, or one sequence's worth of rows for pos_embed,
+ *   vit_quant.py:264-265, broadcast over the batch).
  *   Exact 64x64->128-bit product (the reference forms the product in fp64,
  *   quant_utils.py:229; `*n_fp64_diff` counts elements where that fp64
  *   evaluation would differ from the exact one).
@@ -144,7 +145,7 @@ IVO_API void ivo_requant(const int64_t* z, int64_t rows, int64_t cols,
             int64_t o = shift_rne((i128)z[i] * (i128)mm, (int)ee);
             if (o != requant_fp64(z[i], mm, ee)) diff++;
             if (w) {
-                int64_t wi = w[(wrows == 1 ? 0 : r) * cols + c];
+                int64_t wi = w[(r % wrows) * cols + c];              /* periodic broadcast */
                 int64_t mm1 = m1[me1_len == 1 ? 0 : c], ee1 = e1[me1_len == 1 ? 0 : c];
                 int64_t o1 = shift_rne((i128)wi * (i128)mm1, (int)ee1);
                 if (o1 != requant_fp64(wi, mm1, ee1)) diff++;

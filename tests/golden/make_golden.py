@@ -253,7 +253,7 @@ def model_golden(factory_name, tag, batch, full_prefixes):
            "shapes": np.array([json.dumps(list(cap[n].shape)) for n in names]),
            "weights_sha256": np.array(wsum), "seed_images": np.array(7), "batch": np.array(batch)}
     for n in names:
-        if any(n == p or n.startswith(p) for p in full_prefixes):
+        if n in full_prefixes:
             a = cap[n]
             out["full/" + n] = a.astype(np.int32) if np.abs(a).max() < 2 ** 31 else a
     np.savez_compressed(os.path.join(HERE, "%s.npz" % tag), **out)
@@ -266,10 +266,10 @@ if __name__ == "__main__":
         op_kats()
     if "tiny" in which:
         model_golden("deit_tiny_patch16_224", "deit_tiny_b2", 2,
-                     ["qact_input", "patch_embed", "qact_pos", "qact1", "blocks.0.", "norm", "qact2", "head"])
+                     ["qact1", "blocks.0.attn.qact2", "blocks.0.qact4", "blocks.11.qact4", "qact2", "head"])
     if "calib" in which:
         for f in ("deit_small_patch16_224", "deit_base_patch16_224"):
             model_golden(f, None, None, [])
     if "swin" in which:
         model_golden("swin_tiny_patch4_window7_224", "swin_tiny_b1", 1,
-                     ["qact_input", "patch_embed", "layers.0.blocks.0.", "layers.0.blocks.1.", "norm", "head"])
+                     ["qact1", "layers.0.blocks.1.qact4", "qact3", "head"])
