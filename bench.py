@@ -1,0 +1,314 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: frozen INT8 DeiT forward (BASELINE.json: images/sec DeiT-B INT8 bs=256).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--model NAME] [--batch B]
+
+One "step" = one forward of the synthetic frozen model over one batch of B synthetic 3x224x224
+fp32 images per GPU (batch sharded across ranks, weak scaling, no forward collective; the frozen
+parameter pack is NCCL-broadcast once from rank 0).  Prints ONE JSON line (rank 0):
+
+  value        whole-job images/s, inputs already resident in HBM (CUDA events, max over ranks)
+  e2e          same metric through the public API with HOST buffers: pinned fp32 images -> H2D ->
+               engine -> D2H logits, every step
+  roofline     dominant kernel (tcgen05 INT8 GEMM): algorithmic int-ops / measured launch time vs the
+               measured tensor peak (MEASURED_PEAKS.json bf16 x 2)
+  cpu_baseline the oracle port (oracle/, pinned to the reference) timed on this box's host cores
+  --impl reference   the reference's CPU integer path (oracle port; the reference itself is Python
+               and cannot travel to the GPU box) on rank 0 only, same metric / config
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+METRIC = "images/sec DeiT-B INT8 bs=256"
+MODEL = "deit_base_patch16_224"
+
+
+def int_ops_per_image(meta) -> float:
+    """Algorithmic integer ops (2 x MAC) per image, SURVEY.md section 8(d)."""
+    C, N, H, D, Hd = meta["embed_dim"], meta["n_tok"], meta["num_heads"], meta["head_dim"], meta["mlp_hidden"]
+    pe = (N - 1) * C * meta["in_chans"] * meta["patch"] ** 2
+    blk = N * C * 3 * C + 2 * H * N * N * D + N * C * C + 2 * N * C * Hd
+    return 2.0 * (pe + meta["depth"] * blk + C * meta["num_classes"])
+
+
+def gemm_shapes(meta, B):
+    """(name, M, N, K, launches per forward) of every tcgen05 GEMM launch."""
+    C, N, Hd, L = meta["embed_dim"], meta["n_tok"], meta["mlp_hidden"], meta["depth"]
+    M = B * N
+    return [("patch_embed", B * (N - 1), C, meta["in_chans"] * meta["patch"] ** 2, 1),
+            ("qkv", M, 3 * C, C, L), ("proj", M, C, C, L), ("fc1", M, Hd, C, L), ("fc2", M, C, Hd, L),
+            ("head", B, meta["num_classes"], C, 1)]
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.samples, self._stop = index, [], threading.Event()
+        self.thread = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def __enter__(self):
+        self.thread.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self.thread.join(timeout=3)
+
+    def summary(self):
+        sm = [float(s[0]) for s in self.samples if s and s[0].replace(".", "").isdigit()]
+        mx = [float(s[1]) for s in self.samples if len(s) > 1 and s[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for s in self.samples if len(s) >= 7 for i in range(4) if s[3 + i].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(self.samples)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d, "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+def build_pack(model_name):
+    from ivit_b200.calib import build_synthetic
+    from ivit_b200.pack import export_deit
+    return export_deit(build_synthetic(model_name))
+
+
+# ------------------------------------------------------------------------------------------ reference arm
+def run_reference(args, rank, world):
+    """CPU arm: the oracle port of the reference's integer path (all host threads)."""
+    if rank != 0:
+        return
+    import oracle as O
+    import oracle.model as OM
+    from ivit_b200.synth import synth_images
+    cores = os.cpu_count() or 1
+    O.set_threads(cores)
+    pack = build_pack(args.model)
+    imgs_per_step = args.ref_images
+    x = synth_images(imgs_per_step, seed=11).numpy()
+    for _ in range(min(args.warmup, 1)):
+        OM.deit_forward(pack, x)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        OM.deit_forward(pack, x)
+    dt = (time.perf_counter() - t0) / max(args.steps, 1)
+    val = imgs_per_step / dt
+    line = {"metric": METRIC, "value": val, "unit": "images/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": min(args.warmup, 1), "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "int8", "data": "synthetic", "impl": "reference",
+            "config": {"workload": "%s frozen INT8 forward, 3x224x224 synthetic, batch 256 per GPU" % args.model,
+                       "note": "reference is pure Python/PyTorch and cannot travel to the GPU box; its CPU integer path "
+                               "is timed through the oracle port (oracle/, bit-pinned to the reference)"},
+            "cpu_baseline": {"value": val, "unit": "images/s", "cores": cores, "kind": "port",
+                             "sample": "%d image(s) of the batch per step, GEMMs row-split over %d threads" % (imgs_per_step, cores)},
+            "e2e": {"value": val, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------ our arm
+def time_gemms(eng, B, iters=10):
+    """Average device time of each GEMM shape of the forward, measured with CUDA events on the
+    launching stream (the dominant kernel of the step)."""
+    import ivit_b200.kernels as K
+    meta, t = eng.meta, eng.t
+    dev = eng.device
+    names = {"patch_embed": ("patch_embed.proj", "patch_embed.qact", 16), "qkv": ("blocks.0.attn.qkv", "blocks.0.attn.qact1", 8),
+             "proj": ("blocks.0.attn.proj", "blocks.0.attn.qact3", 16), "fc1": ("blocks.0.mlp.fc1", "blocks.0.mlp.qact_gelu", 8),
+             "fc2": ("blocks.0.mlp.fc2", "blocks.0.mlp.qact2", 16)}
+    res = []
+    for name, M, N, Kd, count in gemm_shapes(meta, B):
+        if name == "head":
+            continue
+        lin, qa, bits = names[name]
+        a = torch.randint(-128, 128, (M, Kd), dtype=torch.int8, device=dev)
+        out = torch.empty((M, N), dtype=torch.int8 if bits == 8 else torch.int16, device=dev)
+        kw = {}
+        if name in ("proj", "fc2"):
+            r = torch.randint(-30000, 30000, (M, N), dtype=torch.int16, device=dev)
+            blk = "blocks.0.qact2" if name == "proj" else "blocks.0.qact4"
+            kw = dict(two_stage=True, me2=eng.s[blk + ".me"], residual=r, res_me=eng.s[blk + ".me_res"])
+        run = lambda: K.gemm_i8(a, t[lin + ".weight_integer"], bias=t[lin + ".bias_integer"], mode="requant",
+                                me=t[qa + ".me"], bits=bits, out=out, **kw)
+        for _ in range(3):
+            run()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(iters):
+            run()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / iters
+        res.append({"name": name, "M": M, "N": N, "K": Kd, "launches": count, "ms": ms,
+                    "tops": 2.0 * M * N * Kd / (ms * 1e-3) / 1e12})
+        del a, out
+    return res
+
+
+def run_ours(args, rank, world, local_rank):
+    import torch.distributed as dist
+    from ivit_b200.dist import broadcast_pack
+    from ivit_b200.engine import Engine
+    from ivit_b200.synth import synth_images
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    pack = build_pack(args.model) if rank == 0 else None
+    if world > 1:
+        pack = broadcast_pack(pack, src=0, device=dev)       # one-time NCCL broadcast of the frozen INT8 parameters
+    eng = Engine(pack, dev)
+    B = args.batch
+    g = torch.Generator(device="cpu")
+    g.manual_seed(1234 + rank)
+    host = torch.randn((B, 3, eng.meta["img_size"], eng.meta["img_size"]), generator=g).pin_memory()
+    x = host.to(dev, non_blocking=True)
+    out_host = torch.empty((B, eng.meta["num_classes"]), dtype=torch.float32).pin_memory()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    def step_resident():
+        eng(x)
+
+    def step_e2e():
+        xd = host.to(dev, non_blocking=True)
+        out_host.copy_(eng(xd), non_blocking=True)
+
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    with ClockSampler(local_rank) as clk:
+        total_ms = timed(step_resident, args.steps)
+    clocks = clk.summary()
+    for _ in range(2):
+        step_e2e()
+    e2e_ms = timed(step_e2e, args.steps)
+
+    ms_step = total_ms / args.steps
+    value = world * B / (ms_step * 1e-3)
+    e2e_val = world * B / (e2e_ms / args.steps * 1e-3)
+    if rank != 0:
+        return
+    peaks, peak_src = measured_peaks()
+    gem = time_gemms(eng, B)
+    ops = sum(2.0 * g_["M"] * g_["N"] * g_["K"] * g_["launches"] for g_ in gem)
+    gms = sum(g_["ms"] * g_["launches"] for g_ in gem)
+    achieved = ops / (gms * 1e-3) / 1e12
+    peak = 2.0 * float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops")))
+    cpu = None
+    if not args.no_cpu_baseline:
+        import oracle as O
+        import oracle.model as OM
+        cores = os.cpu_count() or 1
+        O.set_threads(cores)
+        xs = synth_images(args.ref_images, seed=11).numpy()
+        t0 = time.perf_counter()
+        reps = 0
+        while reps < 1 or (time.perf_counter() - t0 < 10.0 and reps < 50):
+            OM.deit_forward(pack, xs)
+            reps += 1
+        dt = (time.perf_counter() - t0) / reps
+        cpu = {"value": args.ref_images / dt, "unit": "images/s", "cores": cores, "kind": "port",
+               "sample": "%d forward(s) of %d image(s) (same synthetic %s pack), GEMMs row-split over %d host threads" % (
+                   reps, args.ref_images, args.model, cores)}
+    act_mb = B * eng.meta["n_tok"] * eng.meta["mlp_hidden"] / 1e6
+    line = {"metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "int8", "data": "synthetic",
+            "config": {"workload": "%s frozen INT8 forward, batch %d per GPU, 3x224x224 synthetic fp32 images" % (args.model, B),
+                       "global_batch": world * B, "parallelism": "batch sharded dp%d, one-time NCCL weight broadcast" % world,
+                       "l2": "no flush needed: per-step working set (fp32 input %.0f MB + fc1/GELU activations 2 x %.0f MB) exceeds the 126 MB L2" % (
+                           B * 3 * 224 * 224 * 4 / 1e6, act_mb),
+                       "int_ops_per_image": int_ops_per_image(eng.meta)},
+            "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                         "traffic": None, "kernel": "gemm_i8_tcgen05_kernel (all %d GEMM launches of the step)" % sum(g_["launches"] for g_ in gem),
+                         "peak_source": "2 x bf16_tflops_sustained of MEASURED_PEAKS.json (%s); int8 tensor rate = 2 x bf16" % peak_src,
+                         "per_shape": gem, "gemm_share_of_step": gms / ms_step,
+                         "whole_step_int_tops": int_ops_per_image(eng.meta) * B / (ms_step * 1e-3) / 1e12},
+            "cpu_baseline": cpu,
+            "e2e": {"value": e2e_val, "unit": "images/s", "h2d_bytes_per_step": int(host.numel() * 4) * world,
+                    "d2h_bytes_per_step": int(out_host.numel() * 4) * world, "ms_per_step": e2e_ms / args.steps},
+            "gpu_launches": (eng.launches_per_forward - 1) * args.steps,
+            "clocks": clocks}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--model", default=MODEL)
+    ap.add_argument("--batch", type=int, default=256, help="images per GPU per step")
+    ap.add_argument("--ref-images", type=int, default=2, help="images per CPU-baseline step (bounded sample)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback "
+                         "(use --impl reference for the CPU arm)")
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    try:
+        run_ours(args, rank, world, local_rank)
+    finally:
+        if world > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

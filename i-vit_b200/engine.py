@@ -37,7 +37,11 @@ class Engine:
             raise RuntimeError("ivit_b200.Engine runs on a CUDA (sm_100a) device only")
         K.context(self.device)                      # fails loudly without the extension / a Blackwell GPU
         self.use_cuda_graph = use_cuda_graph
-        self.t = {k: torch.from_numpy(v).to(self.device) for k, v in pack.arrays.items()}
+        dev_t = getattr(pack, "device_tensors", None)       # set by dist.broadcast_pack: already on the GPU
+        if dev_t is not None and all(v.device == self.device or (v.is_cuda and self.device.index is None) for v in dev_t.values()):
+            self.t = dict(dev_t)
+        else:
+            self.t = {k: torch.from_numpy(v).to(self.device) for k, v in pack.arrays.items()}
         self.s = {k: (int(v[0, 0]), int(v[0, 1])) for k, v in pack.arrays.items()
                   if (k.endswith(".me") or k.endswith(".me_res")) and v.shape[0] == 1}
         self.x0 = {k: int(v[0]) for k, v in pack.arrays.items() if k.endswith(".x0")}

@@ -54,6 +54,8 @@ def lib():
         L.ivo_shiftgelu.argtypes = [vp, i64, i64, i64, C.c_int, C.c_int, vp]
         L.ivo_layernorm.argtypes = [vp, i64, i64, vp, vp]
         L.ivo_avgpool_rne.argtypes = [vp, i64, i64, i64, vp]
+        L.ivo_set_threads.argtypes = [C.c_int]
+        L.ivo_get_threads.restype = C.c_int
         _lib = L
     return _lib
 
@@ -68,6 +70,12 @@ def _i64(a):
 
 def _f32(a):
     return np.ascontiguousarray(np.asarray(a), dtype=np.float32)
+
+
+def set_threads(n: int) -> int:
+    """Host threads used by the int8 GEMM (the CPU baseline uses every core)."""
+    lib().ivo_set_threads(int(n))
+    return lib().ivo_get_threads()
 
 
 # --------------------------------------------------------------------------- primitives

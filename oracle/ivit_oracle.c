@@ -16,6 +16,7 @@
  * static quantities are defined by fp32 / fp64 IEEE operations).
  */
 #include <math.h>
+#include <pthread.h>
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
@@ -175,10 +176,19 @@ IVO_API void ivo_gemm_nt(const int32_t* a, const int32_t* w, const int64_t* bias
     }
 }
 
-/* int8 fast path of the same contraction (used for whole-model oracles) */
-IVO_API void ivo_gemm_nt_i8(const int8_t* a, const int8_t* w, const int32_t* bias,
-                            int64_t M, int64_t N, int64_t K, int32_t* out) {
-    for (int64_t i = 0; i < M; ++i) {
+/* int8 fast path of the same contraction (used for whole-model oracles and as the CPU
+ * baseline of bench.py): rows are split over `ivo_set_threads` host threads, the dot
+ * product is auto-vectorised per ISA (function multi-versioning, safe on any x86-64). */
+static int g_threads = 1;
+IVO_API void ivo_set_threads(int n) { g_threads = n < 1 ? 1 : (n > 256 ? 256 : n); }
+IVO_API int ivo_get_threads(void) { return g_threads; }
+
+#if defined(__x86_64__)
+__attribute__((target_clones("arch=x86-64-v4", "avx2", "default")))
+#endif
+static void gemm_rows_i8(const int8_t* a, const int8_t* w, const int32_t* bias,
+                         int64_t r0, int64_t r1, int64_t N, int64_t K, int32_t* out) {
+    for (int64_t i = r0; i < r1; ++i) {
         const int8_t* ar = a + i * K;
         for (int64_t j = 0; j < N; ++j) {
             const int8_t* wr = w + j * K;
@@ -187,6 +197,34 @@ IVO_API void ivo_gemm_nt_i8(const int8_t* a, const int8_t* w, const int32_t* bia
             out[i * N + j] = acc + (bias ? bias[j] : 0);
         }
     }
+}
+
+typedef struct {
+    const int8_t* a; const int8_t* w; const int32_t* bias;
+    int64_t r0, r1, N, K; int32_t* out;
+} gemm_job;
+
+static void* gemm_worker(void* p) {
+    gemm_job* j = (gemm_job*)p;
+    gemm_rows_i8(j->a, j->w, j->bias, j->r0, j->r1, j->N, j->K, j->out);
+    return NULL;
+}
+
+IVO_API void ivo_gemm_nt_i8(const int8_t* a, const int8_t* w, const int32_t* bias,
+                            int64_t M, int64_t N, int64_t K, int32_t* out) {
+    int T = g_threads;
+    if (T > M) T = (int)M;
+    if (T <= 1 || M * N * K < (1LL << 22)) {
+        gemm_rows_i8(a, w, bias, 0, M, N, K, out);
+        return;
+    }
+    pthread_t th[256];
+    gemm_job jobs[256];
+    for (int t = 0; t < T; ++t) {
+        jobs[t] = (gemm_job){a, w, bias, M * t / T, M * (t + 1) / T, N, K, out};
+        pthread_create(&th[t], NULL, gemm_worker, &jobs[t]);
+    }
+    for (int t = 0; t < T; ++t) pthread_join(th[t], NULL);
 }
 
 /* ---------------------------------------------------------------------------

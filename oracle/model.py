@@ -21,6 +21,18 @@ def _me(pack, key):
     return t[:, 0], t[:, 1]
 
 
+def _bmm_nt(a, b):
+    """[B,H,M,K] x [B,H,N,K]^T -> [B,H,M,N] through the C contraction (numpy has no fast int64 matmul)."""
+    Bb, Hh, M, _ = a.shape
+    N = b.shape[2]
+    out = np.empty((Bb, Hh, M, N), np.int64)
+    i8 = a.dtype == np.int8 and b.dtype == np.int8
+    for i in range(Bb):
+        for h in range(Hh):
+            out[i, h] = O.gemm_nt(np.ascontiguousarray(a[i, h]), np.ascontiguousarray(b[i, h]))
+    return out
+
+
 def _linear(pack, name, x):
     return O.gemm_nt(x.astype(np.int8), pack[name + ".weight_integer"], pack[name + ".bias_integer"])
 
@@ -64,13 +76,13 @@ def deit_forward(pack, images: np.ndarray, capture: dict = None):
         rec(p + "attn.qact1", qkv, (B, N, 3 * C))
         qkv5 = qkv.reshape(B, N, 3, H, D).transpose(2, 0, 3, 1, 4)                    # :63-64
         qh, kh, vh = qkv5[0], qkv5[1], qkv5[2]                                        # [B,H,N,D]
-        s = np.matmul(qh, kh.transpose(0, 1, 3, 2))                                   # :70-71
+        s = _bmm_nt(qh.astype(np.int8), kh.astype(np.int8))                           # :70-71
         rec(p + "attn.matmul_1", s)
         s = O.requant(s, *_me(pack, p + "attn.qact_attn1.me"), 8)                     # :74
         rec(p + "attn.qact_attn1", s)
         pr = O.shiftmax(s, int(pack[p + "attn.int_softmax.x0"][0]), mt["softmax_bits"])   # :76
         rec(p + "attn.int_softmax", pr)
-        o = np.matmul(pr, vh)                                                         # :79-80
+        o = _bmm_nt(pr, vh.transpose(0, 1, 3, 2))                                     # :79-80
         rec(p + "attn.matmul_2", o)
         o = o.transpose(0, 2, 1, 3).reshape(B * N, C)                                 # :81
         o = O.requant(o, *_me(pack, p + "attn.qact2.me"), 8)                          # :83

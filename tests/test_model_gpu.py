@@ -1,0 +1,112 @@
+"""GPU whole-model parity: the fused engine and the operator-level drop-in path against the CPU
+oracle (full tensors) and against the reference-generated golden digests, DeiT-tiny.  Bit-exact."""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import oracle.model as OM
+from conftest import GOLDEN
+
+pytestmark = pytest.mark.gpu
+
+
+def digest(a):
+    return hashlib.sha256(np.ascontiguousarray(a, dtype="<i8").tobytes()).hexdigest()
+
+
+@pytest.fixture(scope="module")
+def tiny():
+    from ivit_b200.calib import build_synthetic
+    from ivit_b200.engine import Engine
+    from ivit_b200.pack import export_deit
+    from ivit_b200.synth import synth_images
+    model = build_synthetic("deit_tiny_patch16_224")
+    pack = export_deit(model)
+    gold = np.load(os.path.join(GOLDEN, "deit_tiny_b2.npz"))
+    x = synth_images(int(gold["batch"]), seed=int(gold["seed_images"]))
+    cap = {}
+    logits = OM.deit_forward(pack, x.numpy(), cap)
+    eng = Engine(pack, "cuda")
+    return dict(model=model, pack=pack, gold=gold, x=x, cap=cap, logits=logits, eng=eng)
+
+
+def test_engine_matches_oracle_at_every_fused_boundary(tiny):
+    taps = tiny["eng"].forward_taps(tiny["x"].cuda())
+    cap = tiny["cap"]
+    n = 0
+    for name, t in taps.items():
+        if name == "logits":
+            continue
+        got = t.cpu().numpy().astype(np.int64)
+        want = cap[name]
+        assert got.size == want.size, name
+        bad = np.argwhere(got.reshape(-1) != want.reshape(-1))
+        assert len(bad) == 0, "engine diverges from the oracle at %s: %d / %d elements, first flat index %d" % (
+            name, len(bad), want.size, int(bad[0]))
+        n += 1
+    assert n >= 8 * 12 + 4
+    assert np.array_equal(taps["logits"].cpu().numpy(), tiny["logits"]), "logits differ from the oracle"
+
+
+def test_engine_matches_reference_digests(tiny):
+    """Golden digests came from the reference's own modules: no oracle involved in this check."""
+    gold = tiny["gold"]
+    want = dict(zip(gold["names"].tolist(), gold["digests"].tolist()))
+    shapes = dict(zip(gold["names"].tolist(), gold["shapes"].tolist()))
+    taps = tiny["eng"].forward_taps(tiny["x"].cuda())
+    n = 0
+    for name, t in taps.items():
+        if name in want and name != "qact_input":
+            assert digest(t.cpu().numpy().astype(np.int64)) == want[name], "digest mismatch at %s" % name
+            n += 1
+    assert n >= 90
+    err = np.abs(taps["logits"].cpu().numpy().astype(np.float64) - gold["logits"].astype(np.float64)).max()
+    assert err <= 2e-6 * np.abs(gold["logits"]).max()        # see tests/test_model_oracle.py on the head's carrier noise
+    assert (taps["logits"].cpu().numpy().argmax(1) == gold["logits"].argmax(1)).all()
+
+
+def test_cuda_graph_replay_and_batch_sizes(tiny):
+    from ivit_b200.synth import synth_images
+    eng = tiny["eng"]
+    xg = tiny["x"].cuda()
+    a = eng(xg).clone()
+    b = eng(xg).clone()                                      # second call replays the captured graph
+    assert torch.equal(a, b)
+    assert np.array_equal(a.cpu().numpy(), tiny["logits"])
+    x5 = synth_images(5, seed=3)
+    want = OM.deit_forward(tiny["pack"], x5.numpy())
+    assert np.array_equal(eng(x5.cuda()).cpu().numpy(), want)
+    assert np.array_equal(eng(x5[:1].cuda()).cpu().numpy(), want[:1])
+    assert eng.launches_per_forward == 4 + 8 * 12 + 3
+
+
+def test_operator_level_path_matches_engine(tiny):
+    """The drop-in operator classes (fp32 carrier in / out, one kernel per reference operator)
+    give bit-identical logits to the fused engine."""
+    model = tiny["model"].cuda()
+    with torch.no_grad():
+        y = model(tiny["x"].cuda())
+    assert np.array_equal(y.cpu().numpy(), tiny["logits"])
+    model.cpu()
+
+
+def test_operator_level_calibration_pass_runs(tiny):
+    """One unfrozen forward (running_stat=True, quant_modules.py:170-189) through the operator
+    classes on the GPU sets every executed QuantAct's range."""
+    from ivit_b200 import deit
+    from ivit_b200.model_utils import freeze_model, unfreeze_model
+    from ivit_b200.synth import synth_images, synth_parameters
+    m = deit.deit_tiny_patch16_224().eval()
+    synth_parameters(m, 0)
+    m = m.cuda()
+    unfreeze_model(m)
+    with torch.no_grad():
+        m(synth_images(2, seed=0).cuda())
+        freeze_model(m)
+        y1 = m(synth_images(2, seed=5).cuda())
+        y2 = m(synth_images(2, seed=5).cuda())
+    assert torch.equal(y1, y2) and torch.isfinite(y1).all()
+    assert float(torch.as_tensor(m.blocks[3].qact2.max_val)) > 0
