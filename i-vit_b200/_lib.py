@@ -15,10 +15,11 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 SO_PATH = os.path.join(_HERE, "csrc", "libivit_b200.so")
 
-I8, I16, I32, F32, U8 = 0, 1, 2, 3, 4
+I8, I16, I32, F32, U8, F64 = 0, 1, 2, 3, 4, 5
 EPI_RAW_I32, EPI_REQUANT, EPI_CARRIER = 0, 1, 2
 
-TORCH2IVIT = {torch.int8: I8, torch.int16: I16, torch.int32: I32, torch.float32: F32, torch.uint8: U8}
+TORCH2IVIT = {torch.int8: I8, torch.int16: I16, torch.int32: I32, torch.float32: F32, torch.uint8: U8,
+              torch.float64: F64}
 IVIT2TORCH = {v: k for k, v in TORCH2IVIT.items()}
 
 
@@ -49,8 +50,8 @@ _vp, _i64, _int = C.c_void_p, C.c_int64, C.c_int
 SIGNATURES = {
     "ivit_dyadic": [_vp, _vp, _int, _vp, _vp, _vp],
     "ivit_quantize_f32": [_vp, _vp, _i64, _vp, _i64, _i64, _int, _int, _vp, _vp],
-    "ivit_carrier_to_int": [_vp, _vp, _i64, _int, _vp, _int, _int, _vp, _vp],
-    "ivit_int_to_carrier": [_vp, _vp, _int, _i64, _int, _vp, _int, _vp, _vp],
+    "ivit_carrier_to_int": [_vp, _vp, _int, _i64, _int, _vp, _int, _int, _vp, _vp],
+    "ivit_int_to_carrier": [_vp, _vp, _int, _i64, _int, _vp, _int, _int, _vp, _vp],
     "ivit_requant": [_vp, _vp, _int, _i64, _int, _vp, _int, _vp, _int, _i64, _vp, _int, _int, _int, _vp, _vp],
     "ivit_gemm_i8": [_vp, _vp, _i64, _vp, _i64, _i64, _i64, C.POINTER(GemmEpilogue), _vp, _vp],
     "ivit_bmm_i32": [_vp, _vp, _int, _i64, _i64, _vp, _i64, _i64, _int, _i64, _int, _int, _int, _vp, _i64, _i64, _vp],
@@ -60,6 +61,9 @@ SIGNATURES = {
     "ivit_attention_i8": [_vp, _vp, C.POINTER(AttnParams), _vp, _vp],
     "ivit_patchify_i8": [_vp, _vp, _int, _int, _int, _int, _int, _vp, _vp],
     "ivit_embed_tokens": [_vp, _vp, _vp, _vp, _int, _int, _int, Dyadic, Dyadic, _int, _vp, _vp],
+    "ivit_shiftgelu_build_lut": [_vp, C.c_int32, _int, _vp, _int, _vp, _vp],
+    "ivit_shiftgelu_lut": [_vp, _vp, _i64, _int, _vp, _vp, _vp],
+    "ivit_layernorm_i16_i8": [_vp, _vp, _i64, _int, _vp, _vp, _vp, _vp],
 }
 EXPORTS = ["ivit_version", "ivit_last_error", "ivit_create", "ivit_destroy", "ivit_num_sms"] + sorted(SIGNATURES)
 

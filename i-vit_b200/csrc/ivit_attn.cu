@@ -43,12 +43,12 @@ struct AttnArgs {
     int n_win;
 };
 
-constexpr int ATT_WARPS = 7;
+constexpr int ATT_WARPS = 8;
 constexpr int PAD_MARK = -100000;  // marks key columns >= n_tok
 
 // D: head dim (32 | 64).  KT: number of 32-token chunks (n_tok <= 32*KT).
 template <int D, int KT>
-__global__ void __launch_bounds__(ATT_WARPS * 32, 1)
+__global__ void __launch_bounds__(ATT_WARPS * 32, 2)
 attention_kernel(const int8_t* __restrict__ qkv, const AttnArgs p, int8_t* __restrict__ out) {
     constexpr int NT = KT * 4;             // 8-column score tiles
     constexpr int KSTR = D + 16;           // bytes; (KSTR/4) mod 32 spreads the 8 fragment rows over distinct banks
@@ -99,70 +99,93 @@ attention_kernel(const int8_t* __restrict__ qkv, const AttnArgs p, int8_t* __res
     __syncthreads();
 
     const int n_row_tiles = (n_tok + 15) / 16;
+    const UniRq rq_s = make_unirq(p.me_s, 21);        // |Q.K| <= 64 * 128 * 128 = 2^20
+    const UniRq rq_o = make_unirq(p.me_o, 23);        // |P.V| <= 2^15 * 128 = 2^22
+    const int col_lim = n_tok - 2 * q4;               // column 8t + (c&1) + 2*q4 is padding iff 8t + (c&1) >= col_lim
+    const uint32_t e_sat = (uint32_t)sE[256];
     for (int rt = warp; rt < n_row_tiles; rt += ATT_WARPS) {
         const int r0 = rt * 16 + g, r1 = r0 + 8;
         // ---- Q fragments straight from global ----
         uint32_t aq[KK][4];
 #pragma unroll
         for (int kk = 0; kk < KK; ++kk) {
-            aq[kk][0] = (r0 < n_tok) ? *reinterpret_cast<const uint32_t*>(qb + (long long)r0 * ld + 32 * kk + 4 * q4) : 0u;
-            aq[kk][1] = (r1 < n_tok) ? *reinterpret_cast<const uint32_t*>(qb + (long long)r1 * ld + 32 * kk + 4 * q4) : 0u;
-            aq[kk][2] = (r0 < n_tok) ? *reinterpret_cast<const uint32_t*>(qb + (long long)r0 * ld + 32 * kk + 16 + 4 * q4) : 0u;
-            aq[kk][3] = (r1 < n_tok) ? *reinterpret_cast<const uint32_t*>(qb + (long long)r1 * ld + 32 * kk + 16 + 4 * q4) : 0u;
+            aq[kk][0] = (r0 < n_tok) ? __ldg(reinterpret_cast<const uint32_t*>(qb + (long long)r0 * ld + 32 * kk + 4 * q4)) : 0u;
+            aq[kk][1] = (r1 < n_tok) ? __ldg(reinterpret_cast<const uint32_t*>(qb + (long long)r1 * ld + 32 * kk + 4 * q4)) : 0u;
+            aq[kk][2] = (r0 < n_tok) ? __ldg(reinterpret_cast<const uint32_t*>(qb + (long long)r0 * ld + 32 * kk + 16 + 4 * q4)) : 0u;
+            aq[kk][3] = (r1 < n_tok) ? __ldg(reinterpret_cast<const uint32_t*>(qb + (long long)r1 * ld + 32 * kk + 16 + 4 * q4)) : 0u;
         }
-        // ---- S = Q K^T ----
-        int32_t s[NT][4];
+        // ---- S = Q K^T, requantised tile by tile to int8 (qact_attn1 [+ rel-pos bias, mask]) and
+        //      packed four per register: sv[t] = {row r0: col 2q, 2q+1 ; row r1: col 2q, 2q+1} ----
+        uint32_t sv[NT];
+        uint32_t masked[(NT + 7) / 8];                // 4 bits per tile, only meaningful with a Swin mask
+#pragma unroll
+        for (int i = 0; i < (NT + 7) / 8; ++i) masked[i] = 0u;
+        int32_t mx0 = -128, mx1 = -128;
 #pragma unroll
         for (int t = 0; t < NT; ++t) {
-            s[t][0] = s[t][1] = s[t][2] = s[t][3] = 0;
+            int32_t acc[4] = {0, 0, 0, 0};
 #pragma unroll
             for (int kk = 0; kk < KK; ++kk) {
                 const uint32_t b0 = *reinterpret_cast<const uint32_t*>(sK + (8 * t + g) * KSTR + 32 * kk + 4 * q4);
                 const uint32_t b1 = *reinterpret_cast<const uint32_t*>(sK + (8 * t + g) * KSTR + 32 * kk + 16 + 4 * q4);
-                mma_s8s8(s[t], aq[kk], b0, b1);
+                mma_s8s8(acc, aq[kk], b0, b1);
             }
-        }
-        // ---- requant to int8 (qact_attn1), optional rel-pos bias / mask (Swin), row max ----
-        int32_t mx0 = INT32_MIN, mx1 = INT32_MIN;
-#pragma unroll
-        for (int t = 0; t < NT; ++t) {
+            int32_t v[4];
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
-                const int col = 8 * t + 2 * q4 + (c & 1);
-                const int row = (c < 2) ? r0 : r1;
-                int32_t v = clamp_bits<8>(requant32(s[t][c], p.me_s.m, p.me_s.e));
-                if (p.relbias != nullptr && col < n_tok && row < n_tok) {
-                    const int32_t bq = (int32_t)p.relbias[((long long)h * n_tok + row) * n_tok + col];
-                    long long t2 = requant64((long long)v, p.me_s2.m, p.me_s2.e) + requant64((long long)bq, p.me_b.m, p.me_b.e);
-                    v = clamp_i64_bits(t2, 8);
+                v[c] = clamp_bits<8>(unirq_apply(rq_s, acc[c]));
+                if (p.relbias != nullptr || p.mask != nullptr) {       // Swin (uniform branch)
+                    const int col = 8 * t + 2 * q4 + (c & 1);
+                    const int row = (c < 2) ? r0 : r1;
+                    if (col < n_tok && row < n_tok) {
+                        if (p.relbias != nullptr) {
+                            const int32_t bq = (int32_t)p.relbias[((long long)h * n_tok + row) * n_tok + col];
+                            const long long t2 = requant64((long long)v[c], p.me_s2.m, p.me_s2.e) +
+                                                 requant64((long long)bq, p.me_b.m, p.me_b.e);
+                            v[c] = clamp_i64_bits(t2, 8);
+                        }
+                        if (p.mask != nullptr) {
+                            const int32_t mv = p.mask[((long long)(b % p.n_win) * n_tok + row) * n_tok + col];
+                            // a masked entry (addend RNE(-100/s)) is always past the Shiftmax saturation
+                            // point for s < 0.35: remember it, its exponential is E(n*x0)
+                            if (mv != 0) { masked[t / 8] |= 1u << (4 * (t % 8) + c); v[c] = -128; }
+                        }
+                    }
                 }
-                if (p.mask != nullptr && col < n_tok && row < n_tok)
-                    v += p.mask[((long long)(b % p.n_win) * n_tok + row) * n_tok + col];
-                if (col >= n_tok) v = PAD_MARK;
-                s[t][c] = v;
-                if (c < 2) mx0 = v > mx0 ? v : mx0; else mx1 = v > mx1 ? v : mx1;
             }
+            mx0 = max(mx0, max(v[0], v[1]));
+            mx1 = max(mx1, max(v[2], v[3]));
+            sv[t] = (uint32_t)(v[0] & 0xff) | ((uint32_t)(v[1] & 0xff) << 8) | ((uint32_t)(v[2] & 0xff) << 16) | ((uint32_t)v[3] << 24);
+        }
+        // padding columns hold requant(0) = 0 here, which may exceed the true row max: recompute the max
+        // over valid columns only when the tile straddles n_tok (cheap: at most NT compares per element)
+        {
+            int32_t m0 = -128, m1 = -128;
+#pragma unroll
+            for (int t = 0; t < NT; ++t) {
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const bool pad = (8 * t + (c & 1)) >= col_lim;
+                    const int32_t v = (int32_t)(int8_t)((sv[t] >> (8 * c)) & 0xff);
+                    if (!pad) { if (c < 2) m0 = max(m0, v); else m1 = max(m1, v); }
+                }
+            }
+            mx0 = m0; mx1 = m1;
         }
         mx0 = max(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = max(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
         mx1 = max(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = max(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
-        // ---- exponentials (LUT) and row sums ----
+        // ---- exponentials (LUT over max - q) and row sums ----
+        auto expo = [&](int t, int c) -> uint32_t {
+            if ((8 * t + (c & 1)) >= col_lim) return 0u;
+            if (p.mask != nullptr && ((masked[t / 8] >> (4 * (t % 8) + c)) & 1u)) return e_sat;
+            const int32_t v = (int32_t)(int8_t)((sv[t] >> (8 * c)) & 0xff);
+            return (uint32_t)sE[((c < 2) ? mx0 : mx1) - v];
+        };
         unsigned long long sum0 = 0, sum1 = 0;
 #pragma unroll
         for (int t = 0; t < NT; ++t) {
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                const int32_t v = s[t][c];
-                int32_t E = 0;
-                if (v != PAD_MARK) {
-                    int k = ((c < 2) ? mx0 : mx1) - v;
-                    // k > 255 only for masked Swin entries (addend RNE(-100/s)); those are always past the
-                    // saturation point t <= n*x0 when s < 0.35, checked by the caller
-                    k = k > 255 ? 256 : k;
-                    E = sE[k];
-                }
-                s[t][c] = E;
-                if (c < 2) sum0 += (uint32_t)E; else sum1 += (uint32_t)E;
-            }
+            sum0 += (unsigned long long)expo(t, 0) + expo(t, 1);
+            sum1 += (unsigned long long)expo(t, 2) + expo(t, 3);
         }
         sum0 += __shfl_xor_sync(0xffffffffu, sum0, 1); sum0 += __shfl_xor_sync(0xffffffffu, sum0, 2);
         sum1 += __shfl_xor_sync(0xffffffffu, sum1, 1); sum1 += __shfl_xor_sync(0xffffffffu, sum1, 2);
@@ -171,7 +194,7 @@ attention_kernel(const int8_t* __restrict__ qkv, const AttnArgs p, int8_t* __res
         const uint32_t F0 = 2147483647u / (S0 ? S0 : 1u);
         const uint32_t F1 = 2147483647u / (S1 ? S1 : 1u);
 
-        // ---- O = P V with P = (E * F) >> p_shift, hi/lo byte planes ----
+        // ---- O = P V with P = (E * F) >> p_shift (E*F <= S*F < 2^31: 32-bit product), hi/lo byte planes ----
         int32_t ohi[ND][4], olo[ND][4];
 #pragma unroll
         for (int nd = 0; nd < ND; ++nd) {
@@ -184,19 +207,16 @@ attention_kernel(const int8_t* __restrict__ qkv, const AttnArgs p, int8_t* __res
             uint32_t alo[4], ahi[4];
 #pragma unroll
             for (int r = 0; r < 4; ++r) {
-                // fragment register r: rows (r&1 ? r1 : r0), tiles (4kc + (r>>1)*2 + {0,1}), columns {0,1} of each
+                // fragment register r: rows (r&1 ? r1 : r0), tiles 4kc + (r>>1)*2 + {0,1}, columns {0,1} of each
                 const int tA = 4 * kc + (r >> 1) * 2;
                 const int cb = (r & 1) * 2;
                 const uint32_t F = (r & 1) ? F1 : F0;
-                uint32_t lo = 0, hi = 0;
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const uint32_t E = (uint32_t)s[tA + (e >> 1)][cb + (e & 1)];
-                    const uint32_t P = (uint32_t)(((unsigned long long)E * (unsigned long long)F) >> p.p_shift);
-                    lo |= (P & 0xffu) << (8 * e);
-                    hi |= ((P >> 8) & 0xffu) << (8 * e);
-                }
-                alo[r] = lo; ahi[r] = hi;
+                const uint32_t P0 = (expo(tA, cb) * F) >> p.p_shift;
+                const uint32_t P1 = (expo(tA, cb + 1) * F) >> p.p_shift;
+                const uint32_t P2 = (expo(tA + 1, cb) * F) >> p.p_shift;
+                const uint32_t P3 = (expo(tA + 1, cb + 1) * F) >> p.p_shift;
+                alo[r] = __byte_perm(__byte_perm(P0, P1, 0x0040), __byte_perm(P2, P3, 0x0040), 0x5410);
+                ahi[r] = __byte_perm(__byte_perm(P0, P1, 0x0051), __byte_perm(P2, P3, 0x0051), 0x5410);
             }
 #pragma unroll
             for (int nd = 0; nd < ND; ++nd) {
@@ -215,8 +235,8 @@ attention_kernel(const int8_t* __restrict__ qkv, const AttnArgs p, int8_t* __res
                 if (row < n_tok) {
                     const int32_t v0 = (ohi[nd][2 * half] << 8) + olo[nd][2 * half];
                     const int32_t v1 = (ohi[nd][2 * half + 1] << 8) + olo[nd][2 * half + 1];
-                    const int32_t o0 = clamp_bits<8>(requant32(v0, p.me_o.m, p.me_o.e));
-                    const int32_t o1 = clamp_bits<8>(requant32(v1, p.me_o.m, p.me_o.e));
+                    const int32_t o0 = clamp_bits<8>(unirq_apply(rq_o, v0));
+                    const int32_t o1 = clamp_bits<8>(unirq_apply(rq_o, v1));
                     int8_t* dst = out + ((long long)b * n_tok + row) * (long long)(p.H * D) + h * D + 8 * nd + 2 * q4;
                     *reinterpret_cast<uint16_t*>(dst) = (uint16_t)((o0 & 0xff) | ((o1 & 0xff) << 8));
                 }

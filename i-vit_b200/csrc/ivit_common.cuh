@@ -65,6 +65,28 @@ IVIT_DEVINL int32_t requant32_e32(int32_t z, int32_t m, int32_t e) {
     return q;
 }
 
+// A scalar (kernel-uniform) dyadic applied to operands with |z| < 2^zbits.
+struct UniRq {
+    int32_t m, e;
+    long long half;
+    int fast;                         // 16 <= e <= 62 and exact ties unreachable -> branch-free form
+};
+IVIT_DEVINL UniRq make_unirq(ivit_dyadic_t d, int zbits) {
+    UniRq u;
+    u.m = d.m; u.e = d.e;
+    u.half = (d.e >= 1 && d.e <= 62) ? (1LL << (d.e - 1)) : 0;
+    const int tz = __ffs(d.m) - 1;
+    u.fast = (d.e >= 16 && d.e <= 62 && d.m != 0 && (d.e - 1 - tz > zbits)) ? 1 : 0;
+    return u;
+}
+IVIT_DEVINL int32_t unirq_apply(const UniRq& u, int32_t z) {
+    if (u.fast) {                                                  // uniform branch
+        const long long t = (long long)z * (long long)u.m + u.half;
+        return (u.e >= 32) ? ((int32_t)(t >> 32) >> (u.e - 32)) : (int32_t)(t >> u.e);
+    }
+    return sat_i64_to_i32(requant64((long long)z, u.m, u.e));
+}
+
 template <int BITS>
 IVIT_DEVINL int32_t clamp_bits(int32_t v) {
     constexpr int32_t hi = (BITS >= 32) ? 2147483647 : ((1 << (BITS - 1)) - 1);
@@ -103,6 +125,23 @@ IVIT_DEVINL long long shiftexp(int32_t d, int32_t x0, float inv_x0, int n) {
     const int sh = n - k - 1;
     long long E = (sh >= 0) ? ((long long)base << (sh > 46 ? 46 : sh)) : (long long)(base >> 1);
     return E;
+}
+
+// IntLayerNorm's integer square root: k = 2^16; 10x k = floor((k + floor(V/k)) / 2)   quant_modules.py:366-370
+// (exactly 10 steps, no early exit).  For V < 2^52 the 64-bit division is done in fp64: V and k are exact
+// doubles, IEEE division is correctly rounded, and a non-integer quotient V/k is at least 1/k >= 2^-26 away
+// from the next integer while the rounding error is below 2^-52 * 2^36, so truncation gives the exact floor.
+IVIT_DEVINL unsigned long long ln_isqrt10(unsigned long long V) {
+    unsigned long long k = 65536ULL;
+    if (V < (1ULL << 52)) {
+        const double Vd = (double)V;
+#pragma unroll 1
+        for (int it = 0; it < 10; ++it) k = (k + (unsigned long long)(Vd / (double)k)) >> 1;
+    } else {
+#pragma unroll 1
+        for (int it = 0; it < 10; ++it) k = (k + V / k) >> 1;
+    }
+    return k;
 }
 
 // floor((2^31-1) / S) for 1 <= S <= 2^31-1     quant_modules.py:438, 492

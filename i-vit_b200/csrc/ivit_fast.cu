@@ -1,0 +1,227 @@
+// Bandwidth-oriented specialisations of the row operators for the fused engine (sm_100a).
+//
+// The general kernels of ivit_ops.cu evaluate the reference formulas element by element
+// (~100 integer instructions per element for ShiftGELU).  On the hot path the operands are
+// int8, so the expensive functions have tiny domains and become exact lookup tables:
+//
+//   ShiftGELU + mlp.qact1 (quant_modules.py:410-445, layers_quant.py:147-148):
+//       out = clamp8(RNE(q * sigma(q, rowmax) * m / 2^e))   depends only on (q, rowmax) in int8 x int8
+//       -> 64 KB table per layer built ONCE on the device with the general formula
+//          (ivit_shiftgelu_build_lut), applied with one shared-memory byte lookup per element
+//          (ivit_shiftgelu_lut): the kernel is HBM-bound (1 B read + 1 B written per element).
+//
+//   IntLayerNorm + QuantAct (quant_modules.py:353-386): int16 rows -> int8, 16-byte vector
+//       loads, per-channel constants (bias, m, e) held in registers across the rows a warp
+//       processes (a lane always owns the same channels).
+#include "ivit_common.cuh"
+#include "ivit_internal.h"
+
+namespace ivit {
+
+// ------------------------------------------------------------------------------------
+// LUT construction: lut[(mx+128)*256 + (q+128)] for -128 <= q <= mx <= 127 (q > mx unused -> 0)
+// ------------------------------------------------------------------------------------
+__global__ void gelu_lut_build_kernel(int32_t x0, float inv_x0, int n, const ivit_dyadic_t* __restrict__ me,
+                                      int bits, int8_t* __restrict__ lut) {
+    const int mx = (int)blockIdx.x - 128;
+    const int q = (int)threadIdx.x - 128;
+    const ivit_dyadic_t d = me[0];
+    int32_t o = 0;
+    if (q <= mx) {
+        const long long Em = shiftexp(-mx, x0, inv_x0, n);
+        const long long E = shiftexp(q - mx, x0, inv_x0, n);
+        long long S = E + Em;
+        S = S > 2147483647LL ? 2147483647LL : S;
+        const long long F = 2147483647LL / S;
+        const long long sig = (E * F) >> (31 - 8 + 1);
+        o = clamp_i64_bits(requant64((long long)q * sig, d.m, d.e), bits);
+    }
+    lut[blockIdx.x * 256 + threadIdx.x] = (int8_t)o;
+}
+
+// ------------------------------------------------------------------------------------
+// LUT application.  One warp per row; the row lives in registers as 16-byte vectors.
+// ------------------------------------------------------------------------------------
+template <int MAXV>
+__global__ void __launch_bounds__(256)
+gelu_lut_apply_kernel(const int8_t* __restrict__ q, int64_t rows, int cols, const int8_t* __restrict__ lut,
+                      int8_t* __restrict__ out) {
+    __shared__ __align__(16) uint8_t s_lut[8][256];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int nvec = cols >> 4;
+    const int64_t warp0 = (int64_t)blockIdx.x * 8 + w;
+    const int64_t nwarps = (int64_t)gridDim.x * 8;
+    for (int64_t row = warp0; row < rows; row += nwarps) {
+        const uint4* src = reinterpret_cast<const uint4*>(q + row * (int64_t)cols);
+        uint4 v[MAXV];
+        uint32_t mxw = 0x80808080u;                              // four int8 -128
+#pragma unroll
+        for (int j = 0; j < MAXV; ++j) {
+            const int vi = lane + 32 * j;
+            if (vi < nvec) {
+                v[j] = __ldg(src + vi);
+                mxw = __vmaxs4(mxw, v[j].x); mxw = __vmaxs4(mxw, v[j].y);
+                mxw = __vmaxs4(mxw, v[j].z); mxw = __vmaxs4(mxw, v[j].w);
+            }
+        }
+        int32_t mx = max(max((int32_t)(int8_t)(mxw & 0xff), (int32_t)(int8_t)((mxw >> 8) & 0xff)),
+                         max((int32_t)(int8_t)((mxw >> 16) & 0xff), (int32_t)(int8_t)(mxw >> 24)));
+        mx = warp_max_i32(mx);
+        __syncwarp();
+        // this row's 256-byte table line -> shared memory (8 bytes per lane)
+        reinterpret_cast<uint2*>(s_lut[w])[lane] = __ldg(reinterpret_cast<const uint2*>(lut + (mx + 128) * 256) + lane);
+        __syncwarp();
+        const uint8_t* tl = s_lut[w];
+        uint4* dst = reinterpret_cast<uint4*>(out + row * (int64_t)cols);
+#pragma unroll
+        for (int j = 0; j < MAXV; ++j) {
+            const int vi = lane + 32 * j;
+            if (vi < nvec) {
+                uint32_t in[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
+                uint32_t o[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const uint32_t x = in[u] ^ 0x80808080u;       // q + 128 per byte
+                    o[u] = (uint32_t)tl[x & 0xff] | ((uint32_t)tl[(x >> 8) & 0xff] << 8) |
+                           ((uint32_t)tl[(x >> 16) & 0xff] << 16) | ((uint32_t)tl[x >> 24] << 24);
+                }
+                dst[vi] = make_uint4(o[0], o[1], o[2], o[3]);
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// LayerNorm int16 -> int8 with the per-channel QuantAct fused.  C = 8 * NV * 32 at most.
+// ------------------------------------------------------------------------------------
+template <int NV>
+__global__ void __launch_bounds__(256)
+layernorm_i16_i8_kernel(const int16_t* __restrict__ x, int64_t rows, int C, const int32_t* __restrict__ bias_int,
+                        const ivit_dyadic_t* __restrict__ me, int8_t* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int nvec = C >> 3;                                     // vectors of 8 int16
+    const int64_t warp0 = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int64_t nwarps = (int64_t)gridDim.x * 8;
+    // per-channel constants (bias, m, e) staged once per block in shared memory
+    __shared__ __align__(16) int32_t s_b[1024], s_m[1024], s_e[1024];
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        s_b[c] = bias_int[c];
+        const ivit_dyadic_t d = me[c];
+        s_m[c] = d.m; s_e[c] = d.e;
+    }
+    __syncthreads();
+    for (int64_t row = warp0; row < rows; row += nwarps) {
+        const uint4* src = reinterpret_cast<const uint4*>(x + row * (int64_t)C);
+        int32_t y[NV][8];
+        int32_t sum = 0;                                         // |sum| <= 2048 * 32768 < 2^31
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+            const int vi = lane + 32 * j;
+            uint4 t = make_uint4(0, 0, 0, 0);
+            if (vi < nvec) t = __ldg(src + vi);
+            const uint32_t tw[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                y[j][2 * u] = (int32_t)(int16_t)(tw[u] & 0xffff);
+                y[j][2 * u + 1] = (int32_t)(int16_t)(tw[u] >> 16);
+                sum += y[j][2 * u] + y[j][2 * u + 1];
+            }
+        }
+        sum = warp_sum_i32(sum);
+        // mu = RNE(sum / C)
+        int32_t qd = sum / C, rem = sum % C;
+        if (rem < 0) { qd -= 1; rem += C; }
+        if (2 * rem > C || (2 * rem == C && (qd & 1))) qd += 1;
+        const int32_t mu = qd;
+        unsigned long long V = 0;
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+            const bool ok = (lane + 32 * j) < nvec;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int32_t d = ok ? y[j][u] - mu : 0;
+                y[j][u] = d;
+                V += (unsigned long long)((long long)d * d);
+            }
+        }
+        V = (unsigned long long)warp_sum_i64((long long)V);
+        const unsigned long long k = ln_isqrt10(V);
+        const int32_t F = (int32_t)(2147483647ULL / k);          // <= 2^31/64
+        uint2* dst = reinterpret_cast<uint2*>(out + row * (int64_t)C);
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+            const int vi = lane + 32 * j;
+            if (vi < nvec) {
+                uint32_t b[8];
+                int32_t cb[8], cm[8], ce[8];
+                *reinterpret_cast<int4*>(cb) = *reinterpret_cast<const int4*>(s_b + vi * 8);
+                *reinterpret_cast<int4*>(cb + 4) = *reinterpret_cast<const int4*>(s_b + vi * 8 + 4);
+                *reinterpret_cast<int4*>(cm) = *reinterpret_cast<const int4*>(s_m + vi * 8);
+                *reinterpret_cast<int4*>(cm + 4) = *reinterpret_cast<const int4*>(s_m + vi * 8 + 4);
+                *reinterpret_cast<int4*>(ce) = *reinterpret_cast<const int4*>(s_e + vi * 8);
+                *reinterpret_cast<int4*>(ce + 4) = *reinterpret_cast<const int4*>(s_e + vi * 8 + 4);
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    long long o = (((long long)y[j][u] * (long long)F) >> 1) + (long long)cb[u];
+                    o = o > 2147483647LL ? 2147483647LL : (o < -2147483648LL ? -2147483648LL : o);
+                    const int32_t e = ce[u];
+                    int32_t r;
+                    if (e >= 32 && e <= 62) r = requant32_e32((int32_t)o, cm[u], e);
+                    else r = requant32((int32_t)o, cm[u], e);
+                    b[u] = (uint32_t)(clamp_bits<8>(r) & 0xff);
+                }
+                dst[vi] = make_uint2(b[0] | (b[1] << 8) | (b[2] << 16) | (b[3] << 24),
+                                     b[4] | (b[5] << 8) | (b[6] << 16) | (b[7] << 24));
+            }
+        }
+    }
+}
+
+}  // namespace ivit
+
+using namespace ivit;
+
+extern "C" {
+
+int ivit_shiftgelu_build_lut(ivit_ctx* ctx, int32_t x0, int n, const ivit_dyadic_t* me, int bits, int8_t* lut,
+                             ivit_stream stream) {
+    IVIT_REQUIRE(ctx && me && lut, "ivit_shiftgelu_build_lut: null pointer");
+    IVIT_REQUIRE(bits == 8, "ivit_shiftgelu_build_lut: the table holds int8 outputs (bits == 8)");
+    IVIT_REQUIRE(n >= 1 && n <= 30, "ivit_shiftgelu_build_lut: bad n");
+    if (!(x0 <= -8 && x0 >= -65536))
+        return fail(IVIT_ENOTSUP, "ivit_shiftgelu_build_lut: x0=%d outside the supported domain [-65536, -8]", x0);
+    gelu_lut_build_kernel<<<256, 256, 0, st(stream)>>>(x0, 1.0f / (float)x0, n, me, bits, lut);
+    IVIT_LAUNCH_OK("gelu_lut_build_kernel");
+    return IVIT_OK;
+}
+
+int ivit_shiftgelu_lut(ivit_ctx* ctx, const int8_t* q, int64_t rows, int cols, const int8_t* lut, int8_t* out,
+                       ivit_stream stream) {
+    IVIT_REQUIRE(ctx && q && lut && out && rows > 0 && cols > 0, "ivit_shiftgelu_lut: bad arguments");
+    IVIT_REQUIRE(cols % 16 == 0 && cols <= 16 * 32 * 8, "ivit_shiftgelu_lut: cols must be a multiple of 16, <= 4096");
+    IVIT_REQUIRE(((uintptr_t)q % 16) == 0 && ((uintptr_t)out % 16) == 0 && ((uintptr_t)lut % 8) == 0,
+                 "ivit_shiftgelu_lut: q/out must be 16-byte aligned");
+    const int grid = (int)((rows + 7) / 8 < (int64_t)ctx->num_sms * 8 ? (rows + 7) / 8 : (int64_t)ctx->num_sms * 8);
+    const int nv = (cols / 16 + 31) / 32;
+#define GL(MAXV) gelu_lut_apply_kernel<MAXV><<<grid, 256, 0, st(stream)>>>(q, rows, cols, lut, out)
+    if (nv <= 2) GL(2); else if (nv <= 4) GL(4); else if (nv <= 6) GL(6); else GL(8);
+#undef GL
+    IVIT_LAUNCH_OK("gelu_lut_apply_kernel");
+    return IVIT_OK;
+}
+
+int ivit_layernorm_i16_i8(ivit_ctx* ctx, const int16_t* x, int64_t rows, int C, const int32_t* bias_int,
+                          const ivit_dyadic_t* me, int8_t* out, ivit_stream stream) {
+    IVIT_REQUIRE(ctx && x && bias_int && me && out && rows > 0, "ivit_layernorm_i16_i8: bad arguments");
+    IVIT_REQUIRE(C % 8 == 0 && C >= 8 && C <= 8 * 32 * 4, "ivit_layernorm_i16_i8: C must be a multiple of 8, <= 1024");
+    IVIT_REQUIRE(((uintptr_t)x % 16) == 0 && ((uintptr_t)out % 8) == 0, "ivit_layernorm_i16_i8: x must be 16-byte aligned");
+    const int grid = (int)((rows + 7) / 8 < (int64_t)ctx->num_sms * 4 ? (rows + 7) / 8 : (int64_t)ctx->num_sms * 4);
+    const int nv = (C / 8 + 31) / 32;
+#define LNF(NV) layernorm_i16_i8_kernel<NV><<<grid, 256, 0, st(stream)>>>(x, rows, C, bias_int, me, out)
+    if (nv <= 1) LNF(1); else if (nv <= 2) LNF(2); else if (nv <= 3) LNF(3); else LNF(4);
+#undef LNF
+    IVIT_LAUNCH_OK("layernorm_i16_i8_kernel");
+    return IVIT_OK;
+}
+
+}  // extern "C"

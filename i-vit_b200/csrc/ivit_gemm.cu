@@ -45,18 +45,136 @@ struct GemmArgs {
 };
 
 struct alignas(16) ColParam {         // per output column, staged in shared memory per tile
-    int32_t bias;
-    int32_t m;
-    int32_t e;
-    float scale;
+    int32_t m;                        // dyadic multiplier (or the fp32 scale bits for GM_CARRIER)
+    int32_t sh;                       // e - 32
+    long long c;                      // bias*m + 2^(e-1): the fast requant is hi32(acc*m + c) >> sh
 };
+
+__device__ __forceinline__ uint32_t pack_sat_s8x4(int32_t a, int32_t b, int32_t c, int32_t d) {
+    uint32_t hi, r;
+    asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, %3;" : "=r"(hi) : "r"(d), "r"(c), "r"(0));
+    asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(b), "r"(a), "r"(hi));
+    return r;                                                      // a | b<<8 | c<<16 | d<<24, each saturated to int8
+}
+__device__ __forceinline__ uint32_t pack_sat_s16x2(int32_t lo, int32_t hi) {
+    uint32_t r;
+    asm("cvt.pack.sat.s16.s32 %0, %1, %2;" : "=r"(r) : "r"(hi), "r"(lo));
+    return r;
+}
+
+// One 32-column chunk of one output row: registers r[] hold the int32 accumulators.
+template <int MODE>
+__device__ __forceinline__ void epilogue_chunk(const uint32_t (&r)[32], const ColParam* __restrict__ cp,
+                                               const int32_t* __restrict__ cb, const GemmArgs& args, int row,
+                                               bool row_ok, int ncol0, bool fast, const UniRq& rq2, const UniRq& rqr) {
+    const bool full_chunk = (ncol0 + 32 <= args.N);
+    if (MODE == GM_RAW_I32 || MODE == GM_CARRIER) {
+        uint32_t o[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            const int32_t v = (int32_t)r[j] + cb[j];
+            o[j] = (MODE == GM_RAW_I32) ? (uint32_t)v : __float_as_uint(__fmul_rn(__int2float_rn(v), __int_as_float(cp[j].m)));
+        }
+        if (!row_ok) return;
+        uint32_t* dst = reinterpret_cast<uint32_t*>(args.out) + (long long)row * args.out_ld + ncol0;
+        if (full_chunk && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) *reinterpret_cast<uint4*>(dst + j) = make_uint4(o[j], o[j + 1], o[j + 2], o[j + 3]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+                if (ncol0 + j < args.N) dst[j] = o[j];
+        }
+        return;
+    }
+    // ---- first-stage per-channel requant: q = RNE((acc + bias) * m / 2^e) ----
+    int32_t q[32];
+    if (fast) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            const ColParam p = cp[j];
+            const long long t = (long long)(int32_t)r[j] * (long long)p.m + p.c;
+            q[j] = (int32_t)(t >> 32) >> p.sh;
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            const ColParam p = cp[j];
+            q[j] = requant32((int32_t)r[j] + cb[j], p.m, p.sh + 32);
+        }
+    }
+    if (MODE == GM_RQ_I8) {
+        if (!row_ok) return;
+        int8_t* dst = reinterpret_cast<int8_t*>(args.out) + (long long)row * args.out_ld + ncol0;
+        if (full_chunk && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+            uint32_t w[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) w[j] = pack_sat_s8x4(q[4 * j], q[4 * j + 1], q[4 * j + 2], q[4 * j + 3]);
+            *reinterpret_cast<uint4*>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
+            *reinterpret_cast<uint4*>(dst + 16) = make_uint4(w[4], w[5], w[6], w[7]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+                if (ncol0 + j < args.N) dst[j] = (int8_t)clamp_bits<8>(q[j]);
+        }
+        return;
+    }
+    // ---- GM_RQ_I16: optional second (scalar) stage and int16 residual ----
+    //   single stage: clamp(RNE(z*me) + RNE(res*res_me))       one QuantAct with identity
+    //   two stage   : q1 = clamp(RNE(z*me)) is a QuantAct output; a second QuantAct adds the residual
+    //                 (attn.qact3 -> Block.qact2, mlp.qact2 -> Block.qact4; vit_quant.py:85,135,141)
+    if (!row_ok) return;
+    int16_t* dst = reinterpret_cast<int16_t*>(args.out) + (long long)row * args.out_ld + ncol0;
+    const int16_t* res = args.residual
+        ? reinterpret_cast<const int16_t*>(args.residual) + (long long)row * args.res_ld + ncol0 : nullptr;
+    const bool vec = full_chunk && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) &&
+                     (!res || ((reinterpret_cast<uintptr_t>(res) & 15) == 0));
+    int32_t rv[32];
+    if (res) {
+        if (vec) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+                const uint4 t = __ldg(reinterpret_cast<const uint4*>(res + j));
+                const uint32_t tw[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    rv[j + 2 * u] = (int32_t)(int16_t)(tw[u] & 0xffff);
+                    rv[j + 2 * u + 1] = (int32_t)tw[u] >> 16;
+                }
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) rv[j] = (ncol0 + j < args.N) ? (int32_t)res[j] : 0;
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+        int32_t v = q[j];
+        if (args.two_stage) v = unirq_apply(rq2, clamp_bits_rt(v, args.mode_bits));
+        if (res) {
+            const long long s = (long long)v + (long long)unirq_apply(rqr, rv[j]);
+            v = sat_i64_to_i32(s);
+        }
+        q[j] = v;
+    }
+    if (vec && args.mode_bits == 16) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 8)
+            *reinterpret_cast<uint4*>(dst + j) = make_uint4(pack_sat_s16x2(q[j], q[j + 1]), pack_sat_s16x2(q[j + 2], q[j + 3]),
+                                                            pack_sat_s16x2(q[j + 4], q[j + 5]), pack_sat_s16x2(q[j + 6], q[j + 7]));
+    } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+            if (ncol0 + j < args.N) dst[j] = (int16_t)clamp_bits_rt(q[j], args.mode_bits);
+    }
+}
 
 template <int BN, int STAGES>
 struct GemmSmem {
     static constexpr int A_BYTES = GEMM_BM * GEMM_BK;
     static constexpr int B_BYTES = BN * GEMM_BK;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int PARAM_BYTES = 2 * BN * (int)sizeof(ColParam);
+    static constexpr int PARAM_BYTES = 2 * BN * ((int)sizeof(ColParam) + 4);   // ColParam[2][BN] + int32 bias[2][BN]
     static constexpr int BAR_BYTES = 256;
     static constexpr int TOTAL = STAGES * STAGE_BYTES + PARAM_BYTES + BAR_BYTES + 1024;  // +1024 alignment slack
 };
@@ -73,6 +191,7 @@ gemm_i8_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
 
     const uint32_t stage_base = smem_base;
     ColParam* col_params = reinterpret_cast<ColParam*>(smem + STAGES * S::STAGE_BYTES);
+    int32_t* col_bias = reinterpret_cast<int32_t*>(col_params + 2 * BN);
     const uint32_t bar_base = smem_base + STAGES * S::STAGE_BYTES + S::PARAM_BYTES;
     // barrier layout (8 B each): full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], then tmem ptr + flags
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
@@ -168,13 +287,17 @@ gemm_i8_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
         const int ew = warp - 2;                      // 0..3
         const int lane_group = warp & 3;              // TMEM lanes [32*lane_group, +32) are accessible to this warp
         const int et = ew * 32 + lane;                // 0..127 thread index inside the epilogue group
+        // kernel-uniform properties of the scalar second stage / residual dyadics (GM_RQ_I16)
+        const UniRq rq2 = make_unirq(args.me2, 15);
+        const UniRq rqr = make_unirq(args.res_me, 15);
         int as = 0;
         uint32_t aphase = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
             const int m0 = (tile / tiles_n) * GEMM_BM;
             const int n0 = (tile % tiles_n) * BN;
             ColParam* cp = col_params + as * BN;
-            // stage the per-column constants of this tile (coalesced global reads)
+            int32_t* cb = col_bias + as * BN;
+            // ---- stage the per-column constants of this tile (coalesced global reads) ----
             if (et == 0) fast_flag[as] = 1;
             asm volatile("bar.sync 1, 128;" ::: "memory");
             {
@@ -182,17 +305,25 @@ gemm_i8_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
                 for (int c = et; c < BN; c += 128) {
                     const int n = n0 + c;
                     ColParam p;
-                    p.bias = 0; p.m = 0; p.e = 63; p.scale = 0.f;
+                    p.m = 0; p.sh = 31; p.c = 0;
+                    int32_t b = 0;
                     if (n < args.N) {
-                        if (args.bias) p.bias = args.bias[n];
+                        if (args.bias) b = args.bias[n];
                         if (MODE == GM_RQ_I8 || MODE == GM_RQ_I16) {
                             const ivit_dyadic_t d = args.me[n];
-                            p.m = d.m; p.e = d.e;
-                            ok &= (d.e >= 32 && d.e <= 62);
+                            p.m = d.m; p.sh = d.e - 32;
+                            // fast form: t = acc*m + (bias*m + 2^(e-1)); q = hi32(t) >> (e-32).  Needs
+                            // 32 <= e <= 62 and no reachable exact tie (|z| < 2^31: v2(z*m) <= 30 + ctz(m) < e-1)
+                            const int tz = __ffs(d.m) - 1;
+                            const bool f = (d.e >= 32 && d.e <= 62) && (d.e - 1 - tz > 31);
+                            ok &= f ? 1 : 0;
+                            if (d.e >= 1 && d.e <= 62) p.c = (long long)b * (long long)d.m + (1LL << (d.e - 1));
+                        } else if (MODE == GM_CARRIER) {
+                            p.m = __float_as_int(args.scale[n]);
                         }
-                        if (MODE == GM_CARRIER) p.scale = args.scale[n];
                     }
                     cp[c] = p;
+                    cb[c] = b;
                 }
                 if (!ok) atomicAnd(&fast_flag[as], 0);
             }
@@ -205,123 +336,21 @@ gemm_i8_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
             const int row = m0 + lane_group * 32 + lane;
             const bool row_ok = row < args.M;
             const uint32_t t_row = tmem_base + ((uint32_t)(lane_group * 32) << 16) + (uint32_t)(as * BN);
-#pragma unroll 1
-            for (int c0 = 0; c0 < BN; c0 += 32) {
-                uint32_t r[32];
-                ptx::tmem_ld_32x32b_x32(t_row + (uint32_t)c0, r);
-                ptx::tmem_ld_wait();
-                const int ncol0 = n0 + c0;
-                if (ncol0 >= args.N) break;            // uniform: whole chunk out of range
-                const bool full_chunk = (ncol0 + 32 <= args.N);
+            const int n_chunks = min(BN, args.N - n0 + 31) / 32;      // chunks that contain at least one valid column
 
-                if (MODE == GM_RAW_I32 || MODE == GM_CARRIER) {
-                    uint32_t o[32];
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const ColParam p = cp[c0 + j];
-                        const int32_t v = (int32_t)r[j] + p.bias;
-                        o[j] = (MODE == GM_RAW_I32) ? (uint32_t)v : __float_as_uint(__fmul_rn(__int2float_rn(v), p.scale));
-                    }
-                    if (row_ok) {
-                        uint32_t* dst = reinterpret_cast<uint32_t*>(args.out) + (long long)row * args.out_ld + ncol0;
-                        if (full_chunk && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
-#pragma unroll
-                            for (int j = 0; j < 32; j += 4)
-                                *reinterpret_cast<uint4*>(dst + j) = make_uint4(o[j], o[j + 1], o[j + 2], o[j + 3]);
-                        } else {
-#pragma unroll
-                            for (int j = 0; j < 32; ++j)
-                                if (ncol0 + j < args.N) dst[j] = o[j];
-                        }
-                    }
-                } else {
-                    int32_t q[32];
-                    if (fast) {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            const ColParam p = cp[c0 + j];
-                            q[j] = requant32_e32((int32_t)r[j] + p.bias, p.m, p.e);
-                        }
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            const ColParam p = cp[c0 + j];
-                            q[j] = requant32((int32_t)r[j] + p.bias, p.m, p.e);
-                        }
-                    }
-                    if (MODE == GM_RQ_I8) {
-                        if (row_ok) {
-                            int8_t* dst = reinterpret_cast<int8_t*>(args.out) + (long long)row * args.out_ld + ncol0;
-                            if (full_chunk && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
-                                uint32_t w[8];
-#pragma unroll
-                                for (int j = 0; j < 8; ++j) {
-                                    const uint32_t b0 = (uint32_t)(clamp_bits<8>(q[4 * j + 0]) & 0xff);
-                                    const uint32_t b1 = (uint32_t)(clamp_bits<8>(q[4 * j + 1]) & 0xff);
-                                    const uint32_t b2 = (uint32_t)(clamp_bits<8>(q[4 * j + 2]) & 0xff);
-                                    const uint32_t b3 = (uint32_t)(clamp_bits<8>(q[4 * j + 3]) & 0xff);
-                                    w[j] = b0 | (b1 << 8) | (b2 << 16) | (b3 << 24);
-                                }
-                                *reinterpret_cast<uint4*>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
-                                *reinterpret_cast<uint4*>(dst + 16) = make_uint4(w[4], w[5], w[6], w[7]);
-                            } else {
-#pragma unroll
-                                for (int j = 0; j < 32; ++j)
-                                    if (ncol0 + j < args.N) dst[j] = (int8_t)clamp_bits<8>(q[j]);
-                            }
-                        }
-                    } else {  // GM_RQ_I16 (+ optional residual / two-stage)
-                        if (row_ok) {
-                            int16_t* dst = reinterpret_cast<int16_t*>(args.out) + (long long)row * args.out_ld + ncol0;
-                            const int16_t* res = args.residual
-                                ? reinterpret_cast<const int16_t*>(args.residual) + (long long)row * args.res_ld + ncol0 : nullptr;
-                            const bool vec = full_chunk && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) &&
-                                             (!res || ((reinterpret_cast<uintptr_t>(res) & 15) == 0));
-                            int32_t rv[32];
-                            if (res) {
-                                if (vec) {
-#pragma unroll
-                                    for (int j = 0; j < 32; j += 8) {
-                                        const uint4 t = *reinterpret_cast<const uint4*>(res + j);
-                                        const uint32_t tw[4] = {t.x, t.y, t.z, t.w};
-#pragma unroll
-                                        for (int u = 0; u < 4; ++u) {
-                                            rv[j + 2 * u] = (int32_t)(int16_t)(tw[u] & 0xffff);
-                                            rv[j + 2 * u + 1] = (int32_t)(int16_t)(tw[u] >> 16);
-                                        }
-                                    }
-                                } else {
-#pragma unroll
-                                    for (int j = 0; j < 32; ++j) rv[j] = (ncol0 + j < args.N) ? (int32_t)res[j] : 0;
-                                }
-                            }
-#pragma unroll
-                            for (int j = 0; j < 32; ++j) {
-                                // single stage: clamp(RNE(z*me) + RNE(res*res_me)) -- one QuantAct with identity;
-                                // two stage: q1 = clamp(RNE(z*me)) is itself a QuantAct output, then a second
-                                // QuantAct adds the residual (vit_quant.py:85 then :135)
-                                int32_t v = q[j];
-                                if (args.two_stage) v = requant32(clamp_bits_rt(v, args.mode_bits), args.me2.m, args.me2.e);
-                                long long s = (long long)v;
-                                if (res) s += requant64((long long)rv[j], args.res_me.m, args.res_me.e);
-                                q[j] = clamp_i64_bits(s, args.mode_bits);
-                            }
-                            if (vec) {
-#pragma unroll
-                                for (int j = 0; j < 32; j += 8) {
-                                    uint32_t w[4];
-#pragma unroll
-                                    for (int u = 0; u < 4; ++u)
-                                        w[u] = ((uint32_t)q[j + 2 * u] & 0xffffu) | ((uint32_t)q[j + 2 * u + 1] << 16);
-                                    *reinterpret_cast<uint4*>(dst + j) = make_uint4(w[0], w[1], w[2], w[3]);
-                                }
-                            } else {
-#pragma unroll
-                                for (int j = 0; j < 32; ++j)
-                                    if (ncol0 + j < args.N) dst[j] = (int16_t)q[j];
-                            }
-                        }
-                    }
+            uint32_t ra[32], rb[32];
+            ptx::tmem_ld_32x32b_x32(t_row, ra);
+            ptx::tmem_ld_wait();
+#pragma unroll 1
+            for (int ch = 0; ch < n_chunks; ch += 2) {
+                if (ch + 1 < n_chunks) ptx::tmem_ld_32x32b_x32(t_row + (uint32_t)((ch + 1) * 32), rb);
+                epilogue_chunk<MODE>(ra, cp + ch * 32, cb + ch * 32, args, row, row_ok, n0 + ch * 32, fast, rq2, rqr);
+                ptx::tmem_ld_wait();
+                if (ch + 1 < n_chunks) {
+                    if (ch + 2 < n_chunks) ptx::tmem_ld_32x32b_x32(t_row + (uint32_t)((ch + 2) * 32), ra);
+                    epilogue_chunk<MODE>(rb, cp + (ch + 1) * 32, cb + (ch + 1) * 32, args, row, row_ok, n0 + (ch + 1) * 32,
+                                         fast, rq2, rqr);
+                    ptx::tmem_ld_wait();
                 }
             }
             // release the accumulator back to the MMA warp

@@ -25,6 +25,7 @@ inline int dtype_size(int dt) {
         case IVIT_I8: case IVIT_U8: return 1;
         case IVIT_I16: return 2;
         case IVIT_I32: case IVIT_F32: return 4;
+        case IVIT_F64: return 8;
         default: return 0;
     }
 }

@@ -87,6 +87,29 @@ __global__ void carrier_to_int_kernel(const float* __restrict__ x, int64_t n, in
     }
 }
 
+// fp64 carrier (IntLayerNorm outputs reach 2^30 and do not fit the 24-bit mantissa of an fp32
+// carrier; the reference's modules produce an fp64 carrier there when their input is exact)
+__global__ void carrier64_to_int_kernel(const double* __restrict__ x, int64_t n, int cols,
+                                        const float* __restrict__ s, int s_len, int out_dtype,
+                                        void* __restrict__ out) {
+    const double lim_hi = out_dtype == IVIT_I8 ? 127.0 : (out_dtype == IVIT_I16 ? 32767.0 : 2147483647.0);
+    const double lim_lo = out_dtype == IVIT_I8 ? -128.0 : (out_dtype == IVIT_I16 ? -32768.0 : -2147483648.0);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const double sc = (double)s[s_len == 1 ? 0 : (int)(i % cols)];
+        double v = rint(x[i] / sc);
+        v = fmin(fmax(v, lim_lo), lim_hi);
+        store_int(out, out_dtype, i, (int32_t)v);
+    }
+}
+
+__global__ void int_to_carrier64_kernel(const void* __restrict__ q, int q_dtype, int64_t n, int cols,
+                                        const float* __restrict__ s, int s_len, double* __restrict__ out) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const double sc = (double)s[s_len == 1 ? 0 : (int)(i % cols)];
+        out[i] = (double)load_int(q, q_dtype, i) * sc;
+    }
+}
+
 __global__ void int_to_carrier_kernel(const void* __restrict__ q, int q_dtype, int64_t n, int cols,
                                       const float* __restrict__ s, int s_len, float* __restrict__ out) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
@@ -159,9 +182,7 @@ layernorm_kernel(const void* __restrict__ x, int x_dtype, int64_t rows, int C,
         }
         V = (unsigned long long)warp_sum_i64((long long)V);
         // 10 integer Newton steps from 2^16     :366-370 (no early exit; V = 0 -> k = 64)
-        unsigned long long k = 65536ULL;
-#pragma unroll 1
-        for (int it = 0; it < 10; ++it) k = (k + V / k) >> 1;
+        const unsigned long long k = ln_isqrt10(V);
         const long long F = (long long)(2147483647ULL / k);      // :372
 #pragma unroll
         for (int j = 0; j < MAXV; ++j) {
@@ -333,24 +354,32 @@ int ivit_quantize_f32(ivit_ctx* ctx, const float* x, int64_t n, const float* sca
     return IVIT_OK;
 }
 
-int ivit_carrier_to_int(ivit_ctx* ctx, const float* x, int64_t rows, int cols, const float* s,
+int ivit_carrier_to_int(ivit_ctx* ctx, const void* x, int x_dtype, int64_t rows, int cols, const float* s,
                         int s_len, int out_dtype, void* out, ivit_stream stream) {
+    IVIT_REQUIRE(x_dtype == IVIT_F32 || x_dtype == IVIT_F64, "ivit_carrier_to_int: x_dtype must be F32 or F64");
     IVIT_REQUIRE(ctx && x && s && out && rows > 0 && cols > 0, "ivit_carrier_to_int: bad arguments");
     IVIT_REQUIRE(s_len == 1 || s_len == cols, "ivit_carrier_to_int: s_len must be 1 or cols");
     IVIT_REQUIRE(out_dtype == IVIT_I8 || out_dtype == IVIT_I16 || out_dtype == IVIT_I32, "ivit_carrier_to_int: bad out_dtype");
     const int64_t n = rows * cols;
-    carrier_to_int_kernel<<<grid_for(n, 256, ctx->num_sms), 256, 0, st(stream)>>>(x, n, cols, s, s_len, out_dtype, out);
+    if (x_dtype == IVIT_F32)
+        carrier_to_int_kernel<<<grid_for(n, 256, ctx->num_sms), 256, 0, st(stream)>>>((const float*)x, n, cols, s, s_len, out_dtype, out);
+    else
+        carrier64_to_int_kernel<<<grid_for(n, 256, ctx->num_sms), 256, 0, st(stream)>>>((const double*)x, n, cols, s, s_len, out_dtype, out);
     IVIT_LAUNCH_OK("carrier_to_int_kernel");
     return IVIT_OK;
 }
 
 int ivit_int_to_carrier(ivit_ctx* ctx, const void* q, int q_dtype, int64_t rows, int cols,
-                        const float* s, int s_len, float* out, ivit_stream stream) {
+                        const float* s, int s_len, int out_dtype, void* out, ivit_stream stream) {
+    IVIT_REQUIRE(out_dtype == IVIT_F32 || out_dtype == IVIT_F64, "ivit_int_to_carrier: out_dtype must be F32 or F64");
     IVIT_REQUIRE(ctx && q && s && out && rows > 0 && cols > 0, "ivit_int_to_carrier: bad arguments");
     IVIT_REQUIRE(s_len == 1 || s_len == cols, "ivit_int_to_carrier: s_len must be 1 or cols");
-    IVIT_REQUIRE(dtype_size(q_dtype) > 0 && q_dtype != IVIT_F32, "ivit_int_to_carrier: bad q_dtype");
+    IVIT_REQUIRE(dtype_size(q_dtype) > 0 && q_dtype != IVIT_F32 && q_dtype != IVIT_F64, "ivit_int_to_carrier: bad q_dtype");
     const int64_t n = rows * cols;
-    int_to_carrier_kernel<<<grid_for(n, 256, ctx->num_sms), 256, 0, st(stream)>>>(q, q_dtype, n, cols, s, s_len, out);
+    if (out_dtype == IVIT_F32)
+        int_to_carrier_kernel<<<grid_for(n, 256, ctx->num_sms), 256, 0, st(stream)>>>(q, q_dtype, n, cols, s, s_len, (float*)out);
+    else
+        int_to_carrier64_kernel<<<grid_for(n, 256, ctx->num_sms), 256, 0, st(stream)>>>(q, q_dtype, n, cols, s, s_len, (double*)out);
     IVIT_LAUNCH_OK("int_to_carrier_kernel");
     return IVIT_OK;
 }

@@ -45,6 +45,9 @@ class Engine:
         self.s = {k: (int(v[0, 0]), int(v[0, 1])) for k, v in pack.arrays.items()
                   if (k.endswith(".me") or k.endswith(".me_res")) and v.shape[0] == 1}
         self.x0 = {k: int(v[0]) for k, v in pack.arrays.items() if k.endswith(".x0")}
+        # IntGELU + mlp.qact1 over int8 is a function of (q, rowmax): one 64 KiB table per layer, built on the device
+        self.gelu_lut = {i: K.shiftgelu_build_lut(self.x0["blocks.%d.mlp.act.x0" % i], self.t["blocks.%d.mlp.qact1.me" % i])
+                         for i in range(self.meta["depth"])}
         self._plans = {}
         self.launches_per_forward = 0
 
@@ -115,7 +118,7 @@ class Engine:
             tap(p + "qact3", b["ln8"])
             lin(p + "mlp.fc1", b["ln8"], b["h8"], p + "mlp.qact_gelu", 8); n += 1
             tap(p + "mlp.qact_gelu", b["h8"])
-            _gelu_into(b["h8"], self.x0[p + "mlp.act.x0"], t[p + "mlp.qact1.me"], b["g8"]); n += 1
+            K.shiftgelu_lut(b["h8"], self.gelu_lut[i], out=b["g8"]); n += 1
             tap(p + "mlp.qact1", b["g8"])
             lin(p + "mlp.fc2", b["g8"], x, p + "mlp.qact2", 16, residual=x2, stage2=p + "qact4"); n += 1
             tap(p + "qact4", x)
@@ -186,8 +189,11 @@ def _quantize_into(x, scale, out):
 
 def _layernorm_into(x, bias_int, me, out):
     Cc = x.shape[-1]
-    K.call("ivit_layernorm", K.context(x.device), K.ptr(x), K.TORCH2IVIT[x.dtype], x.numel() // Cc, Cc,
-           K.ptr(bias_int), K.ptr(me), 8, K.TORCH2IVIT[out.dtype], K.ptr(out))
+    if x.dtype == torch.int16 and Cc % 8 == 0 and Cc <= 1024:
+        K.layernorm_i16_i8(x, bias_int, me, out=out)          # vectorised hot-path form
+    else:
+        K.call("ivit_layernorm", K.context(x.device), K.ptr(x), K.TORCH2IVIT[x.dtype], x.numel() // Cc, Cc,
+               K.ptr(bias_int), K.ptr(me), 8, K.TORCH2IVIT[out.dtype], K.ptr(out))
 
 
 def _gelu_into(q, x0, me, out):

@@ -59,22 +59,26 @@ def quantize_f32(x: torch.Tensor, scale: torch.Tensor, bits: int, per_row: bool 
 
 
 def carrier_to_int(x: torch.Tensor, s: torch.Tensor, out_dtype=torch.int32):
-    x = x.contiguous().float()
+    """z = RNE(x / s[c]); x is an fp32 (or fp64, see int_to_carrier) carrier."""
+    x = x.contiguous()
+    if x.dtype not in (torch.float32, torch.float64):
+        x = x.float()
     s = s.reshape(-1).contiguous().float()
     cols = x.shape[-1]
     out = torch.empty(x.shape, dtype=out_dtype, device=x.device)
-    call("ivit_carrier_to_int", context(x.device), ptr(x), x.numel() // cols, cols, ptr(s), s.numel(),
-         TORCH2IVIT[out_dtype], ptr(out))
+    call("ivit_carrier_to_int", context(x.device), ptr(x), TORCH2IVIT[x.dtype], x.numel() // cols, cols, ptr(s),
+         s.numel(), TORCH2IVIT[out_dtype], ptr(out))
     return out
 
 
-def int_to_carrier(q: torch.Tensor, s: torch.Tensor):
+def int_to_carrier(q: torch.Tensor, s: torch.Tensor, out_dtype=torch.float32):
+    """x = q * s[c].  out_dtype float64 keeps integers beyond 2^24 exact (IntLayerNorm outputs)."""
     q = q.contiguous()
     s = s.reshape(-1).contiguous().float()
     cols = q.shape[-1]
-    out = torch.empty(q.shape, dtype=torch.float32, device=q.device)
+    out = torch.empty(q.shape, dtype=out_dtype, device=q.device)
     call("ivit_int_to_carrier", context(q.device), ptr(q), TORCH2IVIT[q.dtype], q.numel() // cols, cols,
-         ptr(s), s.numel(), ptr(out))
+         ptr(s), s.numel(), TORCH2IVIT[out_dtype], ptr(out))
     return out
 
 
@@ -213,4 +217,29 @@ def embed_tokens(pe16: torch.Tensor, cls32: torch.Tensor, pos16: torch.Tensor, B
         out = torch.empty((B * n_tok, C), dtype=torch.int16, device=pe16.device)
     call("ivit_embed_tokens", context(pe16.device), ptr(pe16), ptr(cls32), ptr(pos16), B, n_tok, C,
          Dyadic(int(me[0]), int(me[1])), Dyadic(int(me_res[0]), int(me_res[1])), bits, ptr(out))
+    return out
+
+
+def shiftgelu_build_lut(x0: int, me: torch.Tensor, n: int = 23, bits: int = 8) -> torch.Tensor:
+    """64 KiB composite table of IntGELU + scalar 8-bit QuantAct (built once per layer, on the device)."""
+    lut = torch.empty(65536, dtype=torch.int8, device=me.device)
+    call("ivit_shiftgelu_build_lut", context(me.device), int(x0), n, ptr(me), bits, ptr(lut))
+    return lut
+
+
+def shiftgelu_lut(q: torch.Tensor, lut: torch.Tensor, out: torch.Tensor = None):
+    assert q.dtype == torch.int8 and q.is_contiguous()
+    cols = q.shape[-1]
+    if out is None:
+        out = torch.empty_like(q)
+    call("ivit_shiftgelu_lut", context(q.device), ptr(q), q.numel() // cols, cols, ptr(lut), ptr(out))
+    return out
+
+
+def layernorm_i16_i8(x: torch.Tensor, bias_int: torch.Tensor, me: torch.Tensor, out: torch.Tensor = None):
+    assert x.dtype == torch.int16 and x.is_contiguous()
+    Cc = x.shape[-1]
+    if out is None:
+        out = torch.empty(x.shape, dtype=torch.int8, device=x.device)
+    call("ivit_layernorm_i16_i8", context(x.device), ptr(x), x.numel() // Cc, Cc, ptr(bias_int), ptr(me), ptr(out))
     return out

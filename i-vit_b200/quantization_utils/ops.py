@@ -325,7 +325,10 @@ class IntLayerNorm(nn.LayerNorm):
         bias_int, out_sf = self._static(x.shape[2], x.device)
         x_int = K.carrier_to_int(x, scaling_factor.reshape(-1), torch.int32)      # :359
         y = K.layernorm(x_int, bias_int)                                          # :360-382
-        return K.int_to_carrier(y, out_sf), out_sf                                # :384-386
+        # :384-386.  The carrier is fp64: |y| reaches 2^30, beyond the 24-bit mantissa of fp32.  (The
+        # reference's own module returns fp64 here when its input carrier is exact -- SURVEY.md 8c --
+        # and a lossy fp32 product otherwise; the following QuantAct accepts either.)
+        return K.int_to_carrier(y, out_sf, torch.float64), out_sf
 
 
 def _host_scalar(t: torch.Tensor, cache: dict):

@@ -46,7 +46,7 @@ typedef struct ivit_dyadic_t {
     int32_t e;
 } ivit_dyadic_t;
 
-enum { IVIT_I8 = 0, IVIT_I16 = 1, IVIT_I32 = 2, IVIT_F32 = 3, IVIT_U8 = 4 };
+enum { IVIT_I8 = 0, IVIT_I16 = 1, IVIT_I32 = 2, IVIT_F32 = 3, IVIT_U8 = 4, IVIT_F64 = 5 };
 
 enum {
     IVIT_OK = 0,
@@ -83,15 +83,18 @@ IVIT_API int ivit_quantize_f32(ivit_ctx*, const float* x, int64_t n, const float
 
 /* Carrier -> integer: z = RNE(x / s[c]) (first line of fixedpoint_mul.forward,
  * quant_utils.py:220; also the x / scaling_factor of quant_modules.py:94,224-225,359,426,484).
- * x: [rows, cols] fp32; s: 1 or cols entries; saturates to out_dtype. */
-IVIT_API int ivit_carrier_to_int(ivit_ctx*, const float* x, int64_t rows, int cols,
+ * x: [rows, cols] carrier, x_dtype IVIT_F32 or IVIT_F64 (an fp64 carrier is what keeps
+ * IntLayerNorm outputs, up to 2^30, exact -- the reference's modules return fp64 there when
+ * their own input carrier is exact); s: 1 or cols entries; saturates to out_dtype. */
+IVIT_API int ivit_carrier_to_int(ivit_ctx*, const void* x, int x_dtype, int64_t rows, int cols,
                                  const float* s, int s_len, int out_dtype, void* out,
                                  ivit_stream stream);
 
 /* Integer -> carrier: x = float(q) * s[c] (the `* scaling_factor` on every operator's
  * return, e.g. quant_modules.py:96-97,206,228,384,445,497). */
 IVIT_API int ivit_int_to_carrier(ivit_ctx*, const void* q, int q_dtype, int64_t rows, int cols,
-                                 const float* s, int s_len, float* out, ivit_stream stream);
+                                 const float* s, int s_len, int out_dtype, void* out,
+                                 ivit_stream stream);
 
 /* fixedpoint_mul.forward (quant_utils.py:192-253) on integers:
  *   out = clamp( RNE(z*m/2^e) [+ RNE(w*m1/2^e1)], -2^(bits-1), 2^(bits-1)-1 )
@@ -209,6 +212,26 @@ IVIT_API int ivit_attention_i8(ivit_ctx*, const int8_t* qkv, const ivit_attn_par
  * out[(b*Hp + i)*Wp + j, (c*p + u)*p + v] = x[b, c, i*p+u, j*p+v]. */
 IVIT_API int ivit_patchify_i8(ivit_ctx*, const int8_t* x, int B, int Cin, int H, int W, int p,
                               int8_t* out, ivit_stream stream);
+
+/* ---- hot-path specialisations (same results as the general entry points above) ---------- */
+
+/* IntGELU followed by a scalar 8-bit QuantAct (layers_quant.py:147-148) depends only on
+ * (q, rowmax(q)) in int8 x int8.  ivit_shiftgelu_build_lut evaluates the general formula
+ * (quant_modules.py:410-445 + fixedpoint_mul) ONCE per layer into a 64 KiB table
+ *   lut[(mx+128)*256 + (q+128)] = clamp8(RNE(q * sigma(q, mx) * m / 2^e)),  q <= mx
+ * and ivit_shiftgelu_lut applies it: out[r,c] = lut[(rowmax_r+128)*256 + q[r,c]+128].
+ * Bit-identical to ivit_shiftgelu(..., me, 8, IVIT_I8, ...).  cols % 16 == 0, cols <= 4096. */
+IVIT_API int ivit_shiftgelu_build_lut(ivit_ctx*, int32_t x0, int n, const ivit_dyadic_t* me, int bits,
+                                      int8_t* lut, ivit_stream stream);
+IVIT_API int ivit_shiftgelu_lut(ivit_ctx*, const int8_t* q, int64_t rows, int cols, const int8_t* lut,
+                                int8_t* out, ivit_stream stream);
+
+/* IntLayerNorm + per-channel 8-bit QuantAct on an int16 residual stream (vit_quant.py:131-132,
+ * 137-138): vectorised form of ivit_layernorm(x, IVIT_I16, ..., me, 8, IVIT_I8, ...).
+ * C % 8 == 0, C <= 1024. */
+IVIT_API int ivit_layernorm_i16_i8(ivit_ctx*, const int16_t* x, int64_t rows, int C,
+                                   const int32_t* bias_int, const ivit_dyadic_t* me, int8_t* out,
+                                   ivit_stream stream);
 
 /* DeiT stem glue: cls-token concatenation followed by the position-embedding residual QuantAct
  * (vit_quant.py:259-265): out[b,t,:] = clamp(RNE(z*me) + RNE(pos[t,:]*me_res), bits) with

@@ -349,3 +349,42 @@ def test_attention(K, n_seq, n_tok, H, D, p_bits):
     got = K.attention_i8(dev(qkv), n_seq, n_tok, H, D, me_s, x0, me_o, p_bits=p_bits)
     assert np.abs(want).max() > 20, "test should produce non-trivial outputs"
     assert_equal(got, want, "attention n_tok=%d H=%d D=%d P%d" % (n_tok, H, D, p_bits))
+
+
+# ------------------------------------------------------------------------------- hot-path specialisations
+@pytest.mark.parametrize("cols,s", [(768, 0.03), (3072, 0.045), (1536, 0.0734), (384, 0.012), (4096, 0.02), (48, 0.05)])
+def test_shiftgelu_lut_matches_general_and_oracle(K, cols, s):
+    rng = np.random.default_rng(cols)
+    q = rng.integers(-128, 128, (77, cols)).astype(np.int64)
+    q[0] = rng.integers(-128, -1, cols)               # all-negative row
+    q[1] = 127
+    q[2] = -128
+    x0 = O.x0_of(O.gelu_sig_scale(np.float32(s)))
+    s_in = np.float32(s) * np.float32(1 / 128)
+    m, e = K.dyadic_host(np.array([s_in], np.float32), np.float32(0.9 * 127 * 127 * float(s_in) / 127.0))
+    want = O.requant(O.shiftgelu(q, x0), m, e, 8)
+    me = me_dev(K, m, e)
+    lut = K.shiftgelu_build_lut(x0, me)
+    got = K.shiftgelu_lut(dev(q.astype(np.int8)), lut)
+    assert_equal(got, want, "shiftgelu LUT cols=%d" % cols)
+    gen = K.shiftgelu(dev(q.astype(np.int8)), x0, me, 8)
+    assert torch.equal(got, gen)
+
+
+@pytest.mark.parametrize("C,mag", [(768, 9000), (192, 20000), (384, 32767), (96, 300), (1024, 5000), (8, 100)])
+def test_layernorm_i16_i8_fast(K, C, mag):
+    rng = np.random.default_rng(C)
+    q = rng.integers(-mag, mag + 1, (203, C)).astype(np.int64)
+    q[1] = 7                                          # zero variance
+    q[2] = 0
+    q[2, 0] = mag                                     # one-hot
+    half = C // 2
+    q[3, 0] += half - (q[3].sum() % C) if abs(q[3, 0]) < 30000 - C else 0      # exact .5 mean tie when it fits
+    bq = rng.integers(-2 ** 24, 2 ** 24, C).astype(np.int64)
+    z = O.layernorm(q, bq)
+    m, e = rand_me(rng, C, 40, 52, neg_every=5)
+    m[:2] = [2 ** 30, -2 ** 30]
+    e[3] = 20                                         # general (e < 32) requant inside the fast kernel
+    want = O.requant(z, m, e, 8)
+    got = K.layernorm_i16_i8(dev(q.astype(np.int16)), dev(bq.astype(np.int32)), me_dev(K, m, e))
+    assert_equal(got, want, "layernorm_i16_i8 C=%d" % C)

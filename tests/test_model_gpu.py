@@ -86,11 +86,32 @@ def test_cuda_graph_replay_and_batch_sizes(tiny):
 def test_operator_level_path_matches_engine(tiny):
     """The drop-in operator classes (fp32 carrier in / out, one kernel per reference operator)
     give bit-identical logits to the fused engine."""
+    from ivit_b200.quantization_utils import (IntGELU, IntLayerNorm, IntSoftmax, QuantAct, QuantConv2d, QuantLinear,
+                                               QuantMatMul)
     model = tiny["model"].cuda()
+    got, hooks = {}, []
+
+    def mk(name):
+        def hook(mod, inp, out):
+            t, sf = out
+            got[name] = (t.double() / sf.double()).round().to(torch.int64).cpu().numpy()
+        return hook
+
+    for name, mod in model.named_modules():
+        if isinstance(mod, (QuantAct, QuantLinear, QuantConv2d, QuantMatMul, IntLayerNorm, IntSoftmax, IntGELU)):
+            hooks.append(mod.register_forward_hook(mk(name)))
     with torch.no_grad():
         y = model(tiny["x"].cuda())
-    assert np.array_equal(y.cpu().numpy(), tiny["logits"])
+    for h in hooks:
+        h.remove()
     model.cpu()
+    cap = tiny["cap"]
+    for name in cap:                                     # oracle (forward) order: report the FIRST divergence
+        if name in got:
+            bad = int((got[name].reshape(-1) != cap[name].reshape(-1)).sum())
+            assert bad == 0, "operator-level path diverges from the oracle at %s (%d elements)" % (name, bad)
+    assert len(set(cap) & set(got)) >= 250
+    assert np.array_equal(y.cpu().numpy(), tiny["logits"])
 
 
 def test_operator_level_calibration_pass_runs(tiny):
