@@ -55,9 +55,12 @@ attention_kernel(const int8_t* __restrict__ qkv, const AttnArgs p, int8_t* __res
     constexpr int VSTR = KT * 32 + 16;
     constexpr int KK = D / 32;             // k-steps of Q K^T
     constexpr int ND = D / 8;              // 8-column output tiles
-    __shared__ __align__(16) int8_t sK[KT * 32 * KSTR];
-    __shared__ __align__(16) int8_t sVt[D * VSTR];
-    __shared__ int32_t sE[257];              // [256] = saturated value (d <= n*x0), used by masked entries
+    // dynamic shared memory: K tile | V^T tile | exponent LUT | per-thread packed scores
+    extern __shared__ __align__(16) uint8_t att_smem[];
+    int8_t* sK = reinterpret_cast<int8_t*>(att_smem);
+    int8_t* sVt = sK + KT * 32 * KSTR;
+    int32_t* sE = reinterpret_cast<int32_t*>(sVt + D * VSTR);   // [257]; [256] = saturated value (d <= n*x0), used by masked entries
+    uint32_t* sSV = reinterpret_cast<uint32_t*>(sE + 260);       // [ATT_WARPS * NT * 32]
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, q4 = lane & 3;
@@ -103,6 +106,11 @@ attention_kernel(const int8_t* __restrict__ qkv, const AttnArgs p, int8_t* __res
     const UniRq rq_o = make_unirq(p.me_o, 23);        // |P.V| <= 2^15 * 128 = 2^22
     const int col_lim = n_tok - 2 * q4;               // column 8t + (c&1) + 2*q4 is padding iff 8t + (c&1) >= col_lim
     const uint32_t e_sat = (uint32_t)sE[256];
+    const bool swin = (p.relbias != nullptr) || (p.mask != nullptr);
+    uint32_t* my_sv = sSV + (warp * NT) * 32 + lane;  // this thread's packed scores: my_sv[t * 32]
+    // NOTE on code size: the loops over score tiles / key chunks are deliberately NOT unrolled (per-thread state
+    // lives in shared memory).  The fully unrolled version was ~110 KB of SASS and spent 60 % of its cycles
+    // in instruction-fetch stalls (profiles/ncu_full_r1b.md).
     for (int rt = warp; rt < n_row_tiles; rt += ATT_WARPS) {
         const int r0 = rt * 16 + g, r1 = r0 + 8;
         // ---- Q fragments straight from global ----
@@ -114,14 +122,11 @@ attention_kernel(const int8_t* __restrict__ qkv, const AttnArgs p, int8_t* __res
             aq[kk][2] = (r0 < n_tok) ? __ldg(reinterpret_cast<const uint32_t*>(qb + (long long)r0 * ld + 32 * kk + 16 + 4 * q4)) : 0u;
             aq[kk][3] = (r1 < n_tok) ? __ldg(reinterpret_cast<const uint32_t*>(qb + (long long)r1 * ld + 32 * kk + 16 + 4 * q4)) : 0u;
         }
-        // ---- S = Q K^T, requantised tile by tile to int8 (qact_attn1 [+ rel-pos bias, mask]) and
-        //      packed four per register: sv[t] = {row r0: col 2q, 2q+1 ; row r1: col 2q, 2q+1} ----
-        uint32_t sv[NT];
-        uint32_t masked[(NT + 7) / 8];                // 4 bits per tile, only meaningful with a Swin mask
-#pragma unroll
-        for (int i = 0; i < (NT + 7) / 8; ++i) masked[i] = 0u;
+        // ---- S = Q K^T, requantised tile by tile to int8 (qact_attn1 [+ rel-pos bias, mask]) and packed four per
+        //      word: {row r0: col 2q, 2q+1 ; row r1: col 2q, 2q+1}; padding columns and masked entries -> marker ----
         int32_t mx0 = -128, mx1 = -128;
-#pragma unroll
+        uint32_t masked_bits = 0u;                    // Swin only (NT <= 8): 4 bits per tile
+#pragma unroll 1
         for (int t = 0; t < NT; ++t) {
             int32_t acc[4] = {0, 0, 0, 0};
 #pragma unroll
@@ -134,10 +139,11 @@ attention_kernel(const int8_t* __restrict__ qkv, const AttnArgs p, int8_t* __res
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
                 v[c] = clamp_bits<8>(unirq_apply(rq_s, acc[c]));
-                if (p.relbias != nullptr || p.mask != nullptr) {       // Swin (uniform branch)
+                const bool pad = (8 * t + (c & 1)) >= col_lim;
+                if (swin) {                                                  // uniform branch
                     const int col = 8 * t + 2 * q4 + (c & 1);
                     const int row = (c < 2) ? r0 : r1;
-                    if (col < n_tok && row < n_tok) {
+                    if (!pad && row < n_tok) {
                         if (p.relbias != nullptr) {
                             const int32_t bq = (int32_t)p.relbias[((long long)h * n_tok + row) * n_tok + col];
                             const long long t2 = requant64((long long)v[c], p.me_s2.m, p.me_s2.e) +
@@ -145,47 +151,42 @@ attention_kernel(const int8_t* __restrict__ qkv, const AttnArgs p, int8_t* __res
                             v[c] = clamp_i64_bits(t2, 8);
                         }
                         if (p.mask != nullptr) {
-                            const int32_t mv = p.mask[((long long)(b % p.n_win) * n_tok + row) * n_tok + col];
-                            // a masked entry (addend RNE(-100/s)) is always past the Shiftmax saturation
-                            // point for s < 0.35: remember it, its exponential is E(n*x0)
-                            if (mv != 0) { masked[t / 8] |= 1u << (4 * (t % 8) + c); v[c] = -128; }
+                            // a masked entry (addend RNE(-100/s)) is always past the Shiftmax saturation point for
+                            // s < 0.35: remember it, its exponential is E(n*x0)
+                            if (p.mask[((long long)(b % p.n_win) * n_tok + row) * n_tok + col] != 0) {
+                                masked_bits |= 1u << (4 * (t & 7) + c);
+                                v[c] = -128;
+                            }
                         }
                     }
                 }
+                if (pad) v[c] = -128;                                        // never raises the row max
             }
             mx0 = max(mx0, max(v[0], v[1]));
             mx1 = max(mx1, max(v[2], v[3]));
-            sv[t] = (uint32_t)(v[0] & 0xff) | ((uint32_t)(v[1] & 0xff) << 8) | ((uint32_t)(v[2] & 0xff) << 16) | ((uint32_t)v[3] << 24);
-        }
-        // padding columns hold requant(0) = 0 here, which may exceed the true row max: recompute the max
-        // over valid columns only when the tile straddles n_tok (cheap: at most NT compares per element)
-        {
-            int32_t m0 = -128, m1 = -128;
-#pragma unroll
-            for (int t = 0; t < NT; ++t) {
-#pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    const bool pad = (8 * t + (c & 1)) >= col_lim;
-                    const int32_t v = (int32_t)(int8_t)((sv[t] >> (8 * c)) & 0xff);
-                    if (!pad) { if (c < 2) m0 = max(m0, v); else m1 = max(m1, v); }
-                }
-            }
-            mx0 = m0; mx1 = m1;
+            my_sv[t * 32] = (uint32_t)(v[0] & 0xff) | ((uint32_t)(v[1] & 0xff) << 8) | ((uint32_t)(v[2] & 0xff) << 16) |
+                            ((uint32_t)v[3] << 24);
         }
         mx0 = max(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = max(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
         mx1 = max(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = max(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
-        // ---- exponentials (LUT over max - q) and row sums ----
-        auto expo = [&](int t, int c) -> uint32_t {
-            if ((8 * t + (c & 1)) >= col_lim) return 0u;
-            if (p.mask != nullptr && ((masked[t / 8] >> (4 * (t % 8) + c)) & 1u)) return e_sat;
-            const int32_t v = (int32_t)(int8_t)((sv[t] >> (8 * c)) & 0xff);
-            return (uint32_t)sE[((c < 2) ? mx0 : mx1) - v];
+        // ---- exponentials (LUT over max - q): E for the four entries of packed word w of tile t ----
+        auto expo4 = [&](int t, uint32_t w, uint32_t (&E)[4]) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const int32_t v = (int32_t)(int8_t)((w >> (8 * c)) & 0xff);
+                uint32_t e = (uint32_t)sE[((c < 2) ? mx0 : mx1) - v];
+                if (swin && ((masked_bits >> (4 * (t & 7) + c)) & 1u)) e = e_sat;
+                if ((8 * t + (c & 1)) >= col_lim) e = 0u;
+                E[c] = e;
+            }
         };
         unsigned long long sum0 = 0, sum1 = 0;
-#pragma unroll
+#pragma unroll 1
         for (int t = 0; t < NT; ++t) {
-            sum0 += (unsigned long long)expo(t, 0) + expo(t, 1);
-            sum1 += (unsigned long long)expo(t, 2) + expo(t, 3);
+            uint32_t E[4];
+            expo4(t, my_sv[t * 32], E);
+            sum0 += (unsigned long long)E[0] + E[1];
+            sum1 += (unsigned long long)E[2] + E[3];
         }
         sum0 += __shfl_xor_sync(0xffffffffu, sum0, 1); sum0 += __shfl_xor_sync(0xffffffffu, sum0, 2);
         sum1 += __shfl_xor_sync(0xffffffffu, sum1, 1); sum1 += __shfl_xor_sync(0xffffffffu, sum1, 2);
@@ -202,21 +203,23 @@ attention_kernel(const int8_t* __restrict__ qkv, const AttnArgs p, int8_t* __res
             olo[nd][0] = olo[nd][1] = olo[nd][2] = olo[nd][3] = 0;
         }
         const bool two_plane = p.p_bits > 8;
-#pragma unroll
+#pragma unroll 1
         for (int kc = 0; kc < KT; ++kc) {
+            // tiles 4kc .. 4kc+3; fragment register r: rows (r&1 ? r1 : r0), tiles 4kc + (r>>1)*2 + {0,1}
+            uint32_t P[4][4];
+#pragma unroll
+            for (int tt = 0; tt < 4; ++tt) {
+                uint32_t E[4];
+                expo4(4 * kc + tt, my_sv[(4 * kc + tt) * 32], E);
+                P[tt][0] = (E[0] * F0) >> p.p_shift; P[tt][1] = (E[1] * F0) >> p.p_shift;
+                P[tt][2] = (E[2] * F1) >> p.p_shift; P[tt][3] = (E[3] * F1) >> p.p_shift;
+            }
             uint32_t alo[4], ahi[4];
 #pragma unroll
             for (int r = 0; r < 4; ++r) {
-                // fragment register r: rows (r&1 ? r1 : r0), tiles 4kc + (r>>1)*2 + {0,1}, columns {0,1} of each
-                const int tA = 4 * kc + (r >> 1) * 2;
-                const int cb = (r & 1) * 2;
-                const uint32_t F = (r & 1) ? F1 : F0;
-                const uint32_t P0 = (expo(tA, cb) * F) >> p.p_shift;
-                const uint32_t P1 = (expo(tA, cb + 1) * F) >> p.p_shift;
-                const uint32_t P2 = (expo(tA + 1, cb) * F) >> p.p_shift;
-                const uint32_t P3 = (expo(tA + 1, cb + 1) * F) >> p.p_shift;
-                alo[r] = __byte_perm(__byte_perm(P0, P1, 0x0040), __byte_perm(P2, P3, 0x0040), 0x5410);
-                ahi[r] = __byte_perm(__byte_perm(P0, P1, 0x0051), __byte_perm(P2, P3, 0x0051), 0x5410);
+                const int ta = (r >> 1) * 2, cb = (r & 1) * 2;
+                alo[r] = __byte_perm(__byte_perm(P[ta][cb], P[ta][cb + 1], 0x0040), __byte_perm(P[ta + 1][cb], P[ta + 1][cb + 1], 0x0040), 0x5410);
+                ahi[r] = __byte_perm(__byte_perm(P[ta][cb], P[ta][cb + 1], 0x0051), __byte_perm(P[ta + 1][cb], P[ta + 1][cb + 1], 0x0051), 0x5410);
             }
 #pragma unroll
             for (int nd = 0; nd < ND; ++nd) {
@@ -274,6 +277,20 @@ __global__ void bmm_i32_kernel(const TA* __restrict__ A, long long lda, long lon
     if (row < M && col < N) C[bi * sc + (long long)row * ldc + col] = acc;
 }
 
+template <int D, int KT>
+static int launch_attention(int grid, const int8_t* qkv, const AttnArgs& a, int8_t* out, cudaStream_t s) {
+    constexpr int SMEM = KT * 32 * (D + 16) + D * (KT * 32 + 16) + 260 * 4 + ATT_WARPS * KT * 4 * 32 * 4;
+    auto kern = attention_kernel<D, KT>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        IVIT_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+        attr_set = true;
+    }
+    kern<<<grid, ATT_WARPS * 32, SMEM, s>>>(qkv, a, out);
+    IVIT_LAUNCH_OK("attention_kernel");
+    return IVIT_OK;
+}
+
 }  // namespace ivit
 
 using namespace ivit;
@@ -297,17 +314,11 @@ extern "C" int ivit_attention_i8(ivit_ctx* ctx, const int8_t* qkv, const ivit_at
     a.mask = ap->mask; a.n_win = ap->n_win > 0 ? ap->n_win : 1;
     const int grid = ap->n_seq * ap->n_heads;
     cudaStream_t s = st(stream);
-    if (ap->head_dim == 64) {
-        if (ap->n_tok <= 64) attention_kernel<64, 2><<<grid, ATT_WARPS * 32, 0, s>>>(qkv, a, out);
-        else if (ap->n_tok <= 224) attention_kernel<64, 7><<<grid, ATT_WARPS * 32, 0, s>>>(qkv, a, out);
-        else return fail(IVIT_ENOTSUP, "ivit_attention_i8: n_tok=%d > 224 not supported", ap->n_tok);
-    } else {
-        if (ap->n_tok <= 64) attention_kernel<32, 2><<<grid, ATT_WARPS * 32, 0, s>>>(qkv, a, out);
-        else if (ap->n_tok <= 224) attention_kernel<32, 7><<<grid, ATT_WARPS * 32, 0, s>>>(qkv, a, out);
-        else return fail(IVIT_ENOTSUP, "ivit_attention_i8: n_tok=%d > 224 not supported", ap->n_tok);
-    }
-    IVIT_LAUNCH_OK("attention_kernel");
-    return IVIT_OK;
+    if (ap->n_tok > 224) return fail(IVIT_ENOTSUP, "ivit_attention_i8: n_tok=%d > 224 not supported", ap->n_tok);
+    int rc;
+    if (ap->head_dim == 64) rc = (ap->n_tok <= 64) ? launch_attention<64, 2>(grid, qkv, a, out, s) : launch_attention<64, 7>(grid, qkv, a, out, s);
+    else rc = (ap->n_tok <= 64) ? launch_attention<32, 2>(grid, qkv, a, out, s) : launch_attention<32, 7>(grid, qkv, a, out, s);
+    return rc;
 }
 
 extern "C" int ivit_bmm_i32(ivit_ctx* ctx, const void* A, int a_dtype, int64_t lda, int64_t sa, const int8_t* B,

@@ -79,12 +79,17 @@ IVIT_DEVINL UniRq make_unirq(ivit_dyadic_t d, int zbits) {
     u.fast = (d.e >= 16 && d.e <= 62 && d.m != 0 && (d.e - 1 - tz > zbits)) ? 1 : 0;
     return u;
 }
+// out-of-line general form: keeps the (rarely taken) slow path from being inlined at every call site
+// (code size matters: the attention kernel was instruction-fetch bound)
+static __device__ __noinline__ int32_t requant32_general(int32_t z, int32_t m, int32_t e) {
+    return sat_i64_to_i32(requant64((long long)z, m, e));
+}
 IVIT_DEVINL int32_t unirq_apply(const UniRq& u, int32_t z) {
     if (u.fast) {                                                  // uniform branch
         const long long t = (long long)z * (long long)u.m + u.half;
         return (u.e >= 32) ? ((int32_t)(t >> 32) >> (u.e - 32)) : (int32_t)(t >> u.e);
     }
-    return sat_i64_to_i32(requant64((long long)z, u.m, u.e));
+    return requant32_general(z, u.m, u.e);
 }
 
 template <int BITS>

@@ -4,13 +4,14 @@
 //   acc[i,j] = sum_k A[i,k] * W[j,k] (+ bias[j])              QuantLinear.forward, quant_modules.py:93-97
 //   out[i,j] = clamp(RNE(acc * m[j] / 2^e[j]) ...)            QuantAct / fixedpoint_mul, quant_utils.py:192-253
 //
-// Structure (one persistent CTA per SM, 192 threads):
+// Structure (one persistent CTA per SM, 320 threads):
 //   warp 0      TMA producer: A tile [128 x 128 B] and W tile [BN x 128 B] per k-block into a
 //               STAGES-deep shared-memory ring (128-byte swizzle), mbarrier full/empty pairs
 //   warp 1      TMEM allocator + MMA issuer: one thread issues 4 x tcgen05.mma (K = 32 each) per
 //               k-block into one of two TMEM accumulators (128 lanes x BN int32 columns each)
-//   warps 2-5   epilogue: tcgen05.ld 32 columns at a time -> bias + per-channel dyadic requant
-//               (+ residual) in registers -> 16-byte stores.  Runs concurrently with the MMAs of
+//   warps 2-9   epilogue (two warps per TMEM lane group, half of the tile's columns each):
+//               tcgen05.ld 16/32 columns at a time (prefetched one chunk ahead, as is the int16 residual)
+//               -> per-channel dyadic requant (+ second stage + residual) in registers -> 16-byte stores.  Runs concurrently with the MMAs of
 //               the next tile (double-buffered accumulator).
 // Both operands are K-major (row-major A [M,K], row-major W [N,K]), so no transposes anywhere.
 #include <stdio.h>
@@ -25,7 +26,8 @@ namespace ivit {
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 128;          // bytes == int8 elements per k-block (one 128 B swizzle row)
 constexpr int GEMM_UMMA_K = 32;       // K per tcgen05.mma for 8-bit operands
-constexpr int GEMM_THREADS = 192;
+constexpr int GEMM_EPI_THREADS = 256;  // 8 epilogue warps: 2 per TMEM lane group, each takes half of the tile's columns
+constexpr int GEMM_THREADS = 64 + GEMM_EPI_THREADS;
 
 enum GemmMode { GM_RAW_I32 = 0, GM_CARRIER = 1, GM_RQ_I8 = 2, GM_RQ_I16 = 3 };
 
@@ -62,16 +64,40 @@ __device__ __forceinline__ uint32_t pack_sat_s16x2(int32_t lo, int32_t hi) {
     return r;
 }
 
-// One 32-column chunk of one output row: registers r[] hold the int32 accumulators.
-template <int MODE>
-__device__ __forceinline__ void epilogue_chunk(const uint32_t (&r)[32], const ColParam* __restrict__ cp,
-                                               const int32_t* __restrict__ cb, const GemmArgs& args, int row,
-                                               bool row_ok, int ncol0, bool fast, const UniRq& rq2, const UniRq& rqr) {
-    const bool full_chunk = (ncol0 + 32 <= args.N);
-    if (MODE == GM_RAW_I32 || MODE == GM_CARRIER) {
-        uint32_t o[32];
+// Residual prefetch for one CW-column chunk of one row (int16): CW/8 x 16-byte loads issued early so that
+// their latency overlaps the requant arithmetic of the previous chunk.
+template <int CW>
+__device__ __forceinline__ void load_residual(const GemmArgs& args, int row, bool row_ok, int ncol0, uint32_t (&rr)[CW / 2]) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
+    for (int j = 0; j < CW / 2; ++j) rr[j] = 0u;
+    if (!args.residual || !row_ok || ncol0 >= args.N) return;
+    const int16_t* res = reinterpret_cast<const int16_t*>(args.residual) + (long long)row * args.res_ld + ncol0;
+    if (ncol0 + CW <= args.N && ((reinterpret_cast<uintptr_t>(res) & 15) == 0)) {
+#pragma unroll
+        for (int j = 0; j < CW / 8; ++j) {
+            const uint4 t = __ldg(reinterpret_cast<const uint4*>(res) + j);
+            rr[4 * j] = t.x; rr[4 * j + 1] = t.y; rr[4 * j + 2] = t.z; rr[4 * j + 3] = t.w;
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < CW; ++j) {
+            const uint32_t v = (ncol0 + j < args.N) ? (uint32_t)(uint16_t)res[j] : 0u;
+            rr[j >> 1] |= v << (16 * (j & 1));
+        }
+    }
+}
+
+// One CW-column chunk of one output row: registers r[] hold the int32 accumulators.
+template <int MODE, int CW>
+__device__ __forceinline__ void epilogue_chunk(const uint32_t (&r)[CW], const uint32_t (&rr)[CW / 2],
+                                               const ColParam* __restrict__ cp, const int32_t* __restrict__ cb,
+                                               const GemmArgs& args, int row, bool row_ok, int ncol0, bool fast,
+                                               const UniRq& rq2, const UniRq& rqr) {
+    const bool full_chunk = (ncol0 + CW <= args.N);
+    if (MODE == GM_RAW_I32 || MODE == GM_CARRIER) {
+        uint32_t o[CW];
+#pragma unroll
+        for (int j = 0; j < CW; ++j) {
             const int32_t v = (int32_t)r[j] + cb[j];
             o[j] = (MODE == GM_RAW_I32) ? (uint32_t)v : __float_as_uint(__fmul_rn(__int2float_rn(v), __int_as_float(cp[j].m)));
         }
@@ -79,42 +105,42 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&r)[32], const Co
         uint32_t* dst = reinterpret_cast<uint32_t*>(args.out) + (long long)row * args.out_ld + ncol0;
         if (full_chunk && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) *reinterpret_cast<uint4*>(dst + j) = make_uint4(o[j], o[j + 1], o[j + 2], o[j + 3]);
+            for (int j = 0; j < CW; j += 4) *reinterpret_cast<uint4*>(dst + j) = make_uint4(o[j], o[j + 1], o[j + 2], o[j + 3]);
         } else {
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
+            for (int j = 0; j < CW; ++j)
                 if (ncol0 + j < args.N) dst[j] = o[j];
         }
         return;
     }
     // ---- first-stage per-channel requant: q = RNE((acc + bias) * m / 2^e) ----
-    int32_t q[32];
+    int32_t q[CW];
     if (fast) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
+        for (int j = 0; j < CW; ++j) {
             const ColParam p = cp[j];
             const long long t = (long long)(int32_t)r[j] * (long long)p.m + p.c;
             q[j] = (int32_t)(t >> 32) >> p.sh;
         }
     } else {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
+        for (int j = 0; j < CW; ++j) {
             const ColParam p = cp[j];
-            q[j] = requant32((int32_t)r[j] + cb[j], p.m, p.sh + 32);
+            q[j] = requant32_general((int32_t)r[j] + cb[j], p.m, p.sh + 32);
         }
     }
     if (MODE == GM_RQ_I8) {
         if (!row_ok) return;
         int8_t* dst = reinterpret_cast<int8_t*>(args.out) + (long long)row * args.out_ld + ncol0;
         if (full_chunk && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
-            uint32_t w[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) w[j] = pack_sat_s8x4(q[4 * j], q[4 * j + 1], q[4 * j + 2], q[4 * j + 3]);
-            *reinterpret_cast<uint4*>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
-            *reinterpret_cast<uint4*>(dst + 16) = make_uint4(w[4], w[5], w[6], w[7]);
+            for (int j = 0; j < CW; j += 16)
+                *reinterpret_cast<uint4*>(dst + j) = make_uint4(
+                    pack_sat_s8x4(q[j], q[j + 1], q[j + 2], q[j + 3]), pack_sat_s8x4(q[j + 4], q[j + 5], q[j + 6], q[j + 7]),
+                    pack_sat_s8x4(q[j + 8], q[j + 9], q[j + 10], q[j + 11]), pack_sat_s8x4(q[j + 12], q[j + 13], q[j + 14], q[j + 15]));
         } else {
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
+            for (int j = 0; j < CW; ++j)
                 if (ncol0 + j < args.N) dst[j] = (int8_t)clamp_bits<8>(q[j]);
         }
         return;
@@ -124,49 +150,34 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&r)[32], const Co
     //   two stage   : q1 = clamp(RNE(z*me)) is a QuantAct output; a second QuantAct adds the residual
     //                 (attn.qact3 -> Block.qact2, mlp.qact2 -> Block.qact4; vit_quant.py:85,135,141)
     if (!row_ok) return;
-    int16_t* dst = reinterpret_cast<int16_t*>(args.out) + (long long)row * args.out_ld + ncol0;
-    const int16_t* res = args.residual
-        ? reinterpret_cast<const int16_t*>(args.residual) + (long long)row * args.res_ld + ncol0 : nullptr;
-    const bool vec = full_chunk && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) &&
-                     (!res || ((reinterpret_cast<uintptr_t>(res) & 15) == 0));
-    int32_t rv[32];
-    if (res) {
-        if (vec) {
+    const bool has_res = args.residual != nullptr;
 #pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-                const uint4 t = __ldg(reinterpret_cast<const uint4*>(res + j));
-                const uint32_t tw[4] = {t.x, t.y, t.z, t.w};
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    rv[j + 2 * u] = (int32_t)(int16_t)(tw[u] & 0xffff);
-                    rv[j + 2 * u + 1] = (int32_t)tw[u] >> 16;
-                }
-            }
-        } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) rv[j] = (ncol0 + j < args.N) ? (int32_t)res[j] : 0;
-        }
-    }
-#pragma unroll
-    for (int j = 0; j < 32; ++j) {
+    for (int j = 0; j < CW; ++j) {
         int32_t v = q[j];
         if (args.two_stage) v = unirq_apply(rq2, clamp_bits_rt(v, args.mode_bits));
-        if (res) {
-            const long long s = (long long)v + (long long)unirq_apply(rqr, rv[j]);
-            v = sat_i64_to_i32(s);
+        if (has_res) {
+            const int32_t rv = (j & 1) ? ((int32_t)rr[j >> 1] >> 16) : (int32_t)(int16_t)(rr[j >> 1] & 0xffff);
+            v = sat_i64_to_i32((long long)v + (long long)unirq_apply(rqr, rv));
         }
         q[j] = v;
     }
-    if (vec && args.mode_bits == 16) {
+    int16_t* dst = reinterpret_cast<int16_t*>(args.out) + (long long)row * args.out_ld + ncol0;
+    if (full_chunk && args.mode_bits == 16 && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
 #pragma unroll
-        for (int j = 0; j < 32; j += 8)
+        for (int j = 0; j < CW; j += 8)
             *reinterpret_cast<uint4*>(dst + j) = make_uint4(pack_sat_s16x2(q[j], q[j + 1]), pack_sat_s16x2(q[j + 2], q[j + 3]),
                                                             pack_sat_s16x2(q[j + 4], q[j + 5]), pack_sat_s16x2(q[j + 6], q[j + 7]));
     } else {
 #pragma unroll
-        for (int j = 0; j < 32; ++j)
+        for (int j = 0; j < CW; ++j)
             if (ncol0 + j < args.N) dst[j] = (int16_t)clamp_bits_rt(q[j], args.mode_bits);
     }
+}
+
+template <int CW>
+__device__ __forceinline__ void tmem_ld_chunk(uint32_t taddr, uint32_t (&r)[CW]) {
+    if constexpr (CW == 32) ptx::tmem_ld_32x32b_x32(taddr, r);
+    else ptx::tmem_ld_32x32b_x16(taddr, r);
 }
 
 template <int BN, int STAGES>
@@ -218,7 +229,7 @@ gemm_i8_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
         }
         for (int s = 0; s < 2; ++s) {
             ptx::mbar_init(tfull_bar(s), 1);
-            ptx::mbar_init(tempty_bar(s), 4);          // one arrive per epilogue warp
+            ptx::mbar_init(tempty_bar(s), GEMM_EPI_THREADS / 32);   // one arrive per epilogue warp
         }
         ptx::fence_barrier_init();
     }
@@ -283,10 +294,13 @@ gemm_i8_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
             }
         }
     } else {
-        // ================= epilogue (warps 2..5) =================
-        const int ew = warp - 2;                      // 0..3
+        // ================= epilogue (warps 2..9) =================
+        // TMEM lane group is fixed by (warp % 4); the two warps that share a lane group split the tile's columns.
+        const int ew = warp - 2;                      // 0..7
         const int lane_group = warp & 3;              // TMEM lanes [32*lane_group, +32) are accessible to this warp
-        const int et = ew * 32 + lane;                // 0..127 thread index inside the epilogue group
+        const int col_half = ew >> 2;                 // 0: columns [0, BN/2), 1: [BN/2, BN)
+        const int et = ew * 32 + lane;                // 0..255 thread index inside the epilogue group
+        constexpr int CW = (MODE == GM_RQ_I16) ? 16 : 32;
         // kernel-uniform properties of the scalar second stage / residual dyadics (GM_RQ_I16)
         const UniRq rq2 = make_unirq(args.me2, 15);
         const UniRq rqr = make_unirq(args.res_me, 15);
@@ -299,10 +313,10 @@ gemm_i8_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
             int32_t* cb = col_bias + as * BN;
             // ---- stage the per-column constants of this tile (coalesced global reads) ----
             if (et == 0) fast_flag[as] = 1;
-            asm volatile("bar.sync 1, 128;" ::: "memory");
+            asm volatile("bar.sync 1, 256;" ::: "memory");
             {
                 int ok = 1;
-                for (int c = et; c < BN; c += 128) {
+                for (int c = et; c < BN; c += GEMM_EPI_THREADS) {
                     const int n = n0 + c;
                     ColParam p;
                     p.m = 0; p.sh = 31; p.c = 0;
@@ -327,30 +341,42 @@ gemm_i8_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
                 }
                 if (!ok) atomicAnd(&fast_flag[as], 0);
             }
-            asm volatile("bar.sync 1, 128;" ::: "memory");
+            asm volatile("bar.sync 1, 256;" ::: "memory");
             const bool fast = fast_flag[as] != 0;
+
+            const int row = m0 + lane_group * 32 + lane;
+            const bool row_ok = row < args.M;
+            const int c_begin = col_half * (BN / 2);
+            const int c_end = min(c_begin + BN / 2, args.N - n0);        // exclusive, may be <= c_begin
+            const uint32_t t_row = tmem_base + ((uint32_t)(lane_group * 32) << 16) + (uint32_t)(as * BN);
+
+            uint32_t ra[CW], rb[CW], resa[CW / 2], resb[CW / 2];
+            if (MODE == GM_RQ_I16 && c_begin < c_end) load_residual<CW>(args, row, row_ok, n0 + c_begin, resa);
 
             ptx::mbar_wait(tfull_bar(as), aphase);
             ptx::tc_fence_after();
 
-            const int row = m0 + lane_group * 32 + lane;
-            const bool row_ok = row < args.M;
-            const uint32_t t_row = tmem_base + ((uint32_t)(lane_group * 32) << 16) + (uint32_t)(as * BN);
-            const int n_chunks = min(BN, args.N - n0 + 31) / 32;      // chunks that contain at least one valid column
-
-            uint32_t ra[32], rb[32];
-            ptx::tmem_ld_32x32b_x32(t_row, ra);
-            ptx::tmem_ld_wait();
-#pragma unroll 1
-            for (int ch = 0; ch < n_chunks; ch += 2) {
-                if (ch + 1 < n_chunks) ptx::tmem_ld_32x32b_x32(t_row + (uint32_t)((ch + 1) * 32), rb);
-                epilogue_chunk<MODE>(ra, cp + ch * 32, cb + ch * 32, args, row, row_ok, n0 + ch * 32, fast, rq2, rqr);
+            if (c_begin < c_end) {
+                tmem_ld_chunk<CW>(t_row + (uint32_t)c_begin, ra);
                 ptx::tmem_ld_wait();
-                if (ch + 1 < n_chunks) {
-                    if (ch + 2 < n_chunks) ptx::tmem_ld_32x32b_x32(t_row + (uint32_t)((ch + 2) * 32), ra);
-                    epilogue_chunk<MODE>(rb, cp + (ch + 1) * 32, cb + (ch + 1) * 32, args, row, row_ok, n0 + (ch + 1) * 32,
-                                         fast, rq2, rqr);
+#pragma unroll 1
+                for (int c0 = c_begin; c0 < c_end; c0 += 2 * CW) {
+                    const bool has1 = (c0 + CW) < c_end;
+                    const bool has2 = (c0 + 2 * CW) < c_end;
+                    if (has1) {
+                        tmem_ld_chunk<CW>(t_row + (uint32_t)(c0 + CW), rb);
+                        if (MODE == GM_RQ_I16) load_residual<CW>(args, row, row_ok, n0 + c0 + CW, resb);
+                    }
+                    epilogue_chunk<MODE, CW>(ra, resa, cp + c0, cb + c0, args, row, row_ok, n0 + c0, fast, rq2, rqr);
                     ptx::tmem_ld_wait();
+                    if (has1) {
+                        if (has2) {
+                            tmem_ld_chunk<CW>(t_row + (uint32_t)(c0 + 2 * CW), ra);
+                            if (MODE == GM_RQ_I16) load_residual<CW>(args, row, row_ok, n0 + c0 + 2 * CW, resa);
+                        }
+                        epilogue_chunk<MODE, CW>(rb, resb, cp + c0 + CW, cb + c0 + CW, args, row, row_ok, n0 + c0 + CW, fast, rq2, rqr);
+                        ptx::tmem_ld_wait();
+                    }
                 }
             }
             // release the accumulator back to the MMA warp
