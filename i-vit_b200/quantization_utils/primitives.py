@@ -15,7 +15,10 @@ def symmetric_linear_quantization_params(num_bits, min_val, max_val):
         n = 2 ** (num_bits - 1) - 1
         eps = torch.finfo(torch.float32).eps
         max_val = torch.max(-min_val, max_val)
-        scale = max_val / float(n)
+        # tensor / tensor: a true IEEE division on every device.  (tensor / python-scalar is evaluated
+        # as a multiplication by the reciprocal by torch's CUDA kernels, 1 ulp off the CPU result that
+        # the frozen parameter pack and the oracle of record use.)
+        scale = max_val / torch.tensor(float(n), dtype=max_val.dtype, device=max_val.device)
         scale = scale.clamp(min=eps)
     return scale
 
