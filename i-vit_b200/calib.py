@@ -14,7 +14,7 @@ import os
 
 import torch
 
-from . import deit
+from . import deit, swin
 from .quantization_utils import QuantAct
 from .synth import synth_parameters
 
@@ -25,6 +25,7 @@ FACTORIES = {
     "deit_tiny_patch16_224": deit.deit_tiny_patch16_224,
     "deit_small_patch16_224": deit.deit_small_patch16_224,
     "deit_base_patch16_224": deit.deit_base_patch16_224,
+    "swin_tiny_patch4_window7_224": swin.swin_tiny_patch4_window7_224,
 }
 
 

@@ -94,6 +94,8 @@ gelu_lut_apply_kernel(const int8_t* __restrict__ q, int64_t rows, int cols, cons
 // ------------------------------------------------------------------------------------
 // LayerNorm int16 -> int8 with the per-channel QuantAct fused.  C = 8 * NV * 32 at most.
 // ------------------------------------------------------------------------------------
+struct alignas(16) LnCol { int32_t m; int32_t sh; long long c; };   // fast requant constants: hi32(z0*m + c) >> sh
+
 template <int NV>
 __global__ void __launch_bounds__(256)
 layernorm_i16_i8_kernel(const int16_t* __restrict__ x, int64_t rows, int C, const int32_t* __restrict__ bias_int,
@@ -102,18 +104,29 @@ layernorm_i16_i8_kernel(const int16_t* __restrict__ x, int64_t rows, int C, cons
     const int nvec = C >> 3;                                     // vectors of 8 int16
     const int64_t warp0 = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
     const int64_t nwarps = (int64_t)gridDim.x * 8;
-    // per-channel constants (bias, m, e) staged once per block in shared memory
-    __shared__ __align__(16) int32_t s_b[1024], s_m[1024], s_e[1024];
+    // per-channel constants staged once per block.  Fast form (all channels): 32 <= e <= 62, no reachable
+    // exact tie (|z| < 2^31: v2(z*m) <= 30 + ctz(m) < e-1) and |bias| < 2^30, so that
+    //   RNE((floor(y*F/2) + b) * m / 2^e) == hi32(floor(y*F/2)*m + (b*m + 2^(e-1))) >> (e-32)
+    __shared__ LnCol s_c[1024];
+    __shared__ int32_t s_b[1024];
+    int ok = 1;
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
-        s_b[c] = bias_int[c];
+        const int32_t b = bias_int[c];
         const ivit_dyadic_t d = me[c];
-        s_m[c] = d.m; s_e[c] = d.e;
+        const int tz = __ffs(d.m) - 1;
+        const bool f = (d.e >= 32 && d.e <= 62) && (d.e - 1 - tz > 31) && (b > -(1 << 30)) && (b < (1 << 30));
+        ok &= f ? 1 : 0;
+        LnCol p;
+        p.m = d.m; p.sh = d.e - 32;
+        p.c = (d.e >= 1 && d.e <= 62) ? ((long long)b * (long long)d.m + (1LL << (d.e - 1))) : 0;
+        s_c[c] = p;
+        s_b[c] = b;
     }
-    __syncthreads();
+    const bool fast = __syncthreads_and(ok) != 0;
     for (int64_t row = warp0; row < rows; row += nwarps) {
         const uint4* src = reinterpret_cast<const uint4*>(x + row * (int64_t)C);
         int32_t y[NV][8];
-        int32_t sum = 0;                                         // |sum| <= 2048 * 32768 < 2^31
+        int32_t sum = 0;                                         // |sum| <= 1024 * 32768 < 2^31
 #pragma unroll
         for (int j = 0; j < NV; ++j) {
             const int vi = lane + 32 * j;
@@ -123,7 +136,7 @@ layernorm_i16_i8_kernel(const int16_t* __restrict__ x, int64_t rows, int C, cons
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 y[j][2 * u] = (int32_t)(int16_t)(tw[u] & 0xffff);
-                y[j][2 * u + 1] = (int32_t)(int16_t)(tw[u] >> 16);
+                y[j][2 * u + 1] = (int32_t)tw[u] >> 16;
                 sum += y[j][2 * u] + y[j][2 * u + 1];
             }
         }
@@ -136,10 +149,10 @@ layernorm_i16_i8_kernel(const int16_t* __restrict__ x, int64_t rows, int C, cons
         unsigned long long V = 0;
 #pragma unroll
         for (int j = 0; j < NV; ++j) {
-            const bool ok = (lane + 32 * j) < nvec;
+            const bool okv = (lane + 32 * j) < nvec;
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
-                const int32_t d = ok ? y[j][u] - mu : 0;
+                const int32_t d = okv ? y[j][u] - mu : 0;
                 y[j][u] = d;
                 V += (unsigned long long)((long long)d * d);
             }
@@ -152,26 +165,30 @@ layernorm_i16_i8_kernel(const int16_t* __restrict__ x, int64_t rows, int C, cons
         for (int j = 0; j < NV; ++j) {
             const int vi = lane + 32 * j;
             if (vi < nvec) {
-                uint32_t b[8];
-                int32_t cb[8], cm[8], ce[8];
-                *reinterpret_cast<int4*>(cb) = *reinterpret_cast<const int4*>(s_b + vi * 8);
-                *reinterpret_cast<int4*>(cb + 4) = *reinterpret_cast<const int4*>(s_b + vi * 8 + 4);
-                *reinterpret_cast<int4*>(cm) = *reinterpret_cast<const int4*>(s_m + vi * 8);
-                *reinterpret_cast<int4*>(cm + 4) = *reinterpret_cast<const int4*>(s_m + vi * 8 + 4);
-                *reinterpret_cast<int4*>(ce) = *reinterpret_cast<const int4*>(s_e + vi * 8);
-                *reinterpret_cast<int4*>(ce + 4) = *reinterpret_cast<const int4*>(s_e + vi * 8 + 4);
+                int32_t r[8];
+                if (fast) {
 #pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                    long long o = (((long long)y[j][u] * (long long)F) >> 1) + (long long)cb[u];
-                    o = o > 2147483647LL ? 2147483647LL : (o < -2147483648LL ? -2147483648LL : o);
-                    const int32_t e = ce[u];
-                    int32_t r;
-                    if (e >= 32 && e <= 62) r = requant32_e32((int32_t)o, cm[u], e);
-                    else r = requant32((int32_t)o, cm[u], e);
-                    b[u] = (uint32_t)(clamp_bits<8>(r) & 0xff);
+                    for (int u = 0; u < 8; ++u) {
+                        const LnCol p = s_c[vi * 8 + u];
+                        const int32_t z0 = (int32_t)(((long long)y[j][u] * (long long)F) >> 1);   // floor(y*F/2), |.| <= 2^30
+                        const long long t = (long long)z0 * (long long)p.m + p.c;
+                        r[u] = (int32_t)(t >> 32) >> p.sh;
+                    }
+                } else {
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const LnCol p = s_c[vi * 8 + u];
+                        long long o = (((long long)y[j][u] * (long long)F) >> 1) + (long long)s_b[vi * 8 + u];
+                        o = o > 2147483647LL ? 2147483647LL : (o < -2147483648LL ? -2147483648LL : o);
+                        r[u] = requant32_general((int32_t)o, p.m, p.sh + 32);
+                    }
                 }
-                dst[vi] = make_uint2(b[0] | (b[1] << 8) | (b[2] << 16) | (b[3] << 24),
-                                     b[4] | (b[5] << 8) | (b[6] << 16) | (b[7] << 24));
+                uint32_t lo, hi, w0, w1;
+                asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, %3;" : "=r"(hi) : "r"(r[3]), "r"(r[2]), "r"(0));
+                asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, %3;" : "=r"(w0) : "r"(r[1]), "r"(r[0]), "r"(hi));
+                asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, %3;" : "=r"(lo) : "r"(r[7]), "r"(r[6]), "r"(0));
+                asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, %3;" : "=r"(w1) : "r"(r[5]), "r"(r[4]), "r"(lo));
+                dst[vi] = make_uint2(w0, w1);
             }
         }
     }

@@ -88,11 +88,18 @@ __device__ __forceinline__ void load_residual(const GemmArgs& args, int row, boo
 }
 
 // One CW-column chunk of one output row: registers r[] hold the int32 accumulators.
-template <int MODE, int CW>
+// 16-byte store into the 128B-swizzled staging tile: logical (row, byte offset inside the BN*ES-byte tile row)
+__device__ __forceinline__ void sts_swz(uint32_t out_base, int trow, int byte_off, uint4 v) {
+    const uint32_t box = (uint32_t)byte_off >> 7, chunk = ((uint32_t)byte_off >> 4) & 7u;
+    const uint32_t addr = out_base + box * (uint32_t)(GEMM_BM * 128) + (uint32_t)trow * 128u + ((chunk ^ ((uint32_t)trow & 7u)) << 4);
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+template <int MODE, int CW, bool TS>
 __device__ __forceinline__ void epilogue_chunk(const uint32_t (&r)[CW], const uint32_t (&rr)[CW / 2],
                                                const ColParam* __restrict__ cp, const int32_t* __restrict__ cb,
                                                const GemmArgs& args, int row, bool row_ok, int ncol0, bool fast,
-                                               const UniRq& rq2, const UniRq& rqr) {
+                                               const UniRq& rq2, const UniRq& rqr, uint32_t out_base, int trow, int tcol) {
     const bool full_chunk = (ncol0 + CW <= args.N);
     if (MODE == GM_RAW_I32 || MODE == GM_CARRIER) {
         uint32_t o[CW];
@@ -130,6 +137,14 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&r)[CW], const ui
         }
     }
     if (MODE == GM_RQ_I8) {
+        if (TS) {
+#pragma unroll
+            for (int j = 0; j < CW; j += 16)
+                sts_swz(out_base, trow, tcol + j, make_uint4(
+                    pack_sat_s8x4(q[j], q[j + 1], q[j + 2], q[j + 3]), pack_sat_s8x4(q[j + 4], q[j + 5], q[j + 6], q[j + 7]),
+                    pack_sat_s8x4(q[j + 8], q[j + 9], q[j + 10], q[j + 11]), pack_sat_s8x4(q[j + 12], q[j + 13], q[j + 14], q[j + 15])));
+            return;
+        }
         if (!row_ok) return;
         int8_t* dst = reinterpret_cast<int8_t*>(args.out) + (long long)row * args.out_ld + ncol0;
         if (full_chunk && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
@@ -149,7 +164,7 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&r)[CW], const ui
     //   single stage: clamp(RNE(z*me) + RNE(res*res_me))       one QuantAct with identity
     //   two stage   : q1 = clamp(RNE(z*me)) is a QuantAct output; a second QuantAct adds the residual
     //                 (attn.qact3 -> Block.qact2, mlp.qact2 -> Block.qact4; vit_quant.py:85,135,141)
-    if (!row_ok) return;
+    if (!TS && !row_ok) return;
     const bool has_res = args.residual != nullptr;
 #pragma unroll
     for (int j = 0; j < CW; ++j) {
@@ -160,6 +175,13 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&r)[CW], const ui
             v = sat_i64_to_i32((long long)v + (long long)unirq_apply(rqr, rv));
         }
         q[j] = v;
+    }
+    if (TS) {                                                      // mode_bits == 16 guaranteed by the dispatcher
+#pragma unroll
+        for (int j = 0; j < CW; j += 8)
+            sts_swz(out_base, trow, (tcol + j) * 2, make_uint4(pack_sat_s16x2(q[j], q[j + 1]), pack_sat_s16x2(q[j + 2], q[j + 3]),
+                                                               pack_sat_s16x2(q[j + 4], q[j + 5]), pack_sat_s16x2(q[j + 6], q[j + 7])));
+        return;
     }
     int16_t* dst = reinterpret_cast<int16_t*>(args.out) + (long long)row * args.out_ld + ncol0;
     if (full_chunk && args.mode_bits == 16 && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
@@ -180,36 +202,40 @@ __device__ __forceinline__ void tmem_ld_chunk(uint32_t taddr, uint32_t (&r)[CW])
     else ptx::tmem_ld_32x32b_x16(taddr, r);
 }
 
-template <int BN, int STAGES>
+// OUT_ES: bytes per output element staged through shared memory for the TMA store (0: direct global stores)
+template <int BN, int STAGES, int OUT_ES>
 struct GemmSmem {
     static constexpr int A_BYTES = GEMM_BM * GEMM_BK;
     static constexpr int B_BYTES = BN * GEMM_BK;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int OUT_BYTES = GEMM_BM * BN * OUT_ES;                     // [BN*OUT_ES/128 boxes][128 rows][128 B], 128B-swizzled
     static constexpr int PARAM_BYTES = 2 * BN * ((int)sizeof(ColParam) + 4);   // ColParam[2][BN] + int32 bias[2][BN]
     static constexpr int BAR_BYTES = 256;
-    static constexpr int TOTAL = STAGES * STAGE_BYTES + PARAM_BYTES + BAR_BYTES + 1024;  // +1024 alignment slack
+    static constexpr int TOTAL = STAGES * STAGE_BYTES + OUT_BYTES + PARAM_BYTES + BAR_BYTES + 1024;  // +1024 alignment slack
 };
 
-template <int BN, int STAGES, int MODE>
+template <int BN, int STAGES, int MODE, bool TS>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_i8_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                       const GemmArgs args) {
-    using S = GemmSmem<BN, STAGES>;
+                       const __grid_constant__ CUtensorMap tmap_out, const GemmArgs args) {
+    constexpr int OUT_ES = !TS ? 0 : (MODE == GM_RQ_I8 ? 1 : 2);
+    using S = GemmSmem<BN, STAGES, OUT_ES>;
     constexpr uint32_t TMEM_COLS = 2 * BN;            // double-buffered accumulator (256 or 512)
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* smem = smem_raw + (smem_base - ptx::smem_u32(smem_raw));
 
     const uint32_t stage_base = smem_base;
-    ColParam* col_params = reinterpret_cast<ColParam*>(smem + STAGES * S::STAGE_BYTES);
+    const uint32_t out_base = smem_base + STAGES * S::STAGE_BYTES;             // 1024-aligned (stage sizes are)
+    ColParam* col_params = reinterpret_cast<ColParam*>(smem + STAGES * S::STAGE_BYTES + S::OUT_BYTES);
     int32_t* col_bias = reinterpret_cast<int32_t*>(col_params + 2 * BN);
-    const uint32_t bar_base = smem_base + STAGES * S::STAGE_BYTES + S::PARAM_BYTES;
+    const uint32_t bar_base = smem_base + STAGES * S::STAGE_BYTES + S::OUT_BYTES + S::PARAM_BYTES;
     // barrier layout (8 B each): full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], then tmem ptr + flags
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
     auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
     auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + s); };
     auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + 2 + s); };
-    volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + STAGES * S::STAGE_BYTES + S::PARAM_BYTES + 8 * (2 * STAGES + 4));
+    volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + STAGES * S::STAGE_BYTES + S::OUT_BYTES + S::PARAM_BYTES + 8 * (2 * STAGES + 4));
     int* fast_flag = reinterpret_cast<int*>(const_cast<uint32_t*>(tmem_ptr_smem) + 2);   // [2] one per accumulator stage
 
     const int warp = threadIdx.x >> 5;
@@ -223,6 +249,7 @@ gemm_i8_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tensormap(&tmap_a);
         ptx::prefetch_tensormap(&tmap_b);
+        if (TS) ptx::prefetch_tensormap(&tmap_out);
         for (int s = 0; s < STAGES; ++s) {
             ptx::mbar_init(full_bar(s), 1);
             ptx::mbar_init(empty_bar(s), 1);
@@ -312,7 +339,10 @@ gemm_i8_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
             ColParam* cp = col_params + as * BN;
             int32_t* cb = col_bias + as * BN;
             // ---- stage the per-column constants of this tile (coalesced global reads) ----
-            if (et == 0) fast_flag[as] = 1;
+            if (et == 0) {
+                fast_flag[as] = 1;
+                if (TS) ptx::tma_store_wait_read<0>();        // previous tile's TMA store has finished reading the staging tile
+            }
             asm volatile("bar.sync 1, 256;" ::: "memory");
             {
                 int ok = 1;
@@ -367,14 +397,16 @@ gemm_i8_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
                         tmem_ld_chunk<CW>(t_row + (uint32_t)(c0 + CW), rb);
                         if (MODE == GM_RQ_I16) load_residual<CW>(args, row, row_ok, n0 + c0 + CW, resb);
                     }
-                    epilogue_chunk<MODE, CW>(ra, resa, cp + c0, cb + c0, args, row, row_ok, n0 + c0, fast, rq2, rqr);
+                    epilogue_chunk<MODE, CW, TS>(ra, resa, cp + c0, cb + c0, args, row, row_ok, n0 + c0, fast, rq2, rqr,
+                                                 out_base, lane_group * 32 + lane, c0);
                     ptx::tmem_ld_wait();
                     if (has1) {
                         if (has2) {
                             tmem_ld_chunk<CW>(t_row + (uint32_t)(c0 + 2 * CW), ra);
                             if (MODE == GM_RQ_I16) load_residual<CW>(args, row, row_ok, n0 + c0 + 2 * CW, resa);
                         }
-                        epilogue_chunk<MODE, CW>(rb, resb, cp + c0 + CW, cb + c0 + CW, args, row, row_ok, n0 + c0 + CW, fast, rq2, rqr);
+                        epilogue_chunk<MODE, CW, TS>(rb, resb, cp + c0 + CW, cb + c0 + CW, args, row, row_ok, n0 + c0 + CW, fast,
+                                                     rq2, rqr, out_base, lane_group * 32 + lane, c0 + CW);
                         ptx::tmem_ld_wait();
                     }
                 }
@@ -383,8 +415,24 @@ gemm_i8_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
             ptx::tc_fence_before();
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(tempty_bar(as));
+            if (TS) {
+                // staged tile -> global: one elected thread issues a TMA store per 128-byte-wide box
+                // (coalesced, asynchronous, clips the M / N tails)
+                ptx::fence_proxy_async();                          // generic-proxy smem writes -> async proxy
+                asm volatile("bar.sync 2, 256;" ::: "memory");
+                if (et == 0) {
+                    constexpr int BOX_COLS = 128 / (OUT_ES ? OUT_ES : 1);
+                    constexpr int NBOX = BN / BOX_COLS;
+#pragma unroll
+                    for (int bx = 0; bx < NBOX; ++bx)
+                        if (n0 + bx * BOX_COLS < args.N)
+                            ptx::tma_store_2d(&tmap_out, out_base + (uint32_t)(bx * GEMM_BM * 128), (n0 + bx * BOX_COLS) * OUT_ES, m0);   // byte-typed map
+                    ptx::tma_store_commit();
+                }
+            }
             if (++as == 2) { as = 0; aphase ^= 1u; }
         }
+        if (TS && et == 0) ptx::tma_store_wait<0>();               // all stores complete before the CTA exits
     }
 
     ptx::tc_fence_before();
@@ -481,10 +529,13 @@ int make_tmap_2d_u8(ivit_ctx* ctx, CUtensorMap* tm, const void* base, uint64_t i
     return IVIT_OK;
 }
 
-template <int BN, int STAGES, int MODE>
-static int launch_gemm(ivit_ctx* ctx, const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& ga, cudaStream_t s) {
-    using S = GemmSmem<BN, STAGES>;
-    auto kern = gemm_i8_tcgen05_kernel<BN, STAGES, MODE>;
+template <int BN, int STAGES, int MODE, bool TS>
+static int launch_gemm(ivit_ctx* ctx, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const GemmArgs& ga,
+                       cudaStream_t s) {
+    constexpr int OUT_ES = !TS ? 0 : (MODE == GM_RQ_I8 ? 1 : 2);
+    using S = GemmSmem<BN, STAGES, OUT_ES>;
+    static_assert(S::TOTAL <= 227 * 1024, "shared memory budget");
+    auto kern = gemm_i8_tcgen05_kernel<BN, STAGES, MODE, TS>;
     static bool attr_set = false;                     // per instantiation
     if (!attr_set) {
         IVIT_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
@@ -492,7 +543,7 @@ static int launch_gemm(ivit_ctx* ctx, const CUtensorMap& ta, const CUtensorMap& 
     }
     const int tiles = ((ga.M + GEMM_BM - 1) / GEMM_BM) * ((ga.N + BN - 1) / BN);
     const int grid = tiles < ctx->num_sms ? tiles : ctx->num_sms;
-    kern<<<grid, GEMM_THREADS, S::TOTAL, s>>>(ta, tb, ga);
+    kern<<<grid, GEMM_THREADS, S::TOTAL, s>>>(ta, tb, to, ga);
     IVIT_LAUNCH_OK("gemm_i8_tcgen05_kernel");
     return IVIT_OK;
 }
@@ -501,13 +552,27 @@ template <int MODE>
 static int dispatch_bn(ivit_ctx* ctx, const int8_t* A, int64_t lda, const int8_t* W, const GemmArgs& ga, cudaStream_t s) {
     // wide tiles when N is large enough to fill them; 128-wide otherwise (less padding waste)
     const bool wide = (ga.N % 256 == 0) || ga.N >= 1024;
-    CUtensorMap ta, tb;
+    CUtensorMap ta, tb, to;
     int rc = make_tmap_2d_u8(ctx, &ta, A, (uint64_t)ga.K, (uint64_t)ga.M, (uint64_t)lda, GEMM_BK, GEMM_BM);
     if (rc) return rc;
     rc = make_tmap_2d_u8(ctx, &tb, W, (uint64_t)ga.K, (uint64_t)ga.N, (uint64_t)ga.K, GEMM_BK, wide ? 256 : 128);
     if (rc) return rc;
-    if (wide) return launch_gemm<256, 4, MODE>(ctx, ta, tb, ga, s);
-    return launch_gemm<128, 6, MODE>(ctx, ta, tb, ga, s);
+    if constexpr (MODE == GM_RQ_I8 || MODE == GM_RQ_I16) {
+        // Output staged through shared memory and written by TMA when the destination allows it
+        // (16-byte aligned base and row pitch, full-width clamp); otherwise direct stores.
+        constexpr int ES = (MODE == GM_RQ_I8) ? 1 : 2;
+        const bool ts = ((uintptr_t)ga.out % 16 == 0) && ((ga.out_ld * ES) % 16 == 0) && ga.mode_bits == 8 * ES;
+        if (ts) {
+            // byte-typed view of the output: inner dim = N*ES bytes, box = 128 bytes x 128 rows, 128B swizzle
+            rc = make_tmap_2d_u8(ctx, &to, ga.out, (uint64_t)ga.N * ES, (uint64_t)ga.M, (uint64_t)ga.out_ld * ES, 128, GEMM_BM);
+            if (rc) return rc;
+            if (wide) return launch_gemm<256, 3, MODE, true>(ctx, ta, tb, to, ga, s);
+            return launch_gemm<128, 5, MODE, true>(ctx, ta, tb, to, ga, s);
+        }
+    }
+    to = ta;
+    if (wide) return launch_gemm<256, 4, MODE, false>(ctx, ta, tb, to, ga, s);
+    return launch_gemm<128, 6, MODE, false>(ctx, ta, tb, to, ga, s);
 }
 
 }  // namespace ivit
