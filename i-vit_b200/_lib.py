@@ -35,7 +35,7 @@ class GemmEpilogue(C.Structure):
     _fields_ = [("mode", C.c_int), ("bias", C.c_void_p), ("me", C.c_void_p), ("bits", C.c_int),
                 ("residual", C.c_void_p), ("res_dtype", C.c_int), ("res_ld", C.c_int64),
                 ("res_me", Dyadic), ("two_stage", C.c_int), ("me2", Dyadic), ("scale", C.c_void_p),
-                ("out_dtype", C.c_int), ("out_ld", C.c_int64)]
+                ("out_dtype", C.c_int), ("out_ld", C.c_int64), ("acc_bits", C.c_int)]
 
 
 class AttnParams(C.Structure):

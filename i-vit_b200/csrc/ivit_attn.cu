@@ -41,13 +41,15 @@ struct AttnArgs {
     ivit_dyadic_t me_s2, me_b;
     const int32_t* mask;          // [n_win, n_tok, n_tok] or null
     int n_win;
+    long long half_s, half_o;     // 2^(e-1) of me_s / me_o (FAST form)
 };
 
 constexpr int ATT_WARPS = 8;
-constexpr int PAD_MARK = -100000;  // marks key columns >= n_tok
 
 // D: head dim (32 | 64).  KT: number of 32-token chunks (n_tok <= 32*KT).
-template <int D, int KT>
+// SWIN: relative-position-bias QuantAct and/or shifted-window mask present.  P16: 16-bit probabilities (two byte planes).
+// FAST: both scalar requants qualify for the branch-free form (checked on the host, which knows (m, e) by value).
+template <int D, int KT, bool SWIN, bool P16, bool FAST>
 __global__ void __launch_bounds__(ATT_WARPS * 32, 2)
 attention_kernel(const int8_t* __restrict__ qkv, const AttnArgs p, int8_t* __restrict__ out) {
     constexpr int NT = KT * 4;             // 8-column score tiles
@@ -102,15 +104,28 @@ attention_kernel(const int8_t* __restrict__ qkv, const AttnArgs p, int8_t* __res
     __syncthreads();
 
     const int n_row_tiles = (n_tok + 15) / 16;
-    const UniRq rq_s = make_unirq(p.me_s, 21);        // |Q.K| <= 64 * 128 * 128 = 2^20
-    const UniRq rq_o = make_unirq(p.me_o, 23);        // |P.V| <= 2^15 * 128 = 2^22
-    const int col_lim = n_tok - 2 * q4;               // column 8t + (c&1) + 2*q4 is padding iff 8t + (c&1) >= col_lim
+    const int nt_full = n_tok >> 3;                   // score tiles with 8 valid columns
+    const int nt_used = (n_tok + 7) >> 3;             // tiles that contain at least one valid column
+    const int col_lim = n_tok - 2 * q4;               // in the boundary tile: column 8t + (c&1) + 2*q4 is padding iff 8t + (c&1) >= col_lim
     const uint32_t e_sat = (uint32_t)sE[256];
-    const bool swin = (p.relbias != nullptr) || (p.mask != nullptr);
     uint32_t* my_sv = sSV + (warp * NT) * 32 + lane;  // this thread's packed scores: my_sv[t * 32]
+    // FAST (host-checked): both scalar requants have 32 <= e <= 62 and no reachable exact tie, so
+    //   RNE(z*m/2^e) == hi32(z*m + 2^(e-1)) >> (e-32)   -- three instructions, constants in registers
+    const int32_t m_s = p.me_s.m, m_o = p.me_o.m;
+    const int sh_s = p.me_s.e - 32, sh_o = p.me_o.e - 32;
+    const long long half_s = p.half_s, half_o = p.half_o;
+    auto rq_scores = [&](int32_t z) -> int32_t {
+        if (FAST) return (int32_t)(((long long)z * (long long)m_s + half_s) >> 32) >> sh_s;
+        return requant32_general(z, p.me_s.m, p.me_s.e);
+    };
+    auto rq_out = [&](int32_t z) -> int32_t {
+        if (FAST) return (int32_t)(((long long)z * (long long)m_o + half_o) >> 32) >> sh_o;
+        return requant32_general(z, p.me_o.m, p.me_o.e);
+    };
     // NOTE on code size: the loops over score tiles / key chunks are deliberately NOT unrolled (per-thread state
-    // lives in shared memory).  The fully unrolled version was ~110 KB of SASS and spent 60 % of its cycles
-    // in instruction-fetch stalls (profiles/ncu_full_r1b.md).
+    // lives in shared memory) and the Swin / slow-requant variants are separate template instantiations.  The
+    // fully unrolled, all-in-one version was ~110 KB of SASS and spent 60 % of its cycles in instruction-fetch
+    // stalls (profiles/).
     for (int rt = warp; rt < n_row_tiles; rt += ATT_WARPS) {
         const int r0 = rt * 16 + g, r1 = r0 + 8;
         // ---- Q fragments straight from global ----
@@ -123,11 +138,10 @@ attention_kernel(const int8_t* __restrict__ qkv, const AttnArgs p, int8_t* __res
             aq[kk][3] = (r1 < n_tok) ? __ldg(reinterpret_cast<const uint32_t*>(qb + (long long)r1 * ld + 32 * kk + 16 + 4 * q4)) : 0u;
         }
         // ---- S = Q K^T, requantised tile by tile to int8 (qact_attn1 [+ rel-pos bias, mask]) and packed four per
-        //      word: {row r0: col 2q, 2q+1 ; row r1: col 2q, 2q+1}; padding columns and masked entries -> marker ----
+        //      word: {row r0: col 2q, 2q+1 ; row r1: col 2q, 2q+1}; padding columns / masked entries -> -128 ----
         int32_t mx0 = -128, mx1 = -128;
         uint32_t masked_bits = 0u;                    // Swin only (NT <= 8): 4 bits per tile
-#pragma unroll 1
-        for (int t = 0; t < NT; ++t) {
+        auto score_tile = [&](int t, bool boundary) {
             int32_t acc[4] = {0, 0, 0, 0};
 #pragma unroll
             for (int kk = 0; kk < KK; ++kk) {
@@ -138,17 +152,16 @@ attention_kernel(const int8_t* __restrict__ qkv, const AttnArgs p, int8_t* __res
             int32_t v[4];
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
-                v[c] = clamp_bits<8>(unirq_apply(rq_s, acc[c]));
-                const bool pad = (8 * t + (c & 1)) >= col_lim;
-                if (swin) {                                                  // uniform branch
+                v[c] = clamp_bits<8>(rq_scores(acc[c]));
+                const bool pad = boundary && ((8 * t + (c & 1)) >= col_lim);
+                if (SWIN) {
                     const int col = 8 * t + 2 * q4 + (c & 1);
                     const int row = (c < 2) ? r0 : r1;
                     if (!pad && row < n_tok) {
                         if (p.relbias != nullptr) {
                             const int32_t bq = (int32_t)p.relbias[((long long)h * n_tok + row) * n_tok + col];
-                            const long long t2 = requant64((long long)v[c], p.me_s2.m, p.me_s2.e) +
-                                                 requant64((long long)bq, p.me_b.m, p.me_b.e);
-                            v[c] = clamp_i64_bits(t2, 8);
+                            v[c] = clamp_bits<8>(sat_i64_to_i32((long long)requant32_general(v[c], p.me_s2.m, p.me_s2.e) +
+                                                                (long long)requant32_general(bq, p.me_b.m, p.me_b.e)));
                         }
                         if (p.mask != nullptr) {
                             // a masked entry (addend RNE(-100/s)) is always past the Shiftmax saturation point for
@@ -164,27 +177,45 @@ attention_kernel(const int8_t* __restrict__ qkv, const AttnArgs p, int8_t* __res
             }
             mx0 = max(mx0, max(v[0], v[1]));
             mx1 = max(mx1, max(v[2], v[3]));
-            my_sv[t * 32] = (uint32_t)(v[0] & 0xff) | ((uint32_t)(v[1] & 0xff) << 8) | ((uint32_t)(v[2] & 0xff) << 16) |
-                            ((uint32_t)v[3] << 24);
-        }
+            my_sv[t * 32] = __byte_perm(__byte_perm((uint32_t)v[0], (uint32_t)v[1], 0x0040),
+                                        __byte_perm((uint32_t)v[2], (uint32_t)v[3], 0x0040), 0x5410);
+        };
+#pragma unroll 1
+        for (int t = 0; t < nt_full; ++t) score_tile(t, false);
+        if (nt_used > nt_full) score_tile(nt_full, true);
+        for (int t = nt_used; t < NT; ++t) my_sv[t * 32] = 0x80808080u;      // unused tiles: valid LUT index, V rows are zero
         mx0 = max(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = max(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
         mx1 = max(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = max(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
         // ---- exponentials (LUT over max - q): E for the four entries of packed word w of tile t ----
-        auto expo4 = [&](int t, uint32_t w, uint32_t (&E)[4]) {
+        const int32_t* sE0 = sE + mx0;
+        const int32_t* sE1 = sE + mx1;
+        auto expo4 = [&](int t, uint32_t w, uint32_t (&E)[4], bool boundary) {
+            E[0] = (uint32_t)sE0[-(int32_t)(int8_t)(w & 0xff)];
+            E[1] = (uint32_t)sE0[-(int32_t)(int8_t)((w >> 8) & 0xff)];
+            E[2] = (uint32_t)sE1[-(int32_t)(int8_t)((w >> 16) & 0xff)];
+            E[3] = (uint32_t)sE1[-((int32_t)w >> 24)];
+            if (SWIN) {
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                const int32_t v = (int32_t)(int8_t)((w >> (8 * c)) & 0xff);
-                uint32_t e = (uint32_t)sE[((c < 2) ? mx0 : mx1) - v];
-                if (swin && ((masked_bits >> (4 * (t & 7) + c)) & 1u)) e = e_sat;
-                if ((8 * t + (c & 1)) >= col_lim) e = 0u;
-                E[c] = e;
+                for (int c = 0; c < 4; ++c)
+                    if ((masked_bits >> (4 * (t & 7) + c)) & 1u) E[c] = e_sat;
+            }
+            if (boundary) {
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+                    if ((8 * t + (c & 1)) >= col_lim) E[c] = 0u;
             }
         };
         unsigned long long sum0 = 0, sum1 = 0;
 #pragma unroll 1
-        for (int t = 0; t < NT; ++t) {
+        for (int t = 0; t < nt_full; ++t) {
             uint32_t E[4];
-            expo4(t, my_sv[t * 32], E);
+            expo4(t, my_sv[t * 32], E, false);
+            sum0 += (unsigned long long)E[0] + E[1];
+            sum1 += (unsigned long long)E[2] + E[3];
+        }
+        if (nt_used > nt_full) {
+            uint32_t E[4];
+            expo4(nt_full, my_sv[nt_full * 32], E, true);
             sum0 += (unsigned long long)E[0] + E[1];
             sum1 += (unsigned long long)E[2] + E[3];
         }
@@ -195,22 +226,23 @@ attention_kernel(const int8_t* __restrict__ qkv, const AttnArgs p, int8_t* __res
         const uint32_t F0 = 2147483647u / (S0 ? S0 : 1u);
         const uint32_t F1 = 2147483647u / (S1 ? S1 : 1u);
 
-        // ---- O = P V with P = (E * F) >> p_shift (E*F <= S*F < 2^31: 32-bit product), hi/lo byte planes ----
+        // ---- O = P V with P = (E * F) >> p_shift (E*F <= S*F < 2^31: 32-bit product), hi/lo byte planes.
+        //      No padding checks here: V rows of padding tokens are zero in shared memory. ----
         int32_t ohi[ND][4], olo[ND][4];
 #pragma unroll
         for (int nd = 0; nd < ND; ++nd) {
             ohi[nd][0] = ohi[nd][1] = ohi[nd][2] = ohi[nd][3] = 0;
             olo[nd][0] = olo[nd][1] = olo[nd][2] = olo[nd][3] = 0;
         }
-        const bool two_plane = p.p_bits > 8;
+        const int kc_used = (n_tok + 31) >> 5;
 #pragma unroll 1
-        for (int kc = 0; kc < KT; ++kc) {
+        for (int kc = 0; kc < kc_used; ++kc) {
             // tiles 4kc .. 4kc+3; fragment register r: rows (r&1 ? r1 : r0), tiles 4kc + (r>>1)*2 + {0,1}
             uint32_t P[4][4];
 #pragma unroll
             for (int tt = 0; tt < 4; ++tt) {
                 uint32_t E[4];
-                expo4(4 * kc + tt, my_sv[(4 * kc + tt) * 32], E);
+                expo4(4 * kc + tt, my_sv[(4 * kc + tt) * 32], E, false);
                 P[tt][0] = (E[0] * F0) >> p.p_shift; P[tt][1] = (E[1] * F0) >> p.p_shift;
                 P[tt][2] = (E[2] * F1) >> p.p_shift; P[tt][3] = (E[3] * F1) >> p.p_shift;
             }
@@ -219,14 +251,14 @@ attention_kernel(const int8_t* __restrict__ qkv, const AttnArgs p, int8_t* __res
             for (int r = 0; r < 4; ++r) {
                 const int ta = (r >> 1) * 2, cb = (r & 1) * 2;
                 alo[r] = __byte_perm(__byte_perm(P[ta][cb], P[ta][cb + 1], 0x0040), __byte_perm(P[ta + 1][cb], P[ta + 1][cb + 1], 0x0040), 0x5410);
-                ahi[r] = __byte_perm(__byte_perm(P[ta][cb], P[ta][cb + 1], 0x0051), __byte_perm(P[ta + 1][cb], P[ta + 1][cb + 1], 0x0051), 0x5410);
+                if (P16) ahi[r] = __byte_perm(__byte_perm(P[ta][cb], P[ta][cb + 1], 0x0051), __byte_perm(P[ta + 1][cb], P[ta + 1][cb + 1], 0x0051), 0x5410);
             }
 #pragma unroll
             for (int nd = 0; nd < ND; ++nd) {
                 const uint32_t b0 = *reinterpret_cast<const uint32_t*>(sVt + (8 * nd + g) * VSTR + 32 * kc + 4 * q4);
                 const uint32_t b1 = *reinterpret_cast<const uint32_t*>(sVt + (8 * nd + g) * VSTR + 32 * kc + 16 + 4 * q4);
                 mma_u8s8(olo[nd], alo, b0, b1);
-                if (two_plane) mma_u8s8(ohi[nd], ahi, b0, b1);
+                if (P16) mma_u8s8(ohi[nd], ahi, b0, b1);
             }
         }
         // ---- requant (attn.qact2) and store ----
@@ -236,10 +268,10 @@ attention_kernel(const int8_t* __restrict__ qkv, const AttnArgs p, int8_t* __res
             for (int half = 0; half < 2; ++half) {
                 const int row = half ? r1 : r0;
                 if (row < n_tok) {
-                    const int32_t v0 = (ohi[nd][2 * half] << 8) + olo[nd][2 * half];
-                    const int32_t v1 = (ohi[nd][2 * half + 1] << 8) + olo[nd][2 * half + 1];
-                    const int32_t o0 = clamp_bits<8>(unirq_apply(rq_o, v0));
-                    const int32_t o1 = clamp_bits<8>(unirq_apply(rq_o, v1));
+                    const int32_t v0 = P16 ? (ohi[nd][2 * half] << 8) + olo[nd][2 * half] : olo[nd][2 * half];
+                    const int32_t v1 = P16 ? (ohi[nd][2 * half + 1] << 8) + olo[nd][2 * half + 1] : olo[nd][2 * half + 1];
+                    const int32_t o0 = clamp_bits<8>(rq_out(v0));
+                    const int32_t o1 = clamp_bits<8>(rq_out(v1));
                     int8_t* dst = out + ((long long)b * n_tok + row) * (long long)(p.H * D) + h * D + 8 * nd + 2 * q4;
                     *reinterpret_cast<uint16_t*>(dst) = (uint16_t)((o0 & 0xff) | ((o1 & 0xff) << 8));
                 }
@@ -277,10 +309,10 @@ __global__ void bmm_i32_kernel(const TA* __restrict__ A, long long lda, long lon
     if (row < M && col < N) C[bi * sc + (long long)row * ldc + col] = acc;
 }
 
-template <int D, int KT>
+template <int D, int KT, bool SWIN, bool P16, bool FAST>
 static int launch_attention(int grid, const int8_t* qkv, const AttnArgs& a, int8_t* out, cudaStream_t s) {
     constexpr int SMEM = KT * 32 * (D + 16) + D * (KT * 32 + 16) + 260 * 4 + ATT_WARPS * KT * 4 * 32 * 4;
-    auto kern = attention_kernel<D, KT>;
+    auto kern = attention_kernel<D, KT, SWIN, P16, FAST>;
     static bool attr_set = false;
     if (!attr_set) {
         IVIT_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
@@ -289,6 +321,25 @@ static int launch_attention(int grid, const int8_t* qkv, const AttnArgs& a, int8
     kern<<<grid, ATT_WARPS * 32, SMEM, s>>>(qkv, a, out);
     IVIT_LAUNCH_OK("attention_kernel");
     return IVIT_OK;
+}
+
+// branch-free requant is exact iff 32 <= e <= 62 and no exact tie is reachable for |z| < 2^zbits
+static bool fast_dyadic(ivit_dyadic_t d, int zbits) {
+    if (d.m == 0 || d.e < 32 || d.e > 62) return false;
+    const int tz = __builtin_ctz((unsigned)d.m);
+    return d.e - 1 - tz > zbits;
+}
+
+template <int D, int KT>
+static int dispatch_attention(int grid, const int8_t* qkv, const AttnArgs& a, int8_t* out, cudaStream_t s, bool swin, bool p16, bool fast) {
+    // instantiations actually used by the models: DeiT (no bias/mask, 16-bit P) and Swin (bias/mask, 8-bit P)
+    if (!swin && p16) return fast ? launch_attention<D, KT, false, true, true>(grid, qkv, a, out, s)
+                                  : launch_attention<D, KT, false, true, false>(grid, qkv, a, out, s);
+    if (!swin && !p16) return fast ? launch_attention<D, KT, false, false, true>(grid, qkv, a, out, s)
+                                   : launch_attention<D, KT, false, false, false>(grid, qkv, a, out, s);
+    if (p16) return launch_attention<D, KT, true, true, false>(grid, qkv, a, out, s);
+    return fast ? launch_attention<D, KT, true, false, true>(grid, qkv, a, out, s)
+                : launch_attention<D, KT, true, false, false>(grid, qkv, a, out, s);
 }
 
 }  // namespace ivit
@@ -315,9 +366,18 @@ extern "C" int ivit_attention_i8(ivit_ctx* ctx, const int8_t* qkv, const ivit_at
     const int grid = ap->n_seq * ap->n_heads;
     cudaStream_t s = st(stream);
     if (ap->n_tok > 224) return fail(IVIT_ENOTSUP, "ivit_attention_i8: n_tok=%d > 224 not supported", ap->n_tok);
+    const bool swin = (ap->relbias != nullptr) || (ap->mask != nullptr);
+    const bool p16 = ap->p_bits > 8;
+    // |Q.K| <= 64 * 128 * 128 = 2^20 ; |P.V| <= 2^15 * 128 = 2^22
+    const bool fast = fast_dyadic(ap->me_s, 21) && fast_dyadic(ap->me_o, 23);
+    a.half_s = (ap->me_s.e >= 1 && ap->me_s.e <= 62) ? (1LL << (ap->me_s.e - 1)) : 0;
+    a.half_o = (ap->me_o.e >= 1 && ap->me_o.e <= 62) ? (1LL << (ap->me_o.e - 1)) : 0;
+    if (swin && ap->n_tok > 64) return fail(IVIT_ENOTSUP, "ivit_attention_i8: bias/mask path supports n_tok <= 64 (window attention)");
     int rc;
-    if (ap->head_dim == 64) rc = (ap->n_tok <= 64) ? launch_attention<64, 2>(grid, qkv, a, out, s) : launch_attention<64, 7>(grid, qkv, a, out, s);
-    else rc = (ap->n_tok <= 64) ? launch_attention<32, 2>(grid, qkv, a, out, s) : launch_attention<32, 7>(grid, qkv, a, out, s);
+    if (ap->head_dim == 64) rc = (ap->n_tok <= 64) ? dispatch_attention<64, 2>(grid, qkv, a, out, s, swin, p16, fast)
+                                                   : dispatch_attention<64, 7>(grid, qkv, a, out, s, swin, p16, fast);
+    else rc = (ap->n_tok <= 64) ? dispatch_attention<32, 2>(grid, qkv, a, out, s, swin, p16, fast)
+                                : dispatch_attention<32, 7>(grid, qkv, a, out, s, swin, p16, fast);
     return rc;
 }
 

@@ -119,8 +119,9 @@ layernorm_i16_i8_kernel(const int16_t* __restrict__ x, int64_t rows, int C, cons
         LnCol p;
         p.m = d.m; p.sh = d.e - 32;
         p.c = (d.e >= 1 && d.e <= 62) ? ((long long)b * (long long)d.m + (1LL << (d.e - 1))) : 0;
-        s_c[c] = p;
-        s_b[c] = b;
+        // channel c = 8*vi + u is stored at [u][vi]: consecutive lanes (vi) read consecutive 16-byte entries (no bank conflicts)
+        s_c[(c & 7) * nvec + (c >> 3)] = p;
+        s_b[(c & 7) * nvec + (c >> 3)] = b;
     }
     const bool fast = __syncthreads_and(ok) != 0;
     for (int64_t row = warp0; row < rows; row += nwarps) {
@@ -169,7 +170,7 @@ layernorm_i16_i8_kernel(const int16_t* __restrict__ x, int64_t rows, int C, cons
                 if (fast) {
 #pragma unroll
                     for (int u = 0; u < 8; ++u) {
-                        const LnCol p = s_c[vi * 8 + u];
+                        const LnCol p = s_c[u * nvec + vi];
                         const int32_t z0 = (int32_t)(((long long)y[j][u] * (long long)F) >> 1);   // floor(y*F/2), |.| <= 2^30
                         const long long t = (long long)z0 * (long long)p.m + p.c;
                         r[u] = (int32_t)(t >> 32) >> p.sh;
@@ -177,8 +178,8 @@ layernorm_i16_i8_kernel(const int16_t* __restrict__ x, int64_t rows, int C, cons
                 } else {
 #pragma unroll
                     for (int u = 0; u < 8; ++u) {
-                        const LnCol p = s_c[vi * 8 + u];
-                        long long o = (((long long)y[j][u] * (long long)F) >> 1) + (long long)s_b[vi * 8 + u];
+                        const LnCol p = s_c[u * nvec + vi];
+                        long long o = (((long long)y[j][u] * (long long)F) >> 1) + (long long)s_b[u * nvec + vi];
                         o = o > 2147483647LL ? 2147483647LL : (o < -2147483648LL ? -2147483648LL : o);
                         r[u] = requant32_general((int32_t)o, p.m, p.sh + 32);
                     }

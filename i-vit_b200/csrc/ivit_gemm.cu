@@ -31,6 +31,38 @@ constexpr int GEMM_THREADS = 64 + GEMM_EPI_THREADS;
 
 enum GemmMode { GM_RAW_I32 = 0, GM_CARRIER = 1, GM_RQ_I8 = 2, GM_RQ_I16 = 3 };
 
+// A scalar dyadic applied to operands with |z| < 2^zbits, analysed on the host:
+//   kind 1: t = z*m + 2^(e-1); q = t >> e            (16 <= e <= 62, exact tie unreachable)
+//   kind 2: same + tie-to-even correction             (16 <= e <= 62)
+//   kind 0: general out-of-line form (e outside that range)
+struct ScalarRq {
+    int32_t m, e;
+    long long half;
+    unsigned long long tmask;         // 2^e - 1
+    int kind;
+};
+static ScalarRq make_scalar_rq(ivit_dyadic_t d, int zbits) {
+    ScalarRq r;
+    r.m = d.m; r.e = d.e; r.half = 0; r.tmask = 0; r.kind = 0;
+    if (d.m != 0 && d.e >= 16 && d.e <= 62) {
+        r.half = 1LL << (d.e - 1);
+        r.tmask = (1ULL << d.e) - 1ULL;
+        const int tz = __builtin_ctz((unsigned)d.m);
+        r.kind = (d.e - 1 - tz > zbits) ? 1 : 2;
+    }
+    return r;
+}
+__device__ __forceinline__ int32_t scalar_rq_apply(const ScalarRq& u, int32_t z) {
+    if (u.kind == 0) return requant32_general(z, u.m, u.e);          // uniform branch
+    const long long t = (long long)z * (long long)u.m + u.half;
+    int32_t q = (u.e >= 32) ? ((int32_t)(t >> 32) >> (u.e - 32)) : (int32_t)(t >> u.e);
+    if (u.kind == 2) {                                               // uniform branch
+        const bool tie = ((unsigned long long)t & u.tmask) == 0ULL;
+        q -= (int32_t)(tie & (q & 1));
+    }
+    return q;
+}
+
 struct GemmArgs {
     int M, N, K;
     int mode_bits;                    // clamp bits for requant modes
@@ -38,9 +70,9 @@ struct GemmArgs {
     const ivit_dyadic_t* me;
     const void* residual;             // int16 [M, res_ld] (GM_RQ_I16 only)
     long long res_ld;
-    ivit_dyadic_t res_me;
     int two_stage;
-    ivit_dyadic_t me2;
+    ScalarRq rq2, rqr;                // second-stage / residual dyadics, pre-analysed on the host (known by value)
+    int acc_bits;                     // |acc + bias| < 2^acc_bits (tie analysis of the per-column requant)
     const float* scale;
     void* out;
     long long out_ld;
@@ -99,7 +131,7 @@ template <int MODE, int CW, bool TS>
 __device__ __forceinline__ void epilogue_chunk(const uint32_t (&r)[CW], const uint32_t (&rr)[CW / 2],
                                                const ColParam* __restrict__ cp, const int32_t* __restrict__ cb,
                                                const GemmArgs& args, int row, bool row_ok, int ncol0, bool fast,
-                                               const UniRq& rq2, const UniRq& rqr, uint32_t out_base, int trow, int tcol) {
+                                               uint32_t out_base, int trow, int tcol) {
     const bool full_chunk = (ncol0 + CW <= args.N);
     if (MODE == GM_RAW_I32 || MODE == GM_CARRIER) {
         uint32_t o[CW];
@@ -127,13 +159,19 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&r)[CW], const ui
         for (int j = 0; j < CW; ++j) {
             const ColParam p = cp[j];
             const long long t = (long long)(int32_t)r[j] * (long long)p.m + p.c;
-            q[j] = (int32_t)(t >> 32) >> p.sh;
+            const int sh = p.sh & 63;
+            int32_t v = (int32_t)(t >> 32) >> sh;
+            if (p.sh & 256) {                       // this column can reach an exact tie (warp-uniform: one column per j)
+                const bool tie = ((uint32_t)t == 0u) && (((int32_t)(t >> 32) & ((1 << sh) - 1)) == 0);
+                v -= (int32_t)(tie & (v & 1));
+            }
+            q[j] = v;
         }
     } else {
 #pragma unroll
         for (int j = 0; j < CW; ++j) {
             const ColParam p = cp[j];
-            q[j] = requant32_general((int32_t)r[j] + cb[j], p.m, p.sh + 32);
+            q[j] = requant32_general((int32_t)r[j] + cb[j], p.m, (p.sh & 255) >= 128 ? (p.sh & 255) - 256 + 32 : (p.sh & 255) + 32);
         }
     }
     if (MODE == GM_RQ_I8) {
@@ -169,10 +207,11 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&r)[CW], const ui
 #pragma unroll
     for (int j = 0; j < CW; ++j) {
         int32_t v = q[j];
-        if (args.two_stage) v = unirq_apply(rq2, clamp_bits_rt(v, args.mode_bits));
+        if (args.two_stage) v = scalar_rq_apply(args.rq2, clamp_bits_rt(v, args.mode_bits));
         if (has_res) {
             const int32_t rv = (j & 1) ? ((int32_t)rr[j >> 1] >> 16) : (int32_t)(int16_t)(rr[j >> 1] & 0xffff);
-            v = sat_i64_to_i32((long long)v + (long long)unirq_apply(rqr, rv));
+            // |v|, |residual term| < 2^31 individually (e >= 16 for the fast kinds); saturating 64-bit sum in the general case
+            v = sat_i64_to_i32((long long)v + (long long)scalar_rq_apply(args.rqr, rv));
         }
         q[j] = v;
     }
@@ -328,9 +367,6 @@ gemm_i8_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
         const int col_half = ew >> 2;                 // 0: columns [0, BN/2), 1: [BN/2, BN)
         const int et = ew * 32 + lane;                // 0..255 thread index inside the epilogue group
         constexpr int CW = (MODE == GM_RQ_I16) ? 16 : 32;
-        // kernel-uniform properties of the scalar second stage / residual dyadics (GM_RQ_I16)
-        const UniRq rq2 = make_unirq(args.me2, 15);
-        const UniRq rqr = make_unirq(args.res_me, 15);
         int as = 0;
         uint32_t aphase = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -355,12 +391,15 @@ gemm_i8_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
                         if (args.bias) b = args.bias[n];
                         if (MODE == GM_RQ_I8 || MODE == GM_RQ_I16) {
                             const ivit_dyadic_t d = args.me[n];
-                            p.m = d.m; p.sh = d.e - 32;
-                            // fast form: t = acc*m + (bias*m + 2^(e-1)); q = hi32(t) >> (e-32).  Needs
-                            // 32 <= e <= 62 and no reachable exact tie (|z| < 2^31: v2(z*m) <= 30 + ctz(m) < e-1)
+                            // fast form: t = acc*m + (bias*m + 2^(e-1)); q = hi32(t) >> (e-32), needs 32 <= e <= 62
+                            // (whole tile).  An exact tie z*m = (2k+1)*2^(e-1) needs v2(z) = e-1-ctz(m); with
+                            // |z| < 2^acc_bits it is unreachable when e-1-ctz(m) >= acc_bits, else the column is
+                            // flagged (bit 8) and gets the tie-to-even correction.
                             const int tz = __ffs(d.m) - 1;
-                            const bool f = (d.e >= 32 && d.e <= 62) && (d.e - 1 - tz > 31);
-                            ok &= f ? 1 : 0;
+                            const bool in_range = (d.e >= 32 && d.e <= 62);
+                            ok &= in_range ? 1 : 0;
+                            p.m = d.m;
+                            p.sh = ((d.e - 32) & 255) | ((in_range && (d.e - 1 - tz < args.acc_bits)) ? 256 : 0);
                             if (d.e >= 1 && d.e <= 62) p.c = (long long)b * (long long)d.m + (1LL << (d.e - 1));
                         } else if (MODE == GM_CARRIER) {
                             p.m = __float_as_int(args.scale[n]);
@@ -397,7 +436,7 @@ gemm_i8_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
                         tmem_ld_chunk<CW>(t_row + (uint32_t)(c0 + CW), rb);
                         if (MODE == GM_RQ_I16) load_residual<CW>(args, row, row_ok, n0 + c0 + CW, resb);
                     }
-                    epilogue_chunk<MODE, CW, TS>(ra, resa, cp + c0, cb + c0, args, row, row_ok, n0 + c0, fast, rq2, rqr,
+                    epilogue_chunk<MODE, CW, TS>(ra, resa, cp + c0, cb + c0, args, row, row_ok, n0 + c0, fast,
                                                  out_base, lane_group * 32 + lane, c0);
                     ptx::tmem_ld_wait();
                     if (has1) {
@@ -406,7 +445,7 @@ gemm_i8_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
                             if (MODE == GM_RQ_I16) load_residual<CW>(args, row, row_ok, n0 + c0 + 2 * CW, resa);
                         }
                         epilogue_chunk<MODE, CW, TS>(rb, resb, cp + c0 + CW, cb + c0 + CW, args, row, row_ok, n0 + c0 + CW, fast,
-                                                     rq2, rqr, out_base, lane_group * 32 + lane, c0 + CW);
+                                                     out_base, lane_group * 32 + lane, c0 + CW);
                         ptx::tmem_ld_wait();
                     }
                 }
@@ -498,9 +537,9 @@ __global__ void gemm_simt_epilogue(const int32_t* __restrict__ acc, GemmArgs a, 
         const ivit_dyadic_t d = a.me[c];
         int32_t q = requant32(v, d.m, d.e);
         if (mode == GM_RQ_I8) { reinterpret_cast<int8_t*>(a.out)[(long long)r * a.out_ld + c] = (int8_t)clamp_bits_rt(q, a.mode_bits); continue; }
-        if (a.two_stage) q = requant32(clamp_bits_rt(q, a.mode_bits), a.me2.m, a.me2.e);
+        if (a.two_stage) q = requant32(clamp_bits_rt(q, a.mode_bits), a.rq2.m, a.rq2.e);
         long long s = q;
-        if (a.residual) s += requant64((long long)reinterpret_cast<const int16_t*>(a.residual)[(long long)r * a.res_ld + c], a.res_me.m, a.res_me.e);
+        if (a.residual) s += requant64((long long)reinterpret_cast<const int16_t*>(a.residual)[(long long)r * a.res_ld + c], a.rqr.m, a.rqr.e);
         reinterpret_cast<int16_t*>(a.out)[(long long)r * a.out_ld + c] = (int16_t)clamp_i64_bits(s, a.mode_bits);
     }
 }
@@ -590,8 +629,11 @@ extern "C" int ivit_gemm_i8(ivit_ctx* ctx, const int8_t* A, int64_t lda, const i
     ga.M = (int)M; ga.N = (int)N; ga.K = (int)K;
     ga.mode_bits = epi->bits;
     ga.bias = epi->bias; ga.me = epi->me;
-    ga.residual = epi->residual; ga.res_ld = epi->res_ld; ga.res_me = epi->res_me;
-    ga.two_stage = epi->two_stage; ga.me2 = epi->me2;
+    ga.residual = epi->residual; ga.res_ld = epi->res_ld;
+    ga.two_stage = epi->two_stage;
+    ga.rq2 = make_scalar_rq(epi->me2, 15);            // operands are clamped 16-bit values
+    ga.rqr = make_scalar_rq(epi->res_me, 15);
+    ga.acc_bits = (epi->acc_bits > 0 && epi->acc_bits <= 31) ? epi->acc_bits : 31;
     ga.scale = epi->scale; ga.out = out; ga.out_ld = epi->out_ld;
     int mode;
     switch (epi->mode) {

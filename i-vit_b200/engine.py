@@ -20,6 +20,7 @@ are bit-identical to the operator-level path (``quantization_utils``) and to the
 """
 from __future__ import annotations
 
+import numpy as np
 import torch
 
 from . import kernels as K
@@ -48,6 +49,13 @@ class Engine:
         # IntGELU + mlp.qact1 over int8 is a function of (q, rowmax): one 64 KiB table per layer, built on the device
         self.gelu_lut = {i: K.shiftgelu_build_lut(self.x0["blocks.%d.mlp.act.x0" % i], self.t["blocks.%d.mlp.qact1.me" % i])
                          for i in range(self.meta["depth"])}
+        # bound |acc + bias| < 2^acc_bits per linear layer (int8 operands: |acc| <= K * 128 * 128)
+        self.acc_bits = {}
+        for k, v in pack.arrays.items():
+            if k.endswith(".weight_integer"):
+                name = k[:-len(".weight_integer")]
+                bound = int(v.shape[1]) * 128 * 128 + int(np.abs(pack.arrays[name + ".bias_integer"].astype(np.int64)).max()) + 1
+                self.acc_bits[name] = min(31, int(bound).bit_length())
         self._plans = {}
         self.launches_per_forward = 0
 
@@ -89,7 +97,7 @@ class Engine:
             if stage2 is not None:                                   # per-channel QuantAct, then residual QuantAct
                 kw = dict(two_stage=True, me2=s[stage2 + ".me"], residual=residual, res_me=s[stage2 + ".me_res"])
             K.gemm_i8(a, t[name + ".weight_integer"], bias=t[name + ".bias_integer"], mode="requant",
-                      me=t[me_key + ".me"], bits=bits, out=out, **kw)
+                      me=t[me_key + ".me"], bits=bits, out=out, acc_bits=self.acc_bits[name], **kw)
 
         # input quantisation (vit_quant.py:257) -> patch unfold -> patch-embedding GEMM (+patch_embed.qact, 16 bit)
         _quantize_into(b["img"], t["qact_input.scale"], b["img_q"]); n += 1

@@ -101,7 +101,7 @@ def requant(z: torch.Tensor, me: torch.Tensor, bits: int, w: torch.Tensor = None
 
 
 def gemm_i8(a: torch.Tensor, w: torch.Tensor, *, bias=None, mode="raw", me=None, bits=8, residual=None,
-            res_me=(0, 63), two_stage=False, me2=(0, 63), scale=None, out=None):
+            res_me=(0, 63), two_stage=False, me2=(0, 63), scale=None, out=None, acc_bits=0):
     """acc = a @ w.T (+bias) on the tcgen05 int8 path, with the fused epilogue selected by ``mode``:
     'raw' -> int32, 'carrier' -> fp32 acc*scale[n], 'requant' -> int8/int16 (per-channel ``me``)."""
     assert a.dtype == torch.int8 and w.dtype == torch.int8 and a.dim() == 2 and w.dim() == 2
@@ -134,6 +134,7 @@ def gemm_i8(a: torch.Tensor, w: torch.Tensor, *, bias=None, mode="raw", me=None,
     assert out.dtype == odt and out.stride(-1) == 1
     epi.out_dtype = TORCH2IVIT[odt]
     epi.out_ld = out.stride(0)
+    epi.acc_bits = int(acc_bits)
     call("ivit_gemm_i8", context(a.device), ptr(a), a.stride(0), ptr(w), M, N, K, C.byref(epi), ptr(out))
     return out
 

@@ -132,6 +132,9 @@ typedef struct ivit_gemm_epilogue {
     const float* scale;            /* [N] for IVIT_EPI_CARRIER                                */
     int out_dtype;                 /* IVIT_I8 / IVIT_I16 / IVIT_I32 / IVIT_F32                */
     int64_t out_ld;                /* leading dimension (elements) of out, >= N               */
+    int acc_bits;                  /* optional bound |acc + bias| < 2^acc_bits (0 = unknown = 31): lets
+                                      the epilogue prove that an exact .5 tie of the per-channel requant
+                                      is unreachable for most channels (those keep a 3-instruction form) */
 } ivit_gemm_epilogue;
 
 /* QuantLinear.forward contraction (quant_modules.py:93-97), also QuantConv2d on unfolded

@@ -36,7 +36,7 @@ def test_struct_layouts_match_header():
     # field order mirrors the C structs; sizes computed by the same (native) ABI rules
     assert [f[0] for f in L.GemmEpilogue._fields_] == ["mode", "bias", "me", "bits", "residual", "res_dtype",
                                                        "res_ld", "res_me", "two_stage", "me2", "scale",
-                                                       "out_dtype", "out_ld"]
+                                                       "out_dtype", "out_ld", "acc_bits"]
     assert [f[0] for f in L.AttnParams._fields_][:4] == ["n_seq", "n_tok", "n_heads", "head_dim"]
 
 

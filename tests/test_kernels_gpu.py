@@ -258,9 +258,14 @@ def test_gemm_requant_i8(K, M, N, K_, e_lo, e_hi):
     a, w, b = gemm_inputs(rng, M, N, K_)
     m, e = rand_me(rng, N, e_lo, e_hi, neg_every=5)
     m[:3] = [2 ** 30, -2 ** 30, 2 ** 31 - 1]           # power-of-two multipliers produce exact ties
-    want = O.requant(ref_acc(a, w, b), m, e, 8)
+    acc = ref_acc(a, w, b)
+    want = O.requant(acc, m, e, 8)
     got = K.gemm_i8(dev(a), dev(w), bias=dev(b), mode="requant", me=me_dev(K, m, e), bits=8)
     assert_equal(got, want, "gemm rq8 %dx%dx%d e[%d,%d]" % (M, N, K_, e_lo, e_hi))
+    # with the tightest valid accumulator bound most channels take the tie-free form, the 2^30 multipliers stay flagged
+    bits = int(np.abs(acc).max()).bit_length()
+    got = K.gemm_i8(dev(a), dev(w), bias=dev(b), mode="requant", me=me_dev(K, m, e), bits=8, acc_bits=bits)
+    assert_equal(got, want, "gemm rq8 acc_bits=%d %dx%dx%d" % (bits, M, N, K_))
 
 
 @pytest.mark.parametrize("M,N,K_", [(197, 192, 768), (300, 768, 3072), (128, 256, 128)])
@@ -281,11 +286,16 @@ def test_gemm_requant_i16(K, M, N, K_, variant):
             want = O.requant(acc, m, e, 16, res, m1, e1)
         else:
             m2, e2 = rand_me(rng, 1, 30, 33)
+            if M == 128:
+                m2[0], e2[0], m1[0], e1[0] = 2 ** 30, 31, -2 ** 30, 32      # power-of-two ratios: exact ties in both scalar stages
             q1 = O.requant(acc, m, e, 16)
             want = O.requant(q1, m2, e2, 16, res, m1, e1)
             kw.update(two_stage=True, me2=(m2[0], e2[0]))
     got = K.gemm_i8(dev(a), dev(w), bias=dev(b), mode="requant", me=me_dev(K, m, e), bits=16, **kw)
     assert_equal(got, want, "gemm rq16 %s %dx%dx%d" % (variant, M, N, K_))
+    got = K.gemm_i8(dev(a), dev(w), bias=dev(b), mode="requant", me=me_dev(K, m, e), bits=16,
+                    acc_bits=int(np.abs(acc).max()).bit_length(), **kw)
+    assert_equal(got, want, "gemm rq16 %s acc_bits %dx%dx%d" % (variant, M, N, K_))
 
 
 def test_gemm_strided_a_and_out(K):
