@@ -31,36 +31,47 @@ constexpr int GEMM_THREADS = 64 + GEMM_EPI_THREADS;
 
 enum GemmMode { GM_RAW_I32 = 0, GM_CARRIER = 1, GM_RQ_I8 = 2, GM_RQ_I16 = 3 };
 
-// A scalar dyadic applied to operands with |z| < 2^zbits, analysed on the host:
-//   kind 1: t = z*m + 2^(e-1); q = t >> e            (16 <= e <= 62, exact tie unreachable)
-//   kind 2: same + tie-to-even correction             (16 <= e <= 62)
-//   kind 0: general out-of-line form (e outside that range)
+// A scalar dyadic applied to 16-bit operands (|z| < 2^15), analysed on the host (it knows (m, e) by value).
+// Unified branch-free form for 16 <= e <= 62:
+//     t = (z << ls) * m + half';   q = hi32(t) >> rs        with (ls, rs, half') = (32-e, 0, 2^31)   for e <  32
+//                                                                               (0, e-32, 2^(e-1))  for e >= 32
+// (scaling z by 2^(32-e) scales numerator and denominator alike, |z << ls| < 2^31).  `tie` says whether an exact
+// .5 tie is reachable (e-1-ctz(m) <= 15); then tie <=> lo32(t) == 0 && (hi32(t) & himask) == 0 and q -= q & 1.
+// kind 0: e outside [16, 62] -> general out-of-line form.
 struct ScalarRq {
     int32_t m, e;
+    int32_t ls, rs, himask;
     long long half;
-    unsigned long long tmask;         // 2^e - 1
-    int kind;
+    int kind;                         // 0 general, 1 unified form
+    int tie;                          // unified form needs the tie-to-even correction
 };
-static ScalarRq make_scalar_rq(ivit_dyadic_t d, int zbits) {
+static ScalarRq make_scalar_rq(ivit_dyadic_t d) {
     ScalarRq r;
-    r.m = d.m; r.e = d.e; r.half = 0; r.tmask = 0; r.kind = 0;
+    r.m = d.m; r.e = d.e; r.ls = 0; r.rs = 0; r.himask = 0; r.half = 0; r.kind = 0; r.tie = 0;
     if (d.m != 0 && d.e >= 16 && d.e <= 62) {
-        r.half = 1LL << (d.e - 1);
-        r.tmask = (1ULL << d.e) - 1ULL;
-        const int tz = __builtin_ctz((unsigned)d.m);
-        r.kind = (d.e - 1 - tz > zbits) ? 1 : 2;
+        r.kind = 1;
+        if (d.e < 32) { r.ls = 32 - d.e; r.rs = 0; r.half = 1LL << 31; }
+        else { r.ls = 0; r.rs = d.e - 32; r.half = 1LL << (d.e - 1); }
+        r.himask = (1 << r.rs) - 1;
+        r.tie = (d.e - 1 - __builtin_ctz((unsigned)d.m) <= 15) ? 1 : 0;
     }
     return r;
 }
-__device__ __forceinline__ int32_t scalar_rq_apply(const ScalarRq& u, int32_t z) {
-    if (u.kind == 0) return requant32_general(z, u.m, u.e);          // uniform branch
-    const long long t = (long long)z * (long long)u.m + u.half;
-    int32_t q = (u.e >= 32) ? ((int32_t)(t >> 32) >> (u.e - 32)) : (int32_t)(t >> u.e);
-    if (u.kind == 2) {                                               // uniform branch
-        const bool tie = ((unsigned long long)t & u.tmask) == 0ULL;
+template <bool TIE>
+__device__ __forceinline__ int32_t scalar_rq_fast(const ScalarRq& u, int32_t z) {
+    const long long t = (long long)(z << u.ls) * (long long)u.m + u.half;
+    const int32_t hi = (int32_t)(t >> 32);
+    int32_t q = hi >> u.rs;
+    if (TIE) {
+        const bool tie = ((uint32_t)t == 0u) && ((hi & u.himask) == 0);
         q -= (int32_t)(tie & (q & 1));
     }
     return q;
+}
+__device__ __forceinline__ int32_t add_sat_s32(int32_t a, int32_t b) {
+    int32_t r;
+    asm("add.sat.s32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+    return r;
 }
 
 struct GemmArgs {
@@ -73,6 +84,7 @@ struct GemmArgs {
     int two_stage;
     ScalarRq rq2, rqr;                // second-stage / residual dyadics, pre-analysed on the host (known by value)
     int acc_bits;                     // |acc + bias| < 2^acc_bits (tie analysis of the per-column requant)
+    int scalar_mode;                  // 1: rq2/rqr unified form, no ties; 2: unified with tie correction; 0: general
     const float* scale;
     void* out;
     long long out_ld;
@@ -130,7 +142,7 @@ __device__ __forceinline__ void sts_swz(uint32_t out_base, int trow, int byte_of
 template <int MODE, int CW, bool TS>
 __device__ __forceinline__ void epilogue_chunk(const uint32_t (&r)[CW], const uint32_t (&rr)[CW / 2],
                                                const ColParam* __restrict__ cp, const int32_t* __restrict__ cb,
-                                               const GemmArgs& args, int row, bool row_ok, int ncol0, bool fast,
+                                               const GemmArgs& args, int row, bool row_ok, int ncol0, int fast,
                                                uint32_t out_base, int trow, int tcol) {
     const bool full_chunk = (ncol0 + CW <= args.N);
     if (MODE == GM_RAW_I32 || MODE == GM_CARRIER) {
@@ -153,25 +165,32 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&r)[CW], const ui
         return;
     }
     // ---- first-stage per-channel requant: q = RNE((acc + bias) * m / 2^e) ----
+    // tile mode (uniform): 1 = every column has 32 <= e <= 62 and none can reach an exact tie
+    //                      2 = every column has 32 <= e <= 62, some can tie -> correction on all elements
+    //                      0 = general out-of-line form
     int32_t q[CW];
-    if (fast) {
+    if (fast == 1) {
 #pragma unroll
         for (int j = 0; j < CW; ++j) {
             const ColParam p = cp[j];
             const long long t = (long long)(int32_t)r[j] * (long long)p.m + p.c;
-            const int sh = p.sh & 63;
-            int32_t v = (int32_t)(t >> 32) >> sh;
-            if (p.sh & 256) {                       // this column can reach an exact tie (warp-uniform: one column per j)
-                const bool tie = ((uint32_t)t == 0u) && (((int32_t)(t >> 32) & ((1 << sh) - 1)) == 0);
-                v -= (int32_t)(tie & (v & 1));
-            }
-            q[j] = v;
+            q[j] = (int32_t)(t >> 32) >> p.sh;
+        }
+    } else if (fast == 2) {
+#pragma unroll
+        for (int j = 0; j < CW; ++j) {
+            const ColParam p = cp[j];
+            const long long t = (long long)(int32_t)r[j] * (long long)p.m + p.c;
+            const int32_t hi = (int32_t)(t >> 32);
+            int32_t v = hi >> p.sh;
+            const bool tie = ((uint32_t)t == 0u) && ((hi & ((1 << p.sh) - 1)) == 0);
+            q[j] = v - (int32_t)(tie & (v & 1));
         }
     } else {
 #pragma unroll
         for (int j = 0; j < CW; ++j) {
             const ColParam p = cp[j];
-            q[j] = requant32_general((int32_t)r[j] + cb[j], p.m, (p.sh & 255) >= 128 ? (p.sh & 255) - 256 + 32 : (p.sh & 255) + 32);
+            q[j] = requant32_general((int32_t)r[j] + cb[j], p.m, p.sh + 32);
         }
     }
     if (MODE == GM_RQ_I8) {
@@ -198,24 +217,41 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&r)[CW], const ui
         }
         return;
     }
-    // ---- GM_RQ_I16: optional second (scalar) stage and int16 residual ----
+    // ---- GM_RQ_I16 (16-bit clamp): optional second (scalar) stage and int16 residual ----
     //   single stage: clamp(RNE(z*me) + RNE(res*res_me))       one QuantAct with identity
     //   two stage   : q1 = clamp(RNE(z*me)) is a QuantAct output; a second QuantAct adds the residual
     //                 (attn.qact3 -> Block.qact2, mlp.qact2 -> Block.qact4; vit_quant.py:85,135,141)
     if (!TS && !row_ok) return;
     const bool has_res = args.residual != nullptr;
+    auto resid = [&](int j) -> int32_t {
+        return (j & 1) ? ((int32_t)rr[j >> 1] >> 16) : (int32_t)(int16_t)(rr[j >> 1] & 0xffff);
+    };
+    if (args.scalar_mode == 1) {                                   // both scalar dyadics in unified form, no ties
 #pragma unroll
-    for (int j = 0; j < CW; ++j) {
-        int32_t v = q[j];
-        if (args.two_stage) v = scalar_rq_apply(args.rq2, clamp_bits_rt(v, args.mode_bits));
-        if (has_res) {
-            const int32_t rv = (j & 1) ? ((int32_t)rr[j >> 1] >> 16) : (int32_t)(int16_t)(rr[j >> 1] & 0xffff);
-            // |v|, |residual term| < 2^31 individually (e >= 16 for the fast kinds); saturating 64-bit sum in the general case
-            v = sat_i64_to_i32((long long)v + (long long)scalar_rq_apply(args.rqr, rv));
+        for (int j = 0; j < CW; ++j) {
+            int32_t v = q[j];
+            if (args.two_stage) v = scalar_rq_fast<false>(args.rq2, clamp_bits<16>(v));
+            if (has_res) v = add_sat_s32(v, scalar_rq_fast<false>(args.rqr, resid(j)));
+            q[j] = v;
         }
-        q[j] = v;
+    } else if (args.scalar_mode == 2) {                            // unified form with tie-to-even correction
+#pragma unroll
+        for (int j = 0; j < CW; ++j) {
+            int32_t v = q[j];
+            if (args.two_stage) v = scalar_rq_fast<true>(args.rq2, clamp_bits<16>(v));
+            if (has_res) v = add_sat_s32(v, scalar_rq_fast<true>(args.rqr, resid(j)));
+            q[j] = v;
+        }
+    } else {                                                       // general
+#pragma unroll
+        for (int j = 0; j < CW; ++j) {
+            int32_t v = q[j];
+            if (args.two_stage) v = requant32_general(clamp_bits<16>(v), args.rq2.m, args.rq2.e);
+            if (has_res) v = sat_i64_to_i32((long long)v + (long long)requant32_general(resid(j), args.rqr.m, args.rqr.e));
+            q[j] = v;
+        }
     }
-    if (TS) {                                                      // mode_bits == 16 guaranteed by the dispatcher
+    if (TS) {
 #pragma unroll
         for (int j = 0; j < CW; j += 8)
             sts_swz(out_base, trow, (tcol + j) * 2, make_uint4(pack_sat_s16x2(q[j], q[j + 1]), pack_sat_s16x2(q[j + 2], q[j + 3]),
@@ -223,7 +259,7 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&r)[CW], const ui
         return;
     }
     int16_t* dst = reinterpret_cast<int16_t*>(args.out) + (long long)row * args.out_ld + ncol0;
-    if (full_chunk && args.mode_bits == 16 && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+    if (full_chunk && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
 #pragma unroll
         for (int j = 0; j < CW; j += 8)
             *reinterpret_cast<uint4*>(dst + j) = make_uint4(pack_sat_s16x2(q[j], q[j + 1]), pack_sat_s16x2(q[j + 2], q[j + 3]),
@@ -231,7 +267,7 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&r)[CW], const ui
     } else {
 #pragma unroll
         for (int j = 0; j < CW; ++j)
-            if (ncol0 + j < args.N) dst[j] = (int16_t)clamp_bits_rt(q[j], args.mode_bits);
+            if (ncol0 + j < args.N) dst[j] = (int16_t)clamp_bits<16>(q[j]);
     }
 }
 
@@ -381,7 +417,7 @@ gemm_i8_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
             }
             asm volatile("bar.sync 1, 256;" ::: "memory");
             {
-                int ok = 1;
+                int ok = 1, any_tie = 0;
                 for (int c = et; c < BN; c += GEMM_EPI_THREADS) {
                     const int n = n0 + c;
                     ColParam p;
@@ -398,8 +434,9 @@ gemm_i8_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
                             const int tz = __ffs(d.m) - 1;
                             const bool in_range = (d.e >= 32 && d.e <= 62);
                             ok &= in_range ? 1 : 0;
+                            any_tie |= (in_range && (d.e - 1 - tz < args.acc_bits)) ? 1 : 0;
                             p.m = d.m;
-                            p.sh = ((d.e - 32) & 255) | ((in_range && (d.e - 1 - tz < args.acc_bits)) ? 256 : 0);
+                            p.sh = d.e - 32;
                             if (d.e >= 1 && d.e <= 62) p.c = (long long)b * (long long)d.m + (1LL << (d.e - 1));
                         } else if (MODE == GM_CARRIER) {
                             p.m = __float_as_int(args.scale[n]);
@@ -408,10 +445,12 @@ gemm_i8_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
                     cp[c] = p;
                     cb[c] = b;
                 }
-                if (!ok) atomicAnd(&fast_flag[as], 0);
+                if (!ok) atomicAnd(&fast_flag[as], 0);                 // bit 0: all columns in the fast range
+                if (any_tie) atomicOr(&fast_flag[as], 2);              // bit 1: some column can reach an exact tie
             }
             asm volatile("bar.sync 1, 256;" ::: "memory");
-            const bool fast = fast_flag[as] != 0;
+            const int ff = fast_flag[as];
+            const int fast = !(ff & 1) ? 0 : ((ff & 2) ? 2 : 1);
 
             const int row = m0 + lane_group * 32 + lane;
             const bool row_ok = row < args.M;
@@ -631,9 +670,15 @@ extern "C" int ivit_gemm_i8(ivit_ctx* ctx, const int8_t* A, int64_t lda, const i
     ga.bias = epi->bias; ga.me = epi->me;
     ga.residual = epi->residual; ga.res_ld = epi->res_ld;
     ga.two_stage = epi->two_stage;
-    ga.rq2 = make_scalar_rq(epi->me2, 15);            // operands are clamped 16-bit values
-    ga.rqr = make_scalar_rq(epi->res_me, 15);
+    ga.rq2 = make_scalar_rq(epi->me2);                // operands are clamped 16-bit values
+    ga.rqr = make_scalar_rq(epi->res_me);
     ga.acc_bits = (epi->acc_bits > 0 && epi->acc_bits <= 31) ? epi->acc_bits : 31;
+    {
+        const bool use2 = epi->two_stage != 0, user = epi->residual != nullptr;
+        const bool uni = (!use2 || ga.rq2.kind == 1) && (!user || ga.rqr.kind == 1);
+        const bool tie = (use2 && ga.rq2.tie) || (user && ga.rqr.tie);
+        ga.scalar_mode = !uni ? 0 : (tie ? 2 : 1);
+    }
     ga.scale = epi->scale; ga.out = out; ga.out_ld = epi->out_ld;
     int mode;
     switch (epi->mode) {

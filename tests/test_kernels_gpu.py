@@ -288,6 +288,7 @@ def test_gemm_requant_i16(K, M, N, K_, variant):
             m2, e2 = rand_me(rng, 1, 30, 33)
             if M == 128:
                 m2[0], e2[0], m1[0], e1[0] = 2 ** 30, 31, -2 ** 30, 32      # power-of-two ratios: exact ties in both scalar stages
+                kw["res_me"] = (m1[0], e1[0])
             q1 = O.requant(acc, m, e, 16)
             want = O.requant(q1, m2, e2, 16, res, m1, e1)
             kw.update(two_stage=True, me2=(m2[0], e2[0]))
