@@ -289,7 +289,11 @@ struct GemmSmem {
     static constexpr int TOTAL = STAGES * STAGE_BYTES + OUT_BYTES + PARAM_BYTES + BAR_BYTES + 1024;  // +1024 alignment slack
 };
 
-template <int BN, int STAGES, int MODE, bool TS>
+// CM x CN: thread-block cluster shape.  The CM CTAs of a cluster column work on CM consecutive m-tiles of the same
+// n-tile and share its W tile: each loads 1/CM of it and multicasts (TMA .multicast::cluster) to the others; likewise
+// the CN CTAs of a cluster row share the A tile.  L2 -> SM traffic per CTA and k-block drops from A + W to
+// A/CN + W/CM (the un-clustered kernel is L2-bandwidth bound at ~42 B/clk/SM: profiles/).
+template <int BN, int STAGES, int MODE, bool TS, int CM, int CN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_i8_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                        const __grid_constant__ CUtensorMap tmap_out, const GemmArgs args) {
@@ -316,10 +320,24 @@ gemm_i8_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
 
+    constexpr int CS = CM * CN;
+    const uint32_t crank = (CS > 1) ? ptx::cluster_ctarank() : 0u;
+    const int rx = (int)crank % CN, ry = (int)crank / CN;        // position inside the cluster (N index, M index)
+    uint16_t mask_a = 0, mask_b = 0;                             // CTAs sharing my A tile (same ry) / my W tile (same rx)
+#pragma unroll
+    for (int x = 0; x < CN; ++x) mask_a |= (uint16_t)(1u << (ry * CN + x));
+#pragma unroll
+    for (int y = 0; y < CM; ++y) mask_b |= (uint16_t)(1u << (y * CN + rx));
     const int tiles_m = (args.M + GEMM_BM - 1) / GEMM_BM;
     const int tiles_n = (args.N + BN - 1) / BN;
-    const int num_tiles = tiles_m * tiles_n;
+    const int tiles_m_c = (tiles_m + CM - 1) / CM, tiles_n_c = (tiles_n + CN - 1) / CN;
+    const int num_tiles = tiles_m_c * tiles_n_c;                 // cluster tiles (CM x CN CTA tiles each)
+    const int tile_first = (int)blockIdx.x / CS, tile_step = (int)gridDim.x / CS;
     const int num_kb = (args.K + GEMM_BK - 1) / GEMM_BK;
+    // CTA tile of cluster tile `t`: out-of-range tiles (ragged edges of the cluster grid) still run the whole pipeline
+    // (TMA zero-fills, stores are clipped) so that the cluster stays in lock step.
+    auto tile_m0 = [&](int t) { return ((t / tiles_n_c) * CM + ry) * GEMM_BM; };
+    auto tile_n0 = [&](int t) { return ((t % tiles_n_c) * CN + rx) * BN; };
 
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tensormap(&tmap_a);
@@ -327,7 +345,7 @@ gemm_i8_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
         if (TS) ptx::prefetch_tensormap(&tmap_out);
         for (int s = 0; s < STAGES; ++s) {
             ptx::mbar_init(full_bar(s), 1);
-            ptx::mbar_init(empty_bar(s), 1);
+            ptx::mbar_init(empty_bar(s), CM + CN - 1);     // one tcgen05.commit arrival from every CTA I send tiles to
         }
         for (int s = 0; s < 2; ++s) {
             ptx::mbar_init(tfull_bar(s), 1);
@@ -341,6 +359,7 @@ gemm_i8_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
     }
     ptx::tc_fence_before();
     __syncthreads();
+    if (CS > 1) ptx::cluster_sync();                       // peers' barriers are initialised before any remote arrive / multicast
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
 
@@ -349,16 +368,18 @@ gemm_i8_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                const int m0 = (tile / tiles_n) * GEMM_BM;
-                const int n0 = (tile % tiles_n) * BN;
+            constexpr int A_ROWS = GEMM_BM / CN, B_ROWS = BN / CM;   // my slice of the shared tiles
+            for (int tile = tile_first; tile < num_tiles; tile += tile_step) {
+                const int m0 = tile_m0(tile), n0 = tile_n0(tile);
                 for (int kb = 0; kb < num_kb; ++kb) {
-                    ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
-                    ptx::mbar_arrive_expect_tx(full_bar(stage), S::STAGE_BYTES);
-                    const uint32_t a_dst = stage_base + stage * S::STAGE_BYTES;
-                    const uint32_t b_dst = a_dst + S::A_BYTES;
-                    ptx::tma_load_2d(a_dst, &tmap_a, full_bar(stage), kb * GEMM_BK, m0);
-                    ptx::tma_load_2d(b_dst, &tmap_b, full_bar(stage), kb * GEMM_BK, n0);
+                    ptx::mbar_wait(empty_bar(stage), phase ^ 1u);    // every consumer of my slices has released the stage
+                    ptx::mbar_arrive_expect_tx(full_bar(stage), S::STAGE_BYTES);   // my own stage receives the full A + W tiles
+                    const uint32_t a_dst = stage_base + stage * S::STAGE_BYTES + rx * (A_ROWS * GEMM_BK);
+                    const uint32_t b_dst = stage_base + stage * S::STAGE_BYTES + S::A_BYTES + ry * (B_ROWS * GEMM_BK);
+                    if (CN > 1) ptx::tma_load_2d_mc(a_dst, &tmap_a, full_bar(stage), kb * GEMM_BK, m0 + rx * A_ROWS, mask_a);
+                    else ptx::tma_load_2d(a_dst, &tmap_a, full_bar(stage), kb * GEMM_BK, m0);
+                    if (CM > 1) ptx::tma_load_2d_mc(b_dst, &tmap_b, full_bar(stage), kb * GEMM_BK, n0 + ry * B_ROWS, mask_b);
+                    else ptx::tma_load_2d(b_dst, &tmap_b, full_bar(stage), kb * GEMM_BK, n0);
                     if (++stage == STAGES) { stage = 0; phase ^= 1u; }
                 }
             }
@@ -371,7 +392,7 @@ gemm_i8_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
             uint32_t phase = 0;
             int as = 0;
             uint32_t aphase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            for (int tile = tile_first; tile < num_tiles; tile += tile_step) {
                 ptx::mbar_wait(tempty_bar(as), aphase ^ 1u);
                 ptx::tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
@@ -388,7 +409,9 @@ gemm_i8_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
                         ptx::mma_i8_ss(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc,
                                        (kb | k) != 0 ? 1u : 0u);
                     }
-                    ptx::mma_commit(empty_bar(stage));             // frees the smem slot when the MMAs retire
+                    // frees the smem slot when the MMAs retire -- in every CTA that sent a slice of it
+                    if (CS > 1) ptx::mma_commit_mc(empty_bar(stage), (uint16_t)(mask_a | mask_b));
+                    else ptx::mma_commit(empty_bar(stage));
                     if (++stage == STAGES) { stage = 0; phase ^= 1u; }
                 }
                 ptx::mma_commit(tfull_bar(as));                    // accumulator complete -> epilogue
@@ -405,9 +428,8 @@ gemm_i8_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
         constexpr int CW = (MODE == GM_RQ_I16) ? 16 : 32;
         int as = 0;
         uint32_t aphase = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-            const int m0 = (tile / tiles_n) * GEMM_BM;
-            const int n0 = (tile % tiles_n) * BN;
+        for (int tile = tile_first; tile < num_tiles; tile += tile_step) {
+            const int m0 = tile_m0(tile), n0 = tile_n0(tile);
             ColParam* cp = col_params + as * BN;
             int32_t* cb = col_bias + as * BN;
             // ---- stage the per-column constants of this tile (coalesced global reads) ----
@@ -503,7 +525,7 @@ gemm_i8_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
                     constexpr int NBOX = BN / BOX_COLS;
 #pragma unroll
                     for (int bx = 0; bx < NBOX; ++bx)
-                        if (n0 + bx * BOX_COLS < args.N)
+                        if (n0 + bx * BOX_COLS < args.N && m0 < args.M)
                             ptx::tma_store_2d(&tmap_out, out_base + (uint32_t)(bx * GEMM_BM * 128), (n0 + bx * BOX_COLS) * OUT_ES, m0);   // byte-typed map
                     ptx::tma_store_commit();
                 }
@@ -515,6 +537,7 @@ gemm_i8_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
 
     ptx::tc_fence_before();
     __syncthreads();
+    if (CS > 1) ptx::cluster_sync();                       // no CTA exits while a peer may still arrive on its barriers
     if (warp == 1) {
         ptx::tc_fence_after();
         ptx::tmem_dealloc(tmem_base, TMEM_COLS);
@@ -607,21 +630,40 @@ int make_tmap_2d_u8(ivit_ctx* ctx, CUtensorMap* tm, const void* base, uint64_t i
     return IVIT_OK;
 }
 
-template <int BN, int STAGES, int MODE, bool TS>
+template <int BN, int STAGES, int MODE, bool TS, int CM, int CN>
 static int launch_gemm(ivit_ctx* ctx, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const GemmArgs& ga,
                        cudaStream_t s) {
     constexpr int OUT_ES = !TS ? 0 : (MODE == GM_RQ_I8 ? 1 : 2);
+    constexpr int CS = CM * CN;
     using S = GemmSmem<BN, STAGES, OUT_ES>;
     static_assert(S::TOTAL <= 227 * 1024, "shared memory budget");
-    auto kern = gemm_i8_tcgen05_kernel<BN, STAGES, MODE, TS>;
+    auto kern = gemm_i8_tcgen05_kernel<BN, STAGES, MODE, TS, CM, CN>;
     static bool attr_set = false;                     // per instantiation
+    static int max_clusters = 0;
+    cudaLaunchConfig_t cfg = {};
+    cfg.blockDim = dim3(GEMM_THREADS);
+    cfg.dynamicSmemBytes = S::TOTAL;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = (CS > 1) ? 1 : 0;
     if (!attr_set) {
         IVIT_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
+        if (CS > 1) {
+            cfg.gridDim = dim3(CS * ctx->num_sms);
+            IVIT_CUDA_OK(cudaOccupancyMaxActiveClusters(&max_clusters, kern, &cfg));
+            if (max_clusters < 1) return fail(IVIT_ECUDA, "gemm: no co-resident cluster of %d CTAs fits", CS);
+        }
         attr_set = true;
     }
-    const int tiles = ((ga.M + GEMM_BM - 1) / GEMM_BM) * ((ga.N + BN - 1) / BN);
-    const int grid = tiles < ctx->num_sms ? tiles : ctx->num_sms;
-    kern<<<grid, GEMM_THREADS, S::TOTAL, s>>>(ta, tb, to, ga);
+    const int tiles_m = (ga.M + GEMM_BM - 1) / GEMM_BM, tiles_n = (ga.N + BN - 1) / BN;
+    const int ctiles = ((tiles_m + CM - 1) / CM) * ((tiles_n + CN - 1) / CN);
+    const int cap = (CS > 1) ? max_clusters : ctx->num_sms;
+    const int nclusters = ctiles < cap ? ctiles : cap;
+    cfg.gridDim = dim3(nclusters * CS);
+    IVIT_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, ta, tb, to, ga));
     IVIT_LAUNCH_OK("gemm_i8_tcgen05_kernel");
     return IVIT_OK;
 }
@@ -630,10 +672,13 @@ template <int MODE>
 static int dispatch_bn(ivit_ctx* ctx, const int8_t* A, int64_t lda, const int8_t* W, const GemmArgs& ga, cudaStream_t s) {
     // wide tiles when N is large enough to fill them; 128-wide otherwise (less padding waste)
     const bool wide = (ga.N % 256 == 0) || ga.N >= 1024;
+    // cluster of 2 CTAs along M sharing the W tile (TMA multicast) when there is enough work to keep every pair busy
+    static const char* cl_env = getenv("IVIT_GEMM_CLUSTER");
+    const bool cluster = wide && ga.M >= 4 * GEMM_BM && !(cl_env && cl_env[0] == '0');
     CUtensorMap ta, tb, to;
     int rc = make_tmap_2d_u8(ctx, &ta, A, (uint64_t)ga.K, (uint64_t)ga.M, (uint64_t)lda, GEMM_BK, GEMM_BM);
     if (rc) return rc;
-    rc = make_tmap_2d_u8(ctx, &tb, W, (uint64_t)ga.K, (uint64_t)ga.N, (uint64_t)ga.K, GEMM_BK, wide ? 256 : 128);
+    rc = make_tmap_2d_u8(ctx, &tb, W, (uint64_t)ga.K, (uint64_t)ga.N, (uint64_t)ga.K, GEMM_BK, wide ? (cluster ? 128 : 256) : 128);
     if (rc) return rc;
     if constexpr (MODE == GM_RQ_I8 || MODE == GM_RQ_I16) {
         // Output staged through shared memory and written by TMA when the destination allows it
@@ -644,13 +689,18 @@ static int dispatch_bn(ivit_ctx* ctx, const int8_t* A, int64_t lda, const int8_t
             // byte-typed view of the output: inner dim = N*ES bytes, box = 128 bytes x 128 rows, 128B swizzle
             rc = make_tmap_2d_u8(ctx, &to, ga.out, (uint64_t)ga.N * ES, (uint64_t)ga.M, (uint64_t)ga.out_ld * ES, 128, GEMM_BM);
             if (rc) return rc;
-            if (wide) return launch_gemm<256, 3, MODE, true>(ctx, ta, tb, to, ga, s);
-            return launch_gemm<128, 5, MODE, true>(ctx, ta, tb, to, ga, s);
+            if (wide && cluster) return launch_gemm<256, 3, MODE, true, 2, 1>(ctx, ta, tb, to, ga, s);
+            if (wide) return launch_gemm<256, 3, MODE, true, 1, 1>(ctx, ta, tb, to, ga, s);
+            return launch_gemm<128, 5, MODE, true, 1, 1>(ctx, ta, tb, to, ga, s);
         }
     }
     to = ta;
-    if (wide) return launch_gemm<256, 4, MODE, false>(ctx, ta, tb, to, ga, s);
-    return launch_gemm<128, 6, MODE, false>(ctx, ta, tb, to, ga, s);
+    if (wide && cluster) {                            // W box was sized for the cluster: rebuild for the plain kernel
+        rc = make_tmap_2d_u8(ctx, &tb, W, (uint64_t)ga.K, (uint64_t)ga.N, (uint64_t)ga.K, GEMM_BK, 256);
+        if (rc) return rc;
+    }
+    if (wide) return launch_gemm<256, 4, MODE, false, 1, 1>(ctx, ta, tb, to, ga, s);
+    return launch_gemm<128, 6, MODE, false, 1, 1>(ctx, ta, tb, to, ga, s);
 }
 
 }  // namespace ivit

@@ -60,6 +60,24 @@ IVIT_PTX void tma_load_3d(uint32_t dst_smem, const void* tmap, uint32_t bar, int
         ::"r"(dst_smem), "l"(tmap), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
         : "memory");
 }
+// Same, multicast: the tile lands at the same CTA-relative shared address in every CTA of `cta_mask` and signals
+// the mbarrier at the same CTA-relative address in each of them.
+IVIT_PTX void tma_load_2d_mc(uint32_t dst_smem, const void* tmap, uint32_t bar, int32_t c0, int32_t c1, uint16_t cta_mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+        " [%0], [%1, {%4, %5}], [%2], %3;"
+        ::"r"(dst_smem), "l"(tmap), "r"(bar), "h"(cta_mask), "r"(c0), "r"(c1)
+        : "memory");
+}
+// ---- thread-block clusters ---------------------------------------------------------------
+IVIT_PTX uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+IVIT_PTX void cluster_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 // 2D tile store shared -> global (bulk async group).
 IVIT_PTX void tma_store_2d(const void* tmap, uint32_t src_smem, int32_t c0, int32_t c1) {
     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
@@ -94,6 +112,11 @@ IVIT_PTX void mma_i8_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint3
 // Arrive on an mbarrier when all previously issued tcgen05.mma of this thread have completed.
 IVIT_PTX void mma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// Same, arriving on the mbarrier at the same CTA-relative address in every CTA of `cta_mask`.
+IVIT_PTX void mma_commit_mc(uint32_t bar, uint16_t cta_mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"(cta_mask) : "memory");
 }
 IVIT_PTX void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 // 32 lanes x 32 consecutive 32-bit columns: thread i of the warp gets lane (base_lane + i).
