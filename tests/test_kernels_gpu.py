@@ -251,7 +251,8 @@ def test_gemm_matches_oracle_kat(K, kat):
     assert np.array_equal(got.cpu().numpy(), want)
 
 
-@pytest.mark.parametrize("M,N,K_", [(197, 192, 192), (300, 768, 768), (256, 3072, 768), (130, 1000, 768)])
+@pytest.mark.parametrize("M,N,K_", [(197, 192, 192), (300, 768, 768), (256, 3072, 768), (130, 1000, 768),
+                                    (1300, 2304, 768), (2048, 768, 256), (640, 1024, 128)])     # M >= 512: 2-CTA clusters (W multicast)
 @pytest.mark.parametrize("e_lo,e_hi", [(33, 44), (20, 50)])
 def test_gemm_requant_i8(K, M, N, K_, e_lo, e_hi):
     rng = np.random.default_rng(M + N + K_ + e_lo)
@@ -268,7 +269,7 @@ def test_gemm_requant_i8(K, M, N, K_, e_lo, e_hi):
     assert_equal(got, want, "gemm rq8 acc_bits=%d %dx%dx%d" % (bits, M, N, K_))
 
 
-@pytest.mark.parametrize("M,N,K_", [(197, 192, 768), (300, 768, 3072), (128, 256, 128)])
+@pytest.mark.parametrize("M,N,K_", [(197, 192, 768), (300, 768, 3072), (128, 256, 128), (1411, 768, 768), (1024, 1280, 384)])
 @pytest.mark.parametrize("variant", ["plain", "residual", "two_stage"])
 def test_gemm_requant_i16(K, M, N, K_, variant):
     rng = np.random.default_rng(M + N + K_ + len(variant))
