@@ -139,7 +139,7 @@ attention_kernel(const int8_t* __restrict__ qkv, const AttnArgs p, int8_t* __res
         }
         // ---- S = Q K^T, requantised tile by tile to int8 (qact_attn1 [+ rel-pos bias, mask]) and packed four per
         //      word: {row r0: col 2q, 2q+1 ; row r1: col 2q, 2q+1}; padding columns / masked entries -> -128 ----
-        int32_t mx0 = -128, mx1 = -128;
+        uint32_t mxw = 0x80808080u;                   // per-byte running max of the packed scores (bytes 0,1: row r0; 2,3: row r1)
         uint32_t masked_bits = 0u;                    // Swin only (NT <= 8): 4 bits per tile
         auto score_tile = [&](int t, bool boundary) {
             int32_t acc[4] = {0, 0, 0, 0};
@@ -152,9 +152,10 @@ attention_kernel(const int8_t* __restrict__ qkv, const AttnArgs p, int8_t* __res
             int32_t v[4];
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
-                v[c] = clamp_bits<8>(rq_scores(acc[c]));
+                v[c] = rq_scores(acc[c]);                                    // clamped to int8 by the saturating pack below
                 const bool pad = boundary && ((8 * t + (c & 1)) >= col_lim);
                 if (SWIN) {
+                    v[c] = clamp_bits<8>(v[c]);
                     const int col = 8 * t + 2 * q4 + (c & 1);
                     const int row = (c < 2) ? r0 : r1;
                     if (!pad && row < n_tok) {
@@ -175,17 +176,20 @@ attention_kernel(const int8_t* __restrict__ qkv, const AttnArgs p, int8_t* __res
                 }
                 if (pad) v[c] = -128;                                        // never raises the row max
             }
-            mx0 = max(mx0, max(v[0], v[1]));
-            mx1 = max(mx1, max(v[2], v[3]));
-            my_sv[t * 32] = __byte_perm(__byte_perm((uint32_t)v[0], (uint32_t)v[1], 0x0040),
-                                        __byte_perm((uint32_t)v[2], (uint32_t)v[3], 0x0040), 0x5410);
+            uint32_t hi2, w;                                                 // saturate to int8 and pack: v0 | v1<<8 | v2<<16 | v3<<24
+            asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, %3;" : "=r"(hi2) : "r"(v[3]), "r"(v[2]), "r"(0));
+            asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, %3;" : "=r"(w) : "r"(v[1]), "r"(v[0]), "r"(hi2));
+            mxw = __vmaxs4(mxw, w);
+            my_sv[t * 32] = w;
         };
 #pragma unroll 1
         for (int t = 0; t < nt_full; ++t) score_tile(t, false);
         if (nt_used > nt_full) score_tile(nt_full, true);
         for (int t = nt_used; t < NT; ++t) my_sv[t * 32] = 0x80808080u;      // unused tiles: valid LUT index, V rows are zero
-        mx0 = max(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = max(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
-        mx1 = max(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = max(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+        mxw = __vmaxs4(mxw, __shfl_xor_sync(0xffffffffu, mxw, 1));
+        mxw = __vmaxs4(mxw, __shfl_xor_sync(0xffffffffu, mxw, 2));
+        const int32_t mx0 = max((int32_t)(int8_t)(mxw & 0xff), (int32_t)(int8_t)((mxw >> 8) & 0xff));
+        const int32_t mx1 = max((int32_t)(int8_t)((mxw >> 16) & 0xff), (int32_t)mxw >> 24);
         // ---- exponentials (LUT over max - q): E for the four entries of packed word w of tile t ----
         const int32_t* sE0 = sE + mx0;
         const int32_t* sE1 = sE + mx1;
@@ -225,6 +229,11 @@ attention_kernel(const int8_t* __restrict__ qkv, const AttnArgs p, int8_t* __res
         const uint32_t S1 = sum1 > 2147483647ULL ? 2147483647u : (uint32_t)sum1;
         const uint32_t F0 = 2147483647u / (S0 ? S0 : 1u);
         const uint32_t F1 = 2147483647u / (S1 ? S1 : 1u);
+        // P = (E*F) >> p_shift == umulhi(E, F << (32 - p_shift)) when F << (32 - p_shift) fits 32 bits
+        // (F <= (2^31-1)/E_max and E_max >= |x0| * 2^(n-2) >= 2^13 for n = 15: F < 2^18 ... checked, else two-step form)
+        const int lsh = 32 - p.p_shift;
+        const bool hi_form = (F0 >> p.p_shift) == 0u && (F1 >> p.p_shift) == 0u;
+        const uint32_t F0s = F0 << lsh, F1s = F1 << lsh;
 
         // ---- O = P V with P = (E * F) >> p_shift (E*F <= S*F < 2^31: 32-bit product), hi/lo byte planes.
         //      No padding checks here: V rows of padding tokens are zero in shared memory. ----
@@ -243,8 +252,13 @@ attention_kernel(const int8_t* __restrict__ qkv, const AttnArgs p, int8_t* __res
             for (int tt = 0; tt < 4; ++tt) {
                 uint32_t E[4];
                 expo4(4 * kc + tt, my_sv[(4 * kc + tt) * 32], E, false);
-                P[tt][0] = (E[0] * F0) >> p.p_shift; P[tt][1] = (E[1] * F0) >> p.p_shift;
-                P[tt][2] = (E[2] * F1) >> p.p_shift; P[tt][3] = (E[3] * F1) >> p.p_shift;
+                if (hi_form) {                                               // warp-divergence free in practice (same for all rows)
+                    P[tt][0] = __umulhi(E[0], F0s); P[tt][1] = __umulhi(E[1], F0s);
+                    P[tt][2] = __umulhi(E[2], F1s); P[tt][3] = __umulhi(E[3], F1s);
+                } else {
+                    P[tt][0] = (E[0] * F0) >> p.p_shift; P[tt][1] = (E[1] * F0) >> p.p_shift;
+                    P[tt][2] = (E[2] * F1) >> p.p_shift; P[tt][3] = (E[3] * F1) >> p.p_shift;
+                }
             }
             uint32_t alo[4], ahi[4];
 #pragma unroll

@@ -195,6 +195,103 @@ layernorm_i16_i8_kernel(const int16_t* __restrict__ x, int64_t rows, int C, cons
     }
 }
 
+// ------------------------------------------------------------------------------------
+// Stem: input QuantAct (fp32 -> int8, vit_quant.py:257) fused with the patch unfold of QuantConv2d
+// (kernel == stride, layers_quant.py:190): one pass over the fp32 image, no int8 image round trip.
+//   out[(b*Hp + y/p)*Wp + x/p, (c*p + y%p)*p + x%p] = clamp8(RNE(fp32(1/s) * img[b,c,y,x]))
+// One thread per 4 horizontally adjacent pixels (p % 4 == 0): 16-byte loads, 4-byte stores.
+// ------------------------------------------------------------------------------------
+__global__ void quantize_patchify_kernel(const float4* __restrict__ img, const float* __restrict__ scale, int B, int Cin,
+                                         int H, int W, int p, int8_t* __restrict__ out) {
+    const float inv = __fdiv_rn(1.0f, scale[0]);
+    const int W4 = W >> 2, Hp = H / p, Wp = W / p, K = Cin * p * p;
+    const int64_t n4 = (int64_t)B * Cin * H * W4;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+        const int x4 = (int)(i % W4);
+        int64_t r = i / W4;
+        const int y = (int)(r % H); r /= H;
+        const int c = (int)(r % Cin);
+        const int64_t b = r / Cin;
+        const float4 v = __ldg(img + i);
+        const int x = x4 * 4;
+        const int64_t row = (b * Hp + y / p) * Wp + x / p;
+        const int col = (c * p + y % p) * p + x % p;
+        char4 o;
+        o.x = (signed char)fminf(fmaxf(rintf(__fmul_rn(inv, v.x)), -128.f), 127.f);
+        o.y = (signed char)fminf(fmaxf(rintf(__fmul_rn(inv, v.y)), -128.f), 127.f);
+        o.z = (signed char)fminf(fmaxf(rintf(__fmul_rn(inv, v.z)), -128.f), 127.f);
+        o.w = (signed char)fminf(fmaxf(rintf(__fmul_rn(inv, v.w)), -128.f), 127.f);
+        *reinterpret_cast<char4*>(out + row * (int64_t)K + col) = o;
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// Stem: cls-token concatenation + position-embedding residual QuantAct (vit_quant.py:259-265), 8 channels per
+// thread, scalar dyadics analysed on the host (same unified form as the GEMM epilogue's second stage).
+// ------------------------------------------------------------------------------------
+struct EmbRq { int32_t m, ls, rs, himask; long long half; int tie; };
+
+__device__ __forceinline__ int32_t emb_rq(const EmbRq& u, int32_t z) {
+    const long long t = (long long)(z << u.ls) * (long long)u.m + u.half;
+    const int32_t hi = (int32_t)(t >> 32);
+    int32_t q = hi >> u.rs;
+    if (u.tie) {
+        const bool tie = ((uint32_t)t == 0u) && ((hi & u.himask) == 0);
+        q -= (int32_t)(tie & (q & 1));
+    }
+    return q;
+}
+
+__global__ void embed_tokens_fast_kernel(const int16_t* __restrict__ pe, const int32_t* __restrict__ cls,
+                                         const int16_t* __restrict__ pos, int B, int n_tok, int C, EmbRq rq, EmbRq rqp,
+                                         ivit_dyadic_t me, int16_t* __restrict__ out) {
+    const int C8 = C >> 3;
+    const int64_t n8 = (int64_t)B * n_tok * C8;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (int64_t)gridDim.x * blockDim.x) {
+        const int c8 = (int)(i % C8);
+        const int64_t r = i / C8;
+        const int t = (int)(r % n_tok);
+        const int64_t b = r / n_tok;
+        const uint4 pv = __ldg(reinterpret_cast<const uint4*>(pos + (int64_t)t * C) + c8);
+        const uint32_t pw[4] = {pv.x, pv.y, pv.z, pv.w};
+        int32_t z[8];
+        if (t == 0) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) z[u] = cls[c8 * 8 + u];
+        } else {
+            const uint4 v = __ldg(reinterpret_cast<const uint4*>(pe + (b * (n_tok - 1) + (t - 1)) * (int64_t)C) + c8);
+            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { z[2 * u] = (int32_t)(int16_t)(w[u] & 0xffff); z[2 * u + 1] = (int32_t)w[u] >> 16; }
+        }
+        uint32_t o[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            int32_t q[2];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int32_t zz = z[2 * u + h];
+                const int32_t pz = h ? ((int32_t)pw[u] >> 16) : (int32_t)(int16_t)(pw[u] & 0xffff);
+                // the cls token is not a QuantAct output: it may exceed 16 bits -> exact general form for row 0
+                const int32_t a = (t == 0) ? requant32_general(zz, me.m, me.e) : emb_rq(rq, zz);
+                q[h] = a + emb_rq(rqp, pz);
+            }
+            asm("cvt.pack.sat.s16.s32 %0, %1, %2;" : "=r"(o[u]) : "r"(q[1]), "r"(q[0]));
+        }
+        reinterpret_cast<uint4*>(out)[i] = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+}
+
+static bool make_emb_rq(ivit_dyadic_t d, EmbRq* r) {
+    if (d.m == 0 || d.e < 16 || d.e > 62) return false;
+    r->m = d.m;
+    if (d.e < 32) { r->ls = 32 - d.e; r->rs = 0; r->half = 1LL << 31; }
+    else { r->ls = 0; r->rs = d.e - 32; r->half = 1LL << (d.e - 1); }
+    r->himask = (1 << r->rs) - 1;
+    r->tie = (d.e - 1 - __builtin_ctz((unsigned)d.m) <= 15) ? 1 : 0;
+    return true;
+}
+
 }  // namespace ivit
 
 using namespace ivit;
@@ -225,6 +322,34 @@ int ivit_shiftgelu_lut(ivit_ctx* ctx, const int8_t* q, int64_t rows, int cols, c
     if (nv <= 2) GL(2); else if (nv <= 4) GL(4); else if (nv <= 6) GL(6); else GL(8);
 #undef GL
     IVIT_LAUNCH_OK("gelu_lut_apply_kernel");
+    return IVIT_OK;
+}
+
+int ivit_quantize_patchify(ivit_ctx* ctx, const float* img, const float* scale, int B, int Cin, int H, int W, int p,
+                           int8_t* out, ivit_stream stream) {
+    IVIT_REQUIRE(ctx && img && scale && out && B > 0 && Cin > 0 && p > 0, "ivit_quantize_patchify: bad arguments");
+    IVIT_REQUIRE(H % p == 0 && W % p == 0 && p % 4 == 0 && W % 4 == 0, "ivit_quantize_patchify: H, W multiples of the patch size, patch % 4 == 0");
+    IVIT_REQUIRE(((uintptr_t)img % 16) == 0 && ((uintptr_t)out % 4) == 0, "ivit_quantize_patchify: img must be 16-byte aligned");
+    const int64_t n4 = (int64_t)B * Cin * H * (W / 4);
+    const int64_t blocks = (n4 + 255) / 256;
+    const int grid = (int)(blocks < (int64_t)ctx->num_sms * 16 ? blocks : (int64_t)ctx->num_sms * 16);
+    quantize_patchify_kernel<<<grid, 256, 0, st(stream)>>>((const float4*)img, scale, B, Cin, H, W, p, out);
+    IVIT_LAUNCH_OK("quantize_patchify_kernel");
+    return IVIT_OK;
+}
+
+int ivit_embed_tokens_fast(ivit_ctx* ctx, const int16_t* pe, const int32_t* cls, const int16_t* pos, int B, int n_tok,
+                           int C, ivit_dyadic_t me, ivit_dyadic_t me_res, int16_t* out, ivit_stream stream) {
+    IVIT_REQUIRE(ctx && pe && cls && pos && out && B > 0 && n_tok > 1 && C > 0 && C % 8 == 0, "ivit_embed_tokens_fast: bad arguments (C % 8 == 0)");
+    IVIT_REQUIRE(((uintptr_t)pe % 16) == 0 && ((uintptr_t)pos % 16) == 0 && ((uintptr_t)out % 16) == 0, "ivit_embed_tokens_fast: 16-byte alignment");
+    EmbRq rq, rqp;
+    if (!make_emb_rq(me, &rq) || !make_emb_rq(me_res, &rqp))
+        return fail(IVIT_ENOTSUP, "ivit_embed_tokens_fast: dyadic exponents outside [16, 62]; use ivit_embed_tokens");
+    const int64_t n8 = (int64_t)B * n_tok * (C / 8);
+    const int64_t blocks = (n8 + 255) / 256;
+    const int grid = (int)(blocks < (int64_t)ctx->num_sms * 16 ? blocks : (int64_t)ctx->num_sms * 16);
+    embed_tokens_fast_kernel<<<grid, 256, 0, st(stream)>>>(pe, cls, pos, B, n_tok, C, rq, rqp, me, out);
+    IVIT_LAUNCH_OK("embed_tokens_fast_kernel");
     return IVIT_OK;
 }
 

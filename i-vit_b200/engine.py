@@ -100,15 +100,23 @@ class Engine:
                       me=t[me_key + ".me"], bits=bits, out=out, acc_bits=self.acc_bits[name], **kw)
 
         # input quantisation (vit_quant.py:257) -> patch unfold -> patch-embedding GEMM (+patch_embed.qact, 16 bit)
-        _quantize_into(b["img"], t["qact_input.scale"], b["img_q"]); n += 1
-        tap("qact_input", b["img_q"])
-        K.call("ivit_patchify_i8", K.context(self.device), K.ptr(b["img_q"]), B, m["in_chans"], m["img_size"],
-               m["img_size"], m["patch"], K.ptr(b["patches"])); n += 1
+        if taps is None and m["patch"] % 4 == 0:
+            K.quantize_patchify(b["img"], t["qact_input.scale"], m["patch"], out=b["patches"]); n += 1   # one fused pass
+        else:
+            _quantize_into(b["img"], t["qact_input.scale"], b["img_q"]); n += 1
+            tap("qact_input", b["img_q"])
+            K.call("ivit_patchify_i8", K.context(self.device), K.ptr(b["img_q"]), B, m["in_chans"], m["img_size"],
+                   m["img_size"], m["patch"], K.ptr(b["patches"])); n += 1
         lin("patch_embed.proj", b["patches"], b["pe16"], "patch_embed.qact", 16); n += 1
         tap("patch_embed.qact", b["pe16"])
         # cls token + position embedding residual (vit_quant.py:259-265)
-        K.embed_tokens(b["pe16"], t["cls_token_integer"], t["pos_embed_integer"], B, N, C,
-                       s["qact1.me"], s["qact1.me_res"], 16, out=b["xa"]); n += 1
+        e_ok = all(16 <= s[k][1] <= 62 for k in ("qact1.me", "qact1.me_res"))
+        if e_ok and C % 8 == 0:
+            K.embed_tokens_fast(b["pe16"], t["cls_token_integer"], t["pos_embed_integer"], B, N, C,
+                                s["qact1.me"], s["qact1.me_res"], out=b["xa"]); n += 1
+        else:
+            K.embed_tokens(b["pe16"], t["cls_token_integer"], t["pos_embed_integer"], B, N, C,
+                           s["qact1.me"], s["qact1.me_res"], 16, out=b["xa"]); n += 1
         tap("qact1", b["xa"])
         x, x2 = b["xa"], b["xb"]
         for i in range(m["depth"]):

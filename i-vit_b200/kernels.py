@@ -244,3 +244,21 @@ def layernorm_i16_i8(x: torch.Tensor, bias_int: torch.Tensor, me: torch.Tensor, 
         out = torch.empty(x.shape, dtype=torch.int8, device=x.device)
     call("ivit_layernorm_i16_i8", context(x.device), ptr(x), x.numel() // Cc, Cc, ptr(bias_int), ptr(me), ptr(out))
     return out
+
+
+def quantize_patchify(img: torch.Tensor, scale: torch.Tensor, patch: int, out: torch.Tensor = None):
+    """fp32 NCHW image -> int8 patch rows (input QuantAct + unfold in one pass)."""
+    assert img.dtype == torch.float32 and img.dim() == 4 and img.is_contiguous()
+    B, Cin, H, W = img.shape
+    if out is None:
+        out = torch.empty((B * (H // patch) * (W // patch), Cin * patch * patch), dtype=torch.int8, device=img.device)
+    call("ivit_quantize_patchify", context(img.device), ptr(img), ptr(scale), B, Cin, H, W, patch, ptr(out))
+    return out
+
+
+def embed_tokens_fast(pe16, cls32, pos16, B: int, n_tok: int, C: int, me, me_res, out=None):
+    if out is None:
+        out = torch.empty((B * n_tok, C), dtype=torch.int16, device=pe16.device)
+    call("ivit_embed_tokens_fast", context(pe16.device), ptr(pe16), ptr(cls32), ptr(pos16), B, n_tok, C,
+         Dyadic(int(me[0]), int(me[1])), Dyadic(int(me_res[0]), int(me_res[1])), ptr(out))
+    return out

@@ -236,6 +236,17 @@ IVIT_API int ivit_layernorm_i16_i8(ivit_ctx*, const int16_t* x, int64_t rows, in
                                    const int32_t* bias_int, const ivit_dyadic_t* me, int8_t* out,
                                    ivit_stream stream);
 
+/* Input QuantAct (vit_quant.py:257, quant_utils.py:48,90-92) fused with the patch unfold of a kernel == stride
+ * QuantConv2d (layers_quant.py:190): fp32 NCHW image -> int8 GEMM rows, same result as
+ * ivit_quantize_f32(bits 8) followed by ivit_patchify_i8.  patch % 4 == 0. */
+IVIT_API int ivit_quantize_patchify(ivit_ctx*, const float* img, const float* scale, int B, int Cin, int H,
+                                    int W, int p, int8_t* out, ivit_stream stream);
+
+/* Vectorised form of ivit_embed_tokens (bits 16, C % 8 == 0, dyadic exponents in [16, 62]). */
+IVIT_API int ivit_embed_tokens_fast(ivit_ctx*, const int16_t* pe, const int32_t* cls, const int16_t* pos,
+                                    int B, int n_tok, int C, ivit_dyadic_t me, ivit_dyadic_t me_res,
+                                    int16_t* out, ivit_stream stream);
+
 /* DeiT stem glue: cls-token concatenation followed by the position-embedding residual QuantAct
  * (vit_quant.py:259-265): out[b,t,:] = clamp(RNE(z*me) + RNE(pos[t,:]*me_res), bits) with
  * z = cls (int32 [C], RNE(cls_token / s)) for t == 0 and pe[b, t-1, :] (int16 [B*(n_tok-1), C],

@@ -400,3 +400,29 @@ def test_layernorm_i16_i8_fast(K, C, mag):
     want = O.requant(z, m, e, 8)
     got = K.layernorm_i16_i8(dev(q.astype(np.int16)), dev(bq.astype(np.int32)), me_dev(K, m, e))
     assert_equal(got, want, "layernorm_i16_i8 C=%d" % C)
+
+
+def test_quantize_patchify_fused(K):
+    rng = np.random.default_rng(21)
+    for (B, Cin, H, W, p) in [(2, 3, 32, 48, 16), (3, 3, 16, 16, 4), (1, 3, 224, 224, 16)]:
+        x = (rng.standard_normal((B, Cin, H, W)) * 2).astype(np.float32)
+        s = np.float32(0.0191)
+        q = O.quantize_f32(x, s, 8).astype(np.int8)
+        want = q.reshape(B, Cin, H // p, p, W // p, p).transpose(0, 2, 4, 1, 3, 5).reshape(-1, Cin * p * p)
+        got = K.quantize_patchify(dev(x), dev(np.array([s])), p).cpu().numpy()
+        assert np.array_equal(got, want), (B, Cin, H, W, p)
+
+
+def test_embed_tokens_fast_matches_general(K):
+    rng = np.random.default_rng(22)
+    B, N, C = 3, 17, 64
+    pe = rng.integers(-32768, 32768, (B * (N - 1), C)).astype(np.int16)
+    cls = rng.integers(-200000, 200000, C).astype(np.int32)        # the cls token is not clamped to 16 bits
+    pos = rng.integers(-32768, 32768, (N, C)).astype(np.int16)
+    for (m, e), (m1, e1) in [((1518500250, 31), (1234567891, 33)), ((2 ** 30, 30), (-2 ** 30, 32)), ((1900000001, 40), (1100000000, 17))]:
+        x = np.concatenate([np.broadcast_to(cls.astype(np.int64), (B, 1, C)), pe.reshape(B, N - 1, C).astype(np.int64)], axis=1)
+        want = O.requant(x.reshape(B * N, C), [m], [e], 16, pos.astype(np.int64), [m1], [e1])
+        a = K.embed_tokens(dev(pe), dev(cls), dev(pos), B, N, C, (m, e), (m1, e1), 16)
+        b = K.embed_tokens_fast(dev(pe), dev(cls), dev(pos), B, N, C, (m, e), (m1, e1))
+        assert_equal(a, want, "embed_tokens")
+        assert_equal(b, want, "embed_tokens_fast")
