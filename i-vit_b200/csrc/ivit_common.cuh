@@ -136,15 +136,24 @@ IVIT_DEVINL long long shiftexp(int32_t d, int32_t x0, float inv_x0, int n) {
 // (exactly 10 steps, no early exit).  For V < 2^52 the 64-bit division is done in fp64: V and k are exact
 // doubles, IEEE division is correctly rounded, and a non-integer quotient V/k is at least 1/k >= 2^-26 away
 // from the next integer while the rounding error is below 2^-52 * 2^36, so truncation gives the exact floor.
+//
+// Early exit (exact): with s = floor(sqrt(V)), the iterate strictly decreases while k > s and never drops below s,
+// so after the first step "k_next >= k" happens exactly when k == s; from there the sequence is either constant
+// (k_next == s) or alternates s+1, s, s+1, ... (only when V == (s+1)^2 - 1).  The value after the remaining steps
+// follows from their parity.  Typical rows converge in 4-5 steps instead of 10.
 IVIT_DEVINL unsigned long long ln_isqrt10(unsigned long long V) {
     unsigned long long k = 65536ULL;
-    if (V < (1ULL << 52)) {
-        const double Vd = (double)V;
+    const bool small = V < (1ULL << 52);
+    const double Vd = (double)V;
 #pragma unroll 1
-        for (int it = 0; it < 10; ++it) k = (k + (unsigned long long)(Vd / (double)k)) >> 1;
-    } else {
-#pragma unroll 1
-        for (int it = 0; it < 10; ++it) k = (k + V / k) >> 1;
+    for (int it = 0; it < 10; ++it) {
+        const unsigned long long q = small ? (unsigned long long)(Vd / (double)k) : (V / k);
+        const unsigned long long kn = (k + q) >> 1;
+        if (it > 0 && kn >= k) {                     // k == floor(sqrt(V)) reached: kn is k or k + 1
+            const int rem = 9 - it;                  // steps still to take after this one
+            return (kn == k || (rem & 1)) ? k : kn;
+        }
+        k = kn;
     }
     return k;
 }

@@ -271,6 +271,113 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&r)[CW], const ui
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Fragment-layout epilogue (TMA-store path).  tcgen05.ld.16x256b.x4 hands each thread, for a 16-row x 32-column
+// block, rows {g, g+8} (g = lane/4) and columns {8*cb + 2*q + {0,1}} (q = lane%4, cb = 0..3) -- the layout of an MMA
+// C fragment (cute Copy_Traits<SM100_TMEM_LOAD_16dp256b4x>).  A thread therefore needs the per-column constants of
+// only 8 of the 32 columns and re-uses them for 4 rows: shared-memory traffic for the constants drops 4x relative to
+// the one-row-per-thread 32x32b layout, which was the limiter of the epilogue (128 B/clk/SM of LDS delivery).
+// ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tmem_ld_16x256b_x4(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.16x256b.x4.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
+
+// residual pairs (two adjacent int16 columns per 32-bit word) of one 32-row x 32-column chunk in fragment layout:
+// rr[4*row_slot + cb], row_slot 0..3 <-> tile rows trow0 + 8*row_slot
+__device__ __forceinline__ void load_residual_frag(const GemmArgs& args, int grow0, int gcol0, int q4, uint32_t (&rr)[16]) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) rr[j] = 0u;
+    if (!args.residual) return;
+#pragma unroll
+    for (int rs = 0; rs < 4; ++rs) {
+        const int row = grow0 + 8 * rs;
+        if (row < args.M) {
+            const int16_t* base = reinterpret_cast<const int16_t*>(args.residual) + (long long)row * args.res_ld + gcol0 + 2 * q4;
+#pragma unroll
+            for (int cbk = 0; cbk < 4; ++cbk)
+                if (gcol0 + 8 * cbk < args.N) rr[4 * rs + cbk] = __ldg(reinterpret_cast<const uint32_t*>(base + 8 * cbk));
+        }
+    }
+}
+
+template <int MODE>
+__device__ __forceinline__ void epilogue_chunk_frag(const uint32_t (&ra)[16], const uint32_t (&rb)[16], const uint32_t (&rr)[16],
+                                                    const ColParam* __restrict__ cp, const int32_t* __restrict__ cb,
+                                                    const GemmArgs& args, int fast, uint32_t out_base, int trow0, int g,
+                                                    int q4, int tcol0) {
+    // constants of this thread's 8 columns (one 16-byte shared-memory load each, re-used for 4 rows)
+    ColParam P[8];
+#pragma unroll
+    for (int cbk = 0; cbk < 4; ++cbk)
+#pragma unroll
+        for (int pp = 0; pp < 2; ++pp) {
+            const int4 t = *reinterpret_cast<const int4*>(cp + 8 * cbk + 2 * q4 + pp);
+            P[2 * cbk + pp].m = t.x; P[2 * cbk + pp].sh = t.y;
+            P[2 * cbk + pp].c = (long long)(((unsigned long long)(uint32_t)t.w << 32) | (uint32_t)t.z);
+        }
+    constexpr int ES = (MODE == GM_RQ_I8) ? 1 : 2;
+#pragma unroll
+    for (int rs = 0; rs < 4; ++rs) {
+        const int trow = trow0 + 8 * rs;
+        const uint32_t row_addr = out_base + (uint32_t)trow * 128u;
+#pragma unroll
+        for (int cbk = 0; cbk < 4; ++cbk) {
+            int32_t q[2];
+#pragma unroll
+            for (int pp = 0; pp < 2; ++pp) {
+                const int32_t acc = (int32_t)((rs < 2) ? ra[4 * cbk + 2 * (rs & 1) + pp] : rb[4 * cbk + 2 * (rs & 1) + pp]);
+                const ColParam& p = P[2 * cbk + pp];
+                if (fast == 0) {
+                    q[pp] = requant32_general(acc + cb[8 * cbk + 2 * q4 + pp], p.m, p.sh + 32);
+                } else {
+                    const long long t = (long long)acc * (long long)p.m + p.c;
+                    const int32_t hi = (int32_t)(t >> 32);
+                    int32_t v = hi >> p.sh;
+                    if (fast == 2) {
+                        const bool tie = ((uint32_t)t == 0u) && ((hi & ((1 << p.sh) - 1)) == 0);
+                        v -= (int32_t)(tie & (v & 1));
+                    }
+                    q[pp] = v;
+                }
+            }
+            const int bo = (tcol0 + 8 * cbk + 2 * q4) * ES;                 // byte offset inside the staged tile row
+            const uint32_t addr = row_addr + (uint32_t)(bo >> 7) * (uint32_t)(GEMM_BM * 128) +
+                                  (((((uint32_t)bo >> 4) & 7u) ^ (uint32_t)g) << 4) + ((uint32_t)bo & 15u);
+            if (MODE == GM_RQ_I8) {
+                uint32_t w;
+                asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, %3;" : "=r"(w) : "r"(q[1]), "r"(q[0]), "r"(0));
+                asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"((unsigned short)w) : "memory");
+            } else {
+                const uint32_t rw = rr[4 * rs + cbk];
+#pragma unroll
+                for (int pp = 0; pp < 2; ++pp) {
+                    int32_t v = q[pp];
+                    const int32_t rv = pp ? ((int32_t)rw >> 16) : (int32_t)(int16_t)(rw & 0xffff);
+                    if (args.scalar_mode == 1) {
+                        if (args.two_stage) v = scalar_rq_fast<false>(args.rq2, clamp_bits<16>(v));
+                        if (args.residual) v = add_sat_s32(v, scalar_rq_fast<false>(args.rqr, rv));
+                    } else if (args.scalar_mode == 2) {
+                        if (args.two_stage) v = scalar_rq_fast<true>(args.rq2, clamp_bits<16>(v));
+                        if (args.residual) v = add_sat_s32(v, scalar_rq_fast<true>(args.rqr, rv));
+                    } else {
+                        if (args.two_stage) v = requant32_general(clamp_bits<16>(v), args.rq2.m, args.rq2.e);
+                        if (args.residual) v = sat_i64_to_i32((long long)v + (long long)requant32_general(rv, args.rqr.m, args.rqr.e));
+                    }
+                    q[pp] = v;
+                }
+                const uint32_t w = pack_sat_s16x2(q[0], q[1]);
+                asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(w) : "memory");
+            }
+        }
+    }
+}
+
 template <int CW>
 __device__ __forceinline__ void tmem_ld_chunk(uint32_t taddr, uint32_t (&r)[CW]) {
     if constexpr (CW == 32) ptx::tmem_ld_32x32b_x32(taddr, r);
@@ -418,6 +525,103 @@ gemm_i8_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
                 if (++as == 2) { as = 0; aphase ^= 1u; }
             }
         }
+    } else if constexpr (TS) {
+        // ================= epilogue (warps 2..9), fragment layout + TMA store =================
+        const int ew = warp - 2;                      // 0..7
+        const int lane_group = warp & 3;              // TMEM lanes [32*lane_group, +32) are accessible to this warp
+        const int col_half = ew >> 2;                 // 0: columns [0, BN/2), 1: [BN/2, BN)
+        const int et = ew * 32 + lane;                // 0..255 thread index inside the epilogue group
+        const int g = lane >> 2, q4 = lane & 3;
+        const int trow0 = lane_group * 32 + g;        // this thread's tile rows: trow0 + {0, 8, 16, 24}
+        // per-column constants of the NEXT tile are fetched into registers while the current tile is processed
+        int32_t pre_b = 0;
+        ivit_dyadic_t pre_d = {0, 63};
+        auto fetch_params = [&](int n0f) {
+            pre_b = 0; pre_d.m = 0; pre_d.e = 63;
+            const int n = n0f + et;
+            if (et < BN && n < args.N) {
+                if (args.bias) pre_b = __ldg(args.bias + n);
+                pre_d = args.me[n];
+            }
+        };
+        if (tile_first < num_tiles) fetch_params(tile_n0(tile_first));
+        int as = 0;
+        uint32_t aphase = 0;
+        for (int tile = tile_first; tile < num_tiles; tile += tile_step) {
+            const int m0 = tile_m0(tile), n0 = tile_n0(tile);
+            ColParam* cp = col_params + as * BN;
+            int32_t* cb = col_bias + as * BN;
+            // ---- publish this tile's per-column constants (prefetched) ----
+            int ok = 1, any_tie = 0;
+            if (et < BN) {
+                ColParam p;
+                p.m = pre_d.m; p.sh = pre_d.e - 32; p.c = 0;
+                if (pre_d.m != 0) {
+                    // fast form: t = acc*m + (bias*m + 2^(e-1)); q = hi32(t) >> (e-32), needs 32 <= e <= 62 (whole tile).
+                    // An exact tie needs v2(z) = e-1-ctz(m); unreachable for |z| < 2^acc_bits when e-1-ctz(m) >= acc_bits.
+                    const int tz = __ffs(pre_d.m) - 1;
+                    const bool in_range = (pre_d.e >= 32 && pre_d.e <= 62);
+                    ok = in_range ? 1 : 0;
+                    any_tie = (in_range && (pre_d.e - 1 - tz < args.acc_bits)) ? 1 : 0;
+                    if (pre_d.e >= 1 && pre_d.e <= 62) p.c = (long long)pre_b * (long long)pre_d.m + (1LL << (pre_d.e - 1));
+                } else {
+                    p.sh = 31;
+                }
+                cp[et] = p;
+                cb[et] = pre_b;
+            }
+            if (et == 0) ptx::tma_store_wait_read<0>();            // previous tile's TMA store has finished reading the staging tile
+            int all_ok, some_tie;                                  // barrier + block-wide reductions of the two predicates
+            asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.s32 p, %1, 0;\n\tbarrier.cta.red.and.pred q, 1, 256, p;\n\tselp.s32 %0, 1, 0, q;\n\t}"
+                         : "=r"(all_ok) : "r"(ok) : "memory");
+            asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.s32 p, %1, 0;\n\tbarrier.cta.red.or.pred q, 1, 256, p;\n\tselp.s32 %0, 1, 0, q;\n\t}"
+                         : "=r"(some_tie) : "r"(any_tie) : "memory");
+            const int fast = !all_ok ? 0 : (some_tie ? 2 : 1);
+            {
+                const int nxt = tile + tile_step;
+                if (nxt < num_tiles) fetch_params(tile_n0(nxt));   // latency hidden behind this tile's work
+            }
+            const int c_begin = col_half * (BN / 2);
+            const int c_end = min(c_begin + BN / 2, args.N - n0);  // exclusive, may be <= c_begin
+            const uint32_t t_lo = tmem_base + ((uint32_t)(lane_group * 32) << 16) + (uint32_t)(as * BN);
+            const uint32_t t_hi = t_lo + (16u << 16);
+            uint32_t ra[16], rb[16], res_cur[16], res_nxt[16];
+            if (MODE == GM_RQ_I16 && c_begin < c_end) load_residual_frag(args, m0 + trow0, n0 + c_begin, q4, res_cur);
+
+            ptx::mbar_wait(tfull_bar(as), aphase);
+            ptx::tc_fence_after();
+#pragma unroll 1
+            for (int c0 = c_begin; c0 < c_end; c0 += 32) {
+                tmem_ld_16x256b_x4(t_lo + (uint32_t)c0, ra);
+                tmem_ld_16x256b_x4(t_hi + (uint32_t)c0, rb);
+                if (MODE == GM_RQ_I16 && c0 + 32 < c_end) load_residual_frag(args, m0 + trow0, n0 + c0 + 32, q4, res_nxt);
+                ptx::tmem_ld_wait();
+                epilogue_chunk_frag<MODE>(ra, rb, res_cur, cp + c0, cb + c0, args, fast, out_base, trow0, g, q4, c0);
+                if (MODE == GM_RQ_I16) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) res_cur[j] = res_nxt[j];
+                }
+            }
+            // release the accumulator back to the MMA warp
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(tempty_bar(as));
+            // staged tile -> global: one elected thread issues a TMA store per 128-byte-wide box
+            // (coalesced, asynchronous, clips the M / N tails)
+            ptx::fence_proxy_async();                              // generic-proxy smem writes -> async proxy
+            asm volatile("bar.sync 2, 256;" ::: "memory");
+            if (et == 0) {
+                constexpr int BOX_COLS = 128 / (OUT_ES ? OUT_ES : 1);
+                constexpr int NBOX = BN / BOX_COLS;
+#pragma unroll
+                for (int bx = 0; bx < NBOX; ++bx)
+                    if (n0 + bx * BOX_COLS < args.N && m0 < args.M)
+                        ptx::tma_store_2d(&tmap_out, out_base + (uint32_t)(bx * GEMM_BM * 128), (n0 + bx * BOX_COLS) * OUT_ES, m0);   // byte-typed map
+                ptx::tma_store_commit();
+            }
+            if (++as == 2) { as = 0; aphase ^= 1u; }
+        }
+        if (et == 0) ptx::tma_store_wait<0>();                     // all stores complete before the CTA exits
     } else {
         // ================= epilogue (warps 2..9) =================
         // TMEM lane group is fixed by (warp % 4); the two warps that share a lane group split the tile's columns.
@@ -684,7 +888,8 @@ static int dispatch_bn(ivit_ctx* ctx, const int8_t* A, int64_t lda, const int8_t
         // Output staged through shared memory and written by TMA when the destination allows it
         // (16-byte aligned base and row pitch, full-width clamp); otherwise direct stores.
         constexpr int ES = (MODE == GM_RQ_I8) ? 1 : 2;
-        const bool ts = ((uintptr_t)ga.out % 16 == 0) && ((ga.out_ld * ES) % 16 == 0) && ga.mode_bits == 8 * ES;
+        const bool ts = ((uintptr_t)ga.out % 16 == 0) && ((ga.out_ld * ES) % 16 == 0) && ga.mode_bits == 8 * ES && ga.N % 8 == 0 &&
+                        (!ga.residual || (((uintptr_t)ga.residual % 4) == 0 && ga.res_ld % 2 == 0));
         if (ts) {
             // byte-typed view of the output: inner dim = N*ES bytes, box = 128 bytes x 128 rows, 128B swizzle
             rc = make_tmap_2d_u8(ctx, &to, ga.out, (uint64_t)ga.N * ES, (uint64_t)ga.M, (uint64_t)ga.out_ld * ES, 128, GEMM_BM);
