@@ -99,6 +99,22 @@ def measured_peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
 
 
+def ncu_traffic(kernel_substr):
+    """Average DRAM bytes per launch of a kernel from the newest committed ncu --set full summary
+    (profiles/ncu_full_*.json, written by tools/summarize_ncu.py); None if there is none."""
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "ncu_full_*.json")))
+    if not files:
+        return None, None
+    d = json.load(open(files[-1]))
+    tot_b = tot_n = 0
+    for name, e in d["kernels"].items():
+        if kernel_substr in name:
+            tot_b += e["dram_bytes"]
+            tot_n += e["launches"]
+    return (tot_b / tot_n if tot_n else None), os.path.basename(files[-1])
+
+
 def build_pack(model_name):
     from ivit_b200.calib import build_synthetic
     from ivit_b200.pack import export_deit
@@ -292,7 +308,9 @@ def run_ours(args, rank, world, local_rank):
                            B * 3 * 224 * 224 * 4 / 1e6, act_mb),
                        "int_ops_per_image": int_ops_per_image(eng.meta)},
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "gemm_i8_tcgen05_kernel (all %d GEMM launches of the step)" % sum(g_["launches"] for g_ in gem),
+                         "traffic": ncu_traffic("gemm_i8_tcgen05_kernel")[0], "traffic_source": ncu_traffic("gemm_i8_tcgen05_kernel")[1],
+                         "algorithmic_bytes_per_launch": sum((g_["M"] * g_["K"] + g_["N"] * g_["K"] + g_["M"] * g_["N"] * (1 if g_["name"] in ("qkv", "fc1") else 4))
+                                                             * g_["launches"] for g_ in gem) / sum(g_["launches"] for g_ in gem), "kernel": "gemm_i8_tcgen05_kernel (all %d GEMM launches of the step)" % sum(g_["launches"] for g_ in gem),
                          "peak_source": "2 x bf16_tflops_sustained of MEASURED_PEAKS.json (%s); int8 tensor rate = 2 x bf16" % peak_src,
                          "per_shape": gem, "gemm_share_of_step": gms / ms_step,
                          "whole_step_int_tops": int_ops_per_image(eng.meta) * B / (ms_step * 1e-3) / 1e12},

@@ -26,7 +26,10 @@ namespace ivit {
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 128;          // bytes == int8 elements per k-block (one 128 B swizzle row)
 constexpr int GEMM_UMMA_K = 32;       // K per tcgen05.mma for 8-bit operands
-constexpr int GEMM_EPI_THREADS = 256;  // 8 epilogue warps: 2 per TMEM lane group, each takes half of the tile's columns
+// Fragment-layout epilogue (tcgen05.ld.16x256b): measured SLOWER than the row-per-thread form (profiles/), kept for reference
+constexpr bool GEMM_FRAG_EPILOGUE = false;
+constexpr int GEMM_EPI_WARPS_PER_GROUP = 4;   // epilogue warps per TMEM lane group; each takes 1/4 of the tile's columns
+constexpr int GEMM_EPI_THREADS = 128 * GEMM_EPI_WARPS_PER_GROUP;
 constexpr int GEMM_THREADS = 64 + GEMM_EPI_THREADS;
 
 enum GemmMode { GM_RAW_I32 = 0, GM_CARRIER = 1, GM_RQ_I8 = 2, GM_RQ_I16 = 3 };
@@ -525,8 +528,8 @@ gemm_i8_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
                 if (++as == 2) { as = 0; aphase ^= 1u; }
             }
         }
-    } else if constexpr (TS) {
-        // ================= epilogue (warps 2..9), fragment layout + TMA store =================
+    } else if constexpr (TS && GEMM_FRAG_EPILOGUE) {
+        // ================= epilogue, fragment layout + TMA store (experimental) =================
         const int ew = warp - 2;                      // 0..7
         const int lane_group = warp & 3;              // TMEM lanes [32*lane_group, +32) are accessible to this warp
         const int col_half = ew >> 2;                 // 0: columns [0, BN/2), 1: [BN/2, BN)
@@ -627,8 +630,8 @@ gemm_i8_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
         // TMEM lane group is fixed by (warp % 4); the two warps that share a lane group split the tile's columns.
         const int ew = warp - 2;                      // 0..7
         const int lane_group = warp & 3;              // TMEM lanes [32*lane_group, +32) are accessible to this warp
-        const int col_half = ew >> 2;                 // 0: columns [0, BN/2), 1: [BN/2, BN)
-        const int et = ew * 32 + lane;                // 0..255 thread index inside the epilogue group
+        const int col_part = ew >> 2;                 // which 1/GEMM_EPI_WARPS_PER_GROUP of the tile's columns
+        const int et = ew * 32 + lane;                // thread index inside the epilogue group
         constexpr int CW = (MODE == GM_RQ_I16) ? 16 : 32;
         int as = 0;
         uint32_t aphase = 0;
@@ -641,7 +644,7 @@ gemm_i8_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
                 fast_flag[as] = 1;
                 if (TS) ptx::tma_store_wait_read<0>();        // previous tile's TMA store has finished reading the staging tile
             }
-            asm volatile("bar.sync 1, 256;" ::: "memory");
+            asm volatile("bar.sync 1, %0;" ::"n"(GEMM_EPI_THREADS) : "memory");
             {
                 int ok = 1, any_tie = 0;
                 for (int c = et; c < BN; c += GEMM_EPI_THREADS) {
@@ -674,14 +677,15 @@ gemm_i8_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
                 if (!ok) atomicAnd(&fast_flag[as], 0);                 // bit 0: all columns in the fast range
                 if (any_tie) atomicOr(&fast_flag[as], 2);              // bit 1: some column can reach an exact tie
             }
-            asm volatile("bar.sync 1, 256;" ::: "memory");
+            asm volatile("bar.sync 1, %0;" ::"n"(GEMM_EPI_THREADS) : "memory");
             const int ff = fast_flag[as];
             const int fast = !(ff & 1) ? 0 : ((ff & 2) ? 2 : 1);
 
             const int row = m0 + lane_group * 32 + lane;
             const bool row_ok = row < args.M;
-            const int c_begin = col_half * (BN / 2);
-            const int c_end = min(c_begin + BN / 2, args.N - n0);        // exclusive, may be <= c_begin
+            constexpr int CPART = BN / GEMM_EPI_WARPS_PER_GROUP;
+            const int c_begin = col_part * CPART;
+            const int c_end = min(c_begin + CPART, args.N - n0);         // exclusive, may be <= c_begin
             const uint32_t t_row = tmem_base + ((uint32_t)(lane_group * 32) << 16) + (uint32_t)(as * BN);
 
             uint32_t ra[CW], rb[CW], resa[CW / 2], resb[CW / 2];
@@ -723,7 +727,7 @@ gemm_i8_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
                 // staged tile -> global: one elected thread issues a TMA store per 128-byte-wide box
                 // (coalesced, asynchronous, clips the M / N tails)
                 ptx::fence_proxy_async();                          // generic-proxy smem writes -> async proxy
-                asm volatile("bar.sync 2, 256;" ::: "memory");
+                asm volatile("bar.sync 2, %0;" ::"n"(GEMM_EPI_THREADS) : "memory");
                 if (et == 0) {
                     constexpr int BOX_COLS = 128 / (OUT_ES ? OUT_ES : 1);
                     constexpr int NBOX = BN / BOX_COLS;

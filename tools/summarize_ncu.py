@@ -49,6 +49,23 @@ def full(src, dst):
     out = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
     hdr, units = rows[0], rows[1]
+    # machine-readable per-kernel DRAM traffic (bench.py's roofline.traffic reads this file)
+    import json
+    traffic = {}
+    for r in rows[2:]:
+        d = dict(zip(hdr, r))
+        def val(k):
+            v = float(d[k].replace(",", ""))
+            u = units[hdr.index(k)].lower()
+            return v * {"byte": 1, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}.get(u, 1)
+        name = re.sub(r"\(.*", "", d.get("Kernel Name", "?"))
+        e = traffic.setdefault(name, {"launches": 0, "dram_bytes": 0.0, "time_us": 0.0})
+        e["launches"] += 1
+        e["dram_bytes"] += val("dram__bytes_read.sum") + val("dram__bytes_write.sum")
+        tu = units[hdr.index("gpu__time_duration.sum")].lower()
+        e["time_us"] += float(d["gpu__time_duration.sum"].replace(",", "")) * {"ns": 1e-3, "us": 1, "usecond": 1, "ms": 1e3, "msecond": 1e3, "nsecond": 1e-3}.get(tu, 1)
+    with open(dst.replace(".md", ".json"), "w") as f:
+        json.dump({"source": src, "kernels": traffic}, f, indent=1)
     with open(dst, "w") as f:
         f.write("# ncu --set full summary\n\nSource: `%s` (`ncu --set full --clock-control none --import-source on`).\n\n" % src)
         for r in rows[2:]:
