@@ -26,9 +26,7 @@ namespace ivit {
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 128;          // bytes == int8 elements per k-block (one 128 B swizzle row)
 constexpr int GEMM_UMMA_K = 32;       // K per tcgen05.mma for 8-bit operands
-// Fragment-layout epilogue (tcgen05.ld.16x256b): measured SLOWER than the row-per-thread form (profiles/), kept for reference
-constexpr bool GEMM_FRAG_EPILOGUE = false;
-constexpr int GEMM_EPI_WARPS_PER_GROUP = 4;   // epilogue warps per TMEM lane group; each takes 1/4 of the tile's columns
+constexpr int GEMM_EPI_WARPS_PER_GROUP = 2;   // epilogue warps per TMEM lane group; each takes 1/2 of the tile's columns
 constexpr int GEMM_EPI_THREADS = 128 * GEMM_EPI_WARPS_PER_GROUP;
 constexpr int GEMM_THREADS = 64 + GEMM_EPI_THREADS;
 
@@ -98,6 +96,15 @@ struct alignas(16) ColParam {         // per output column, staged in shared mem
     int32_t sh;                       // e - 32
     long long c;                      // bias*m + 2^(e-1): the fast requant is hi32(acc*m + c) >> sh
 };
+
+// one 16-byte (warp-broadcast) shared-memory load per column: the epilogue is bounded by shared-memory wavefronts
+__device__ __forceinline__ ColParam ld_col_param(const ColParam* p) {
+    const int4 t = *reinterpret_cast<const int4*>(p);
+    ColParam r;
+    r.m = t.x; r.sh = t.y;
+    r.c = (long long)(((unsigned long long)(uint32_t)t.w << 32) | (uint32_t)t.z);
+    return r;
+}
 
 __device__ __forceinline__ uint32_t pack_sat_s8x4(int32_t a, int32_t b, int32_t c, int32_t d) {
     uint32_t hi, r;
@@ -175,14 +182,14 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&r)[CW], const ui
     if (fast == 1) {
 #pragma unroll
         for (int j = 0; j < CW; ++j) {
-            const ColParam p = cp[j];
+            const ColParam p = ld_col_param(cp + j);
             const long long t = (long long)(int32_t)r[j] * (long long)p.m + p.c;
             q[j] = (int32_t)(t >> 32) >> p.sh;
         }
     } else if (fast == 2) {
 #pragma unroll
         for (int j = 0; j < CW; ++j) {
-            const ColParam p = cp[j];
+            const ColParam p = ld_col_param(cp + j);
             const long long t = (long long)(int32_t)r[j] * (long long)p.m + p.c;
             const int32_t hi = (int32_t)(t >> 32);
             int32_t v = hi >> p.sh;
@@ -192,7 +199,7 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&r)[CW], const ui
     } else {
 #pragma unroll
         for (int j = 0; j < CW; ++j) {
-            const ColParam p = cp[j];
+            const ColParam p = ld_col_param(cp + j);
             q[j] = requant32_general((int32_t)r[j] + cb[j], p.m, p.sh + 32);
         }
     }
@@ -274,113 +281,6 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&r)[CW], const ui
     }
 }
 
-// ------------------------------------------------------------------------------------------------------------
-// Fragment-layout epilogue (TMA-store path).  tcgen05.ld.16x256b.x4 hands each thread, for a 16-row x 32-column
-// block, rows {g, g+8} (g = lane/4) and columns {8*cb + 2*q + {0,1}} (q = lane%4, cb = 0..3) -- the layout of an MMA
-// C fragment (cute Copy_Traits<SM100_TMEM_LOAD_16dp256b4x>).  A thread therefore needs the per-column constants of
-// only 8 of the 32 columns and re-uses them for 4 rows: shared-memory traffic for the constants drops 4x relative to
-// the one-row-per-thread 32x32b layout, which was the limiter of the epilogue (128 B/clk/SM of LDS delivery).
-// ------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void tmem_ld_16x256b_x4(uint32_t taddr, uint32_t (&r)[16]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.16x256b.x4.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr)
-        : "memory");
-}
-
-// residual pairs (two adjacent int16 columns per 32-bit word) of one 32-row x 32-column chunk in fragment layout:
-// rr[4*row_slot + cb], row_slot 0..3 <-> tile rows trow0 + 8*row_slot
-__device__ __forceinline__ void load_residual_frag(const GemmArgs& args, int grow0, int gcol0, int q4, uint32_t (&rr)[16]) {
-#pragma unroll
-    for (int j = 0; j < 16; ++j) rr[j] = 0u;
-    if (!args.residual) return;
-#pragma unroll
-    for (int rs = 0; rs < 4; ++rs) {
-        const int row = grow0 + 8 * rs;
-        if (row < args.M) {
-            const int16_t* base = reinterpret_cast<const int16_t*>(args.residual) + (long long)row * args.res_ld + gcol0 + 2 * q4;
-#pragma unroll
-            for (int cbk = 0; cbk < 4; ++cbk)
-                if (gcol0 + 8 * cbk < args.N) rr[4 * rs + cbk] = __ldg(reinterpret_cast<const uint32_t*>(base + 8 * cbk));
-        }
-    }
-}
-
-template <int MODE>
-__device__ __forceinline__ void epilogue_chunk_frag(const uint32_t (&ra)[16], const uint32_t (&rb)[16], const uint32_t (&rr)[16],
-                                                    const ColParam* __restrict__ cp, const int32_t* __restrict__ cb,
-                                                    const GemmArgs& args, int fast, uint32_t out_base, int trow0, int g,
-                                                    int q4, int tcol0) {
-    // constants of this thread's 8 columns (one 16-byte shared-memory load each, re-used for 4 rows)
-    ColParam P[8];
-#pragma unroll
-    for (int cbk = 0; cbk < 4; ++cbk)
-#pragma unroll
-        for (int pp = 0; pp < 2; ++pp) {
-            const int4 t = *reinterpret_cast<const int4*>(cp + 8 * cbk + 2 * q4 + pp);
-            P[2 * cbk + pp].m = t.x; P[2 * cbk + pp].sh = t.y;
-            P[2 * cbk + pp].c = (long long)(((unsigned long long)(uint32_t)t.w << 32) | (uint32_t)t.z);
-        }
-    constexpr int ES = (MODE == GM_RQ_I8) ? 1 : 2;
-#pragma unroll
-    for (int rs = 0; rs < 4; ++rs) {
-        const int trow = trow0 + 8 * rs;
-        const uint32_t row_addr = out_base + (uint32_t)trow * 128u;
-#pragma unroll
-        for (int cbk = 0; cbk < 4; ++cbk) {
-            int32_t q[2];
-#pragma unroll
-            for (int pp = 0; pp < 2; ++pp) {
-                const int32_t acc = (int32_t)((rs < 2) ? ra[4 * cbk + 2 * (rs & 1) + pp] : rb[4 * cbk + 2 * (rs & 1) + pp]);
-                const ColParam& p = P[2 * cbk + pp];
-                if (fast == 0) {
-                    q[pp] = requant32_general(acc + cb[8 * cbk + 2 * q4 + pp], p.m, p.sh + 32);
-                } else {
-                    const long long t = (long long)acc * (long long)p.m + p.c;
-                    const int32_t hi = (int32_t)(t >> 32);
-                    int32_t v = hi >> p.sh;
-                    if (fast == 2) {
-                        const bool tie = ((uint32_t)t == 0u) && ((hi & ((1 << p.sh) - 1)) == 0);
-                        v -= (int32_t)(tie & (v & 1));
-                    }
-                    q[pp] = v;
-                }
-            }
-            const int bo = (tcol0 + 8 * cbk + 2 * q4) * ES;                 // byte offset inside the staged tile row
-            const uint32_t addr = row_addr + (uint32_t)(bo >> 7) * (uint32_t)(GEMM_BM * 128) +
-                                  (((((uint32_t)bo >> 4) & 7u) ^ (uint32_t)g) << 4) + ((uint32_t)bo & 15u);
-            if (MODE == GM_RQ_I8) {
-                uint32_t w;
-                asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, %3;" : "=r"(w) : "r"(q[1]), "r"(q[0]), "r"(0));
-                asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"((unsigned short)w) : "memory");
-            } else {
-                const uint32_t rw = rr[4 * rs + cbk];
-#pragma unroll
-                for (int pp = 0; pp < 2; ++pp) {
-                    int32_t v = q[pp];
-                    const int32_t rv = pp ? ((int32_t)rw >> 16) : (int32_t)(int16_t)(rw & 0xffff);
-                    if (args.scalar_mode == 1) {
-                        if (args.two_stage) v = scalar_rq_fast<false>(args.rq2, clamp_bits<16>(v));
-                        if (args.residual) v = add_sat_s32(v, scalar_rq_fast<false>(args.rqr, rv));
-                    } else if (args.scalar_mode == 2) {
-                        if (args.two_stage) v = scalar_rq_fast<true>(args.rq2, clamp_bits<16>(v));
-                        if (args.residual) v = add_sat_s32(v, scalar_rq_fast<true>(args.rqr, rv));
-                    } else {
-                        if (args.two_stage) v = requant32_general(clamp_bits<16>(v), args.rq2.m, args.rq2.e);
-                        if (args.residual) v = sat_i64_to_i32((long long)v + (long long)requant32_general(rv, args.rqr.m, args.rqr.e));
-                    }
-                    q[pp] = v;
-                }
-                const uint32_t w = pack_sat_s16x2(q[0], q[1]);
-                asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(w) : "memory");
-            }
-        }
-    }
-}
-
 template <int CW>
 __device__ __forceinline__ void tmem_ld_chunk(uint32_t taddr, uint32_t (&r)[CW]) {
     if constexpr (CW == 32) ptx::tmem_ld_32x32b_x32(taddr, r);
@@ -388,10 +288,11 @@ __device__ __forceinline__ void tmem_ld_chunk(uint32_t taddr, uint32_t (&r)[CW])
 }
 
 // OUT_ES: bytes per output element staged through shared memory for the TMA store (0: direct global stores)
-template <int BN, int STAGES, int OUT_ES>
+// PAIR: the CTA holds only its half of the W tile (the other half lives in the peer CTA of the pair)
+template <int BN, int STAGES, int OUT_ES, bool PAIR>
 struct GemmSmem {
     static constexpr int A_BYTES = GEMM_BM * GEMM_BK;
-    static constexpr int B_BYTES = BN * GEMM_BK;
+    static constexpr int B_BYTES = (PAIR ? BN / 2 : BN) * GEMM_BK;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int OUT_BYTES = GEMM_BM * BN * OUT_ES;                     // [BN*OUT_ES/128 boxes][128 rows][128 B], 128B-swizzled
     static constexpr int PARAM_BYTES = 2 * BN * ((int)sizeof(ColParam) + 4);   // ColParam[2][BN] + int32 bias[2][BN]
@@ -399,17 +300,20 @@ struct GemmSmem {
     static constexpr int TOTAL = STAGES * STAGE_BYTES + OUT_BYTES + PARAM_BYTES + BAR_BYTES + 1024;  // +1024 alignment slack
 };
 
-// CM x CN: thread-block cluster shape.  The CM CTAs of a cluster column work on CM consecutive m-tiles of the same
-// n-tile and share its W tile: each loads 1/CM of it and multicasts (TMA .multicast::cluster) to the others; likewise
-// the CN CTAs of a cluster row share the A tile.  L2 -> SM traffic per CTA and k-block drops from A + W to
-// A/CN + W/CM (the un-clustered kernel is L2-bandwidth bound at ~42 B/clk/SM: profiles/).
-template <int BN, int STAGES, int MODE, bool TS, int CM, int CN>
+// PAIR = true: CTA-pair kernel (tcgen05 cta_group::2).  The two CTAs of a 2-CTA cluster (the two SMs of a TPC) work on
+// two consecutive m-tiles of the same n-tile as ONE 256 x BN MMA: each CTA loads its own 128 rows of A and HALF of the
+// W tile, the leader (even rank) issues the MMAs for both, each CTA gets its 128 accumulator rows in its own TMEM and
+// runs its own epilogue.  Per MMA an SM's shared memory then feeds 128 x 32 B of A + BN/2 x 32 B of W instead of
+// 128 x 32 + BN x 32: the un-paired kernel saturates the SM's shared-memory data pipe (tensor-core operand reads +
+// epilogue LDS/STS ~ 93 % of peak wavefronts, profiles/ncu_full_r1g), which is what bounds it, not the tensor pipe.
+template <int BN, int STAGES, int MODE, bool TS, bool PAIR>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_i8_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                        const __grid_constant__ CUtensorMap tmap_out, const GemmArgs args) {
     constexpr int OUT_ES = !TS ? 0 : (MODE == GM_RQ_I8 ? 1 : 2);
-    using S = GemmSmem<BN, STAGES, OUT_ES>;
+    using S = GemmSmem<BN, STAGES, OUT_ES, PAIR>;
     constexpr uint32_t TMEM_COLS = 2 * BN;            // double-buffered accumulator (256 or 512)
+    constexpr int EPI_WARPS = GEMM_EPI_THREADS / 32;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* smem = smem_raw + (smem_base - ptx::smem_u32(smem_raw));
@@ -430,46 +334,45 @@ gemm_i8_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
 
-    constexpr int CS = CM * CN;
-    const uint32_t crank = (CS > 1) ? ptx::cluster_ctarank() : 0u;
-    const int rx = (int)crank % CN, ry = (int)crank / CN;        // position inside the cluster (N index, M index)
-    uint16_t mask_a = 0, mask_b = 0;                             // CTAs sharing my A tile (same ry) / my W tile (same rx)
-#pragma unroll
-    for (int x = 0; x < CN; ++x) mask_a |= (uint16_t)(1u << (ry * CN + x));
-#pragma unroll
-    for (int y = 0; y < CM; ++y) mask_b |= (uint16_t)(1u << (y * CN + rx));
+    constexpr int CS = PAIR ? 2 : 1;                             // CTAs per cluster, stacked along M
+    const int ry = PAIR ? (int)ptx::cluster_ctarank() : 0;       // 0 = leader
     const int tiles_m = (args.M + GEMM_BM - 1) / GEMM_BM;
     const int tiles_n = (args.N + BN - 1) / BN;
-    const int tiles_m_c = (tiles_m + CM - 1) / CM, tiles_n_c = (tiles_n + CN - 1) / CN;
-    const int num_tiles = tiles_m_c * tiles_n_c;                 // cluster tiles (CM x CN CTA tiles each)
+    const int tiles_m_c = (tiles_m + CS - 1) / CS;
+    const int num_tiles = tiles_m_c * tiles_n;                   // cluster tiles (CS CTA tiles each)
     const int tile_first = (int)blockIdx.x / CS, tile_step = (int)gridDim.x / CS;
     const int num_kb = (args.K + GEMM_BK - 1) / GEMM_BK;
-    // CTA tile of cluster tile `t`: out-of-range tiles (ragged edges of the cluster grid) still run the whole pipeline
-    // (TMA zero-fills, stores are clipped) so that the cluster stays in lock step.
-    auto tile_m0 = [&](int t) { return ((t / tiles_n_c) * CM + ry) * GEMM_BM; };
-    auto tile_n0 = [&](int t) { return ((t % tiles_n_c) * CN + rx) * BN; };
+    // CTA tile of cluster tile `t`: an out-of-range m-tile of the peer (odd tile count) still runs the whole pipeline
+    // (TMA zero-fills, stores are clipped) so that the pair stays in lock step.
+    auto tile_m0 = [&](int t) { return ((t / tiles_n) * CS + ry) * GEMM_BM; };
+    auto tile_n0 = [&](int t) { return (t % tiles_n) * BN; };
 
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tensormap(&tmap_a);
         ptx::prefetch_tensormap(&tmap_b);
         if (TS) ptx::prefetch_tensormap(&tmap_out);
         for (int s = 0; s < STAGES; ++s) {
-            ptx::mbar_init(full_bar(s), 1);
-            ptx::mbar_init(empty_bar(s), CM + CN - 1);     // one tcgen05.commit arrival from every CTA I send tiles to
+            ptx::mbar_init(full_bar(s), 1);                // PAIR: only the leader's is used (both CTAs' loads signal it)
+            ptx::mbar_init(empty_bar(s), 1);               // one tcgen05.commit arrival (PAIR: multicast by the leader)
         }
         for (int s = 0; s < 2; ++s) {
             ptx::mbar_init(tfull_bar(s), 1);
-            ptx::mbar_init(tempty_bar(s), GEMM_EPI_THREADS / 32);   // one arrive per epilogue warp
+            ptx::mbar_init(tempty_bar(s), CS * EPI_WARPS); // one arrive per epilogue warp (PAIR: of both CTAs, on the leader's)
         }
         ptx::fence_barrier_init();
     }
     if (warp == 1) {
-        ptx::tmem_alloc(ptx::smem_u32(const_cast<uint32_t*>(tmem_ptr_smem)), TMEM_COLS);
-        ptx::tmem_relinquish();
+        if (PAIR) {
+            ptx::tmem_alloc_pair(ptx::smem_u32(const_cast<uint32_t*>(tmem_ptr_smem)), TMEM_COLS);
+            ptx::tmem_relinquish_pair();
+        } else {
+            ptx::tmem_alloc(ptx::smem_u32(const_cast<uint32_t*>(tmem_ptr_smem)), TMEM_COLS);
+            ptx::tmem_relinquish();
+        }
     }
     ptx::tc_fence_before();
     __syncthreads();
-    if (CS > 1) ptx::cluster_sync();                       // peers' barriers are initialised before any remote arrive / multicast
+    if (PAIR) ptx::cluster_sync();                         // the peer's barriers and TMEM exist before any remote arrive / pair MMA
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
 
@@ -478,32 +381,38 @@ gemm_i8_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            constexpr int A_ROWS = GEMM_BM / CN, B_ROWS = BN / CM;   // my slice of the shared tiles
+            const uint32_t full0 = PAIR ? ptx::mapa(full_bar(0), 0) : 0u;   // leader's full[0] in the cluster window
             for (int tile = tile_first; tile < num_tiles; tile += tile_step) {
                 const int m0 = tile_m0(tile), n0 = tile_n0(tile);
                 for (int kb = 0; kb < num_kb; ++kb) {
-                    ptx::mbar_wait(empty_bar(stage), phase ^ 1u);    // every consumer of my slices has released the stage
-                    ptx::mbar_arrive_expect_tx(full_bar(stage), S::STAGE_BYTES);   // my own stage receives the full A + W tiles
-                    const uint32_t a_dst = stage_base + stage * S::STAGE_BYTES + rx * (A_ROWS * GEMM_BK);
-                    const uint32_t b_dst = stage_base + stage * S::STAGE_BYTES + S::A_BYTES + ry * (B_ROWS * GEMM_BK);
-                    if (CN > 1) ptx::tma_load_2d_mc(a_dst, &tmap_a, full_bar(stage), kb * GEMM_BK, m0 + rx * A_ROWS, mask_a);
-                    else ptx::tma_load_2d(a_dst, &tmap_a, full_bar(stage), kb * GEMM_BK, m0);
-                    if (CM > 1) ptx::tma_load_2d_mc(b_dst, &tmap_b, full_bar(stage), kb * GEMM_BK, n0 + ry * B_ROWS, mask_b);
-                    else ptx::tma_load_2d(b_dst, &tmap_b, full_bar(stage), kb * GEMM_BK, n0);
+                    ptx::mbar_wait(empty_bar(stage), phase ^ 1u);    // the MMAs that read this stage have retired
+                    const uint32_t a_dst = stage_base + stage * S::STAGE_BYTES;
+                    const uint32_t b_dst = a_dst + S::A_BYTES;
+                    if (PAIR) {
+                        // the leader's barrier collects the bytes of both CTAs' loads
+                        if (ry == 0) ptx::mbar_arrive_expect_tx(full_bar(stage), 2 * S::STAGE_BYTES);
+                        ptx::tma_load_2d_pair(a_dst, &tmap_a, full0 + 8u * stage, kb * GEMM_BK, m0);
+                        ptx::tma_load_2d_pair(b_dst, &tmap_b, full0 + 8u * stage, kb * GEMM_BK, n0 + ry * (BN / 2));
+                    } else {
+                        ptx::mbar_arrive_expect_tx(full_bar(stage), S::STAGE_BYTES);
+                        ptx::tma_load_2d(a_dst, &tmap_a, full_bar(stage), kb * GEMM_BK, m0);
+                        ptx::tma_load_2d(b_dst, &tmap_b, full_bar(stage), kb * GEMM_BK, n0);
+                    }
                     if (++stage == STAGES) { stage = 0; phase ^= 1u; }
                 }
             }
         }
     } else if (warp == 1) {
-        // ================= MMA issuer =================
-        if (lane == 0) {
-            constexpr uint32_t idesc = ptx::umma_idesc_i8(GEMM_BM, BN, 1, 1);
+        // ================= MMA issuer (PAIR: leader CTA only) =================
+        if (lane == 0 && ry == 0) {
+            constexpr uint32_t idesc = ptx::umma_idesc_i8(CS * GEMM_BM, BN, 1, 1);
             int stage = 0;
             uint32_t phase = 0;
             int as = 0;
             uint32_t aphase = 0;
             for (int tile = tile_first; tile < num_tiles; tile += tile_step) {
-                ptx::mbar_wait(tempty_bar(as), aphase ^ 1u);
+                if (PAIR) ptx::mbar_wait_cluster(tempty_bar(as), aphase ^ 1u);
+                else ptx::mbar_wait(tempty_bar(as), aphase ^ 1u);
                 ptx::tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
                 for (int kb = 0; kb < num_kb; ++kb) {
@@ -516,115 +425,22 @@ gemm_i8_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
 #pragma unroll
                     for (int k = 0; k < GEMM_BK / GEMM_UMMA_K; ++k) {
                         // advance along K inside the 128 B swizzle row: +32 B == +2 in the (addr >> 4) field
-                        ptx::mma_i8_ss(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc,
-                                       (kb | k) != 0 ? 1u : 0u);
+                        if (PAIR) ptx::mma_i8_ss_pair(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc,
+                                                      (kb | k) != 0 ? 1u : 0u);
+                        else ptx::mma_i8_ss(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc,
+                                            (kb | k) != 0 ? 1u : 0u);
                     }
-                    // frees the smem slot when the MMAs retire -- in every CTA that sent a slice of it
-                    if (CS > 1) ptx::mma_commit_mc(empty_bar(stage), (uint16_t)(mask_a | mask_b));
+                    // frees the smem slot when the MMAs retire (PAIR: in both CTAs)
+                    if (PAIR) ptx::mma_commit_pair_mc(empty_bar(stage), (uint16_t)3);
                     else ptx::mma_commit(empty_bar(stage));
                     if (++stage == STAGES) { stage = 0; phase ^= 1u; }
                 }
-                ptx::mma_commit(tfull_bar(as));                    // accumulator complete -> epilogue
+                // accumulator complete -> epilogue (PAIR: of both CTAs)
+                if (PAIR) ptx::mma_commit_pair_mc(tfull_bar(as), (uint16_t)3);
+                else ptx::mma_commit(tfull_bar(as));
                 if (++as == 2) { as = 0; aphase ^= 1u; }
             }
         }
-    } else if constexpr (TS && GEMM_FRAG_EPILOGUE) {
-        // ================= epilogue, fragment layout + TMA store (experimental) =================
-        const int ew = warp - 2;                      // 0..7
-        const int lane_group = warp & 3;              // TMEM lanes [32*lane_group, +32) are accessible to this warp
-        const int col_half = ew >> 2;                 // 0: columns [0, BN/2), 1: [BN/2, BN)
-        const int et = ew * 32 + lane;                // 0..255 thread index inside the epilogue group
-        const int g = lane >> 2, q4 = lane & 3;
-        const int trow0 = lane_group * 32 + g;        // this thread's tile rows: trow0 + {0, 8, 16, 24}
-        // per-column constants of the NEXT tile are fetched into registers while the current tile is processed
-        int32_t pre_b = 0;
-        ivit_dyadic_t pre_d = {0, 63};
-        auto fetch_params = [&](int n0f) {
-            pre_b = 0; pre_d.m = 0; pre_d.e = 63;
-            const int n = n0f + et;
-            if (et < BN && n < args.N) {
-                if (args.bias) pre_b = __ldg(args.bias + n);
-                pre_d = args.me[n];
-            }
-        };
-        if (tile_first < num_tiles) fetch_params(tile_n0(tile_first));
-        int as = 0;
-        uint32_t aphase = 0;
-        for (int tile = tile_first; tile < num_tiles; tile += tile_step) {
-            const int m0 = tile_m0(tile), n0 = tile_n0(tile);
-            ColParam* cp = col_params + as * BN;
-            int32_t* cb = col_bias + as * BN;
-            // ---- publish this tile's per-column constants (prefetched) ----
-            int ok = 1, any_tie = 0;
-            if (et < BN) {
-                ColParam p;
-                p.m = pre_d.m; p.sh = pre_d.e - 32; p.c = 0;
-                if (pre_d.m != 0) {
-                    // fast form: t = acc*m + (bias*m + 2^(e-1)); q = hi32(t) >> (e-32), needs 32 <= e <= 62 (whole tile).
-                    // An exact tie needs v2(z) = e-1-ctz(m); unreachable for |z| < 2^acc_bits when e-1-ctz(m) >= acc_bits.
-                    const int tz = __ffs(pre_d.m) - 1;
-                    const bool in_range = (pre_d.e >= 32 && pre_d.e <= 62);
-                    ok = in_range ? 1 : 0;
-                    any_tie = (in_range && (pre_d.e - 1 - tz < args.acc_bits)) ? 1 : 0;
-                    if (pre_d.e >= 1 && pre_d.e <= 62) p.c = (long long)pre_b * (long long)pre_d.m + (1LL << (pre_d.e - 1));
-                } else {
-                    p.sh = 31;
-                }
-                cp[et] = p;
-                cb[et] = pre_b;
-            }
-            if (et == 0) ptx::tma_store_wait_read<0>();            // previous tile's TMA store has finished reading the staging tile
-            int all_ok, some_tie;                                  // barrier + block-wide reductions of the two predicates
-            asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.s32 p, %1, 0;\n\tbarrier.cta.red.and.pred q, 1, 256, p;\n\tselp.s32 %0, 1, 0, q;\n\t}"
-                         : "=r"(all_ok) : "r"(ok) : "memory");
-            asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.s32 p, %1, 0;\n\tbarrier.cta.red.or.pred q, 1, 256, p;\n\tselp.s32 %0, 1, 0, q;\n\t}"
-                         : "=r"(some_tie) : "r"(any_tie) : "memory");
-            const int fast = !all_ok ? 0 : (some_tie ? 2 : 1);
-            {
-                const int nxt = tile + tile_step;
-                if (nxt < num_tiles) fetch_params(tile_n0(nxt));   // latency hidden behind this tile's work
-            }
-            const int c_begin = col_half * (BN / 2);
-            const int c_end = min(c_begin + BN / 2, args.N - n0);  // exclusive, may be <= c_begin
-            const uint32_t t_lo = tmem_base + ((uint32_t)(lane_group * 32) << 16) + (uint32_t)(as * BN);
-            const uint32_t t_hi = t_lo + (16u << 16);
-            uint32_t ra[16], rb[16], res_cur[16], res_nxt[16];
-            if (MODE == GM_RQ_I16 && c_begin < c_end) load_residual_frag(args, m0 + trow0, n0 + c_begin, q4, res_cur);
-
-            ptx::mbar_wait(tfull_bar(as), aphase);
-            ptx::tc_fence_after();
-#pragma unroll 1
-            for (int c0 = c_begin; c0 < c_end; c0 += 32) {
-                tmem_ld_16x256b_x4(t_lo + (uint32_t)c0, ra);
-                tmem_ld_16x256b_x4(t_hi + (uint32_t)c0, rb);
-                if (MODE == GM_RQ_I16 && c0 + 32 < c_end) load_residual_frag(args, m0 + trow0, n0 + c0 + 32, q4, res_nxt);
-                ptx::tmem_ld_wait();
-                epilogue_chunk_frag<MODE>(ra, rb, res_cur, cp + c0, cb + c0, args, fast, out_base, trow0, g, q4, c0);
-                if (MODE == GM_RQ_I16) {
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) res_cur[j] = res_nxt[j];
-                }
-            }
-            // release the accumulator back to the MMA warp
-            ptx::tc_fence_before();
-            __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(tempty_bar(as));
-            // staged tile -> global: one elected thread issues a TMA store per 128-byte-wide box
-            // (coalesced, asynchronous, clips the M / N tails)
-            ptx::fence_proxy_async();                              // generic-proxy smem writes -> async proxy
-            asm volatile("bar.sync 2, 256;" ::: "memory");
-            if (et == 0) {
-                constexpr int BOX_COLS = 128 / (OUT_ES ? OUT_ES : 1);
-                constexpr int NBOX = BN / BOX_COLS;
-#pragma unroll
-                for (int bx = 0; bx < NBOX; ++bx)
-                    if (n0 + bx * BOX_COLS < args.N && m0 < args.M)
-                        ptx::tma_store_2d(&tmap_out, out_base + (uint32_t)(bx * GEMM_BM * 128), (n0 + bx * BOX_COLS) * OUT_ES, m0);   // byte-typed map
-                ptx::tma_store_commit();
-            }
-            if (++as == 2) { as = 0; aphase ^= 1u; }
-        }
-        if (et == 0) ptx::tma_store_wait<0>();                     // all stores complete before the CTA exits
     } else {
         // ================= epilogue (warps 2..9) =================
         // TMEM lane group is fixed by (warp % 4); the two warps that share a lane group split the tile's columns.
@@ -722,7 +538,10 @@ gemm_i8_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
             // release the accumulator back to the MMA warp
             ptx::tc_fence_before();
             __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(tempty_bar(as));
+            if (lane == 0) {
+                if (PAIR) ptx::mbar_arrive_cluster(ptx::mapa(tempty_bar(as), 0));   // the leader's MMA warp owns both accumulators
+                else ptx::mbar_arrive(tempty_bar(as));
+            }
             if (TS) {
                 // staged tile -> global: one elected thread issues a TMA store per 128-byte-wide box
                 // (coalesced, asynchronous, clips the M / N tails)
@@ -745,10 +564,11 @@ gemm_i8_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
 
     ptx::tc_fence_before();
     __syncthreads();
-    if (CS > 1) ptx::cluster_sync();                       // no CTA exits while a peer may still arrive on its barriers
+    if (PAIR) ptx::cluster_sync();                         // no CTA exits while its peer may still use its barriers / smem / TMEM
     if (warp == 1) {
         ptx::tc_fence_after();
-        ptx::tmem_dealloc(tmem_base, TMEM_COLS);
+        if (PAIR) ptx::tmem_dealloc_pair(tmem_base, TMEM_COLS);
+        else ptx::tmem_dealloc(tmem_base, TMEM_COLS);
     }
 }
 
@@ -838,14 +658,14 @@ int make_tmap_2d_u8(ivit_ctx* ctx, CUtensorMap* tm, const void* base, uint64_t i
     return IVIT_OK;
 }
 
-template <int BN, int STAGES, int MODE, bool TS, int CM, int CN>
+template <int BN, int STAGES, int MODE, bool TS, bool PAIR>
 static int launch_gemm(ivit_ctx* ctx, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const GemmArgs& ga,
                        cudaStream_t s) {
     constexpr int OUT_ES = !TS ? 0 : (MODE == GM_RQ_I8 ? 1 : 2);
-    constexpr int CS = CM * CN;
-    using S = GemmSmem<BN, STAGES, OUT_ES>;
+    constexpr int CS = PAIR ? 2 : 1;
+    using S = GemmSmem<BN, STAGES, OUT_ES, PAIR>;
     static_assert(S::TOTAL <= 227 * 1024, "shared memory budget");
-    auto kern = gemm_i8_tcgen05_kernel<BN, STAGES, MODE, TS, CM, CN>;
+    auto kern = gemm_i8_tcgen05_kernel<BN, STAGES, MODE, TS, PAIR>;
     static bool attr_set = false;                     // per instantiation
     static int max_clusters = 0;
     cudaLaunchConfig_t cfg = {};
@@ -867,7 +687,7 @@ static int launch_gemm(ivit_ctx* ctx, const CUtensorMap& ta, const CUtensorMap& 
         attr_set = true;
     }
     const int tiles_m = (ga.M + GEMM_BM - 1) / GEMM_BM, tiles_n = (ga.N + BN - 1) / BN;
-    const int ctiles = ((tiles_m + CM - 1) / CM) * ((tiles_n + CN - 1) / CN);
+    const int ctiles = ((tiles_m + CS - 1) / CS) * tiles_n;
     const int cap = (CS > 1) ? max_clusters : ctx->num_sms;
     const int nclusters = ctiles < cap ? ctiles : cap;
     cfg.gridDim = dim3(nclusters * CS);
@@ -880,13 +700,14 @@ template <int MODE>
 static int dispatch_bn(ivit_ctx* ctx, const int8_t* A, int64_t lda, const int8_t* W, const GemmArgs& ga, cudaStream_t s) {
     // wide tiles when N is large enough to fill them; 128-wide otherwise (less padding waste)
     const bool wide = (ga.N % 256 == 0) || ga.N >= 1024;
-    // cluster of 2 CTAs along M sharing the W tile (TMA multicast) when there is enough work to keep every pair busy
-    static const char* cl_env = getenv("IVIT_GEMM_CLUSTER");
-    const bool cluster = wide && ga.M >= 4 * GEMM_BM && !(cl_env && cl_env[0] == '0');
+    // CTA pairs (cta_group::2, 256 x 256 MMA over two SMs) when there is enough work to keep every pair busy
+    static const char* pair_env = getenv("IVIT_GEMM_PAIR");
+    const bool pair = wide && ga.M >= 4 * GEMM_BM && !(pair_env && pair_env[0] == '0');
     CUtensorMap ta, tb, to;
     int rc = make_tmap_2d_u8(ctx, &ta, A, (uint64_t)ga.K, (uint64_t)ga.M, (uint64_t)lda, GEMM_BK, GEMM_BM);
     if (rc) return rc;
-    rc = make_tmap_2d_u8(ctx, &tb, W, (uint64_t)ga.K, (uint64_t)ga.N, (uint64_t)ga.K, GEMM_BK, wide ? (cluster ? 128 : 256) : 128);
+    // W box: each CTA of a pair loads half of the 256-row W tile
+    rc = make_tmap_2d_u8(ctx, &tb, W, (uint64_t)ga.K, (uint64_t)ga.N, (uint64_t)ga.K, GEMM_BK, (wide && !pair) ? 256 : 128);
     if (rc) return rc;
     if constexpr (MODE == GM_RQ_I8 || MODE == GM_RQ_I16) {
         // Output staged through shared memory and written by TMA when the destination allows it
@@ -898,18 +719,15 @@ static int dispatch_bn(ivit_ctx* ctx, const int8_t* A, int64_t lda, const int8_t
             // byte-typed view of the output: inner dim = N*ES bytes, box = 128 bytes x 128 rows, 128B swizzle
             rc = make_tmap_2d_u8(ctx, &to, ga.out, (uint64_t)ga.N * ES, (uint64_t)ga.M, (uint64_t)ga.out_ld * ES, 128, GEMM_BM);
             if (rc) return rc;
-            if (wide && cluster) return launch_gemm<256, 3, MODE, true, 2, 1>(ctx, ta, tb, to, ga, s);
-            if (wide) return launch_gemm<256, 3, MODE, true, 1, 1>(ctx, ta, tb, to, ga, s);
-            return launch_gemm<128, 5, MODE, true, 1, 1>(ctx, ta, tb, to, ga, s);
+            if (pair) return launch_gemm<256, (ES == 1 ? 5 : 4), MODE, true, true>(ctx, ta, tb, to, ga, s);
+            if (wide) return launch_gemm<256, 3, MODE, true, false>(ctx, ta, tb, to, ga, s);
+            return launch_gemm<128, 5, MODE, true, false>(ctx, ta, tb, to, ga, s);
         }
     }
     to = ta;
-    if (wide && cluster) {                            // W box was sized for the cluster: rebuild for the plain kernel
-        rc = make_tmap_2d_u8(ctx, &tb, W, (uint64_t)ga.K, (uint64_t)ga.N, (uint64_t)ga.K, GEMM_BK, 256);
-        if (rc) return rc;
-    }
-    if (wide) return launch_gemm<256, 4, MODE, false, 1, 1>(ctx, ta, tb, to, ga, s);
-    return launch_gemm<128, 6, MODE, false, 1, 1>(ctx, ta, tb, to, ga, s);
+    if (pair) return launch_gemm<256, 6, MODE, false, true>(ctx, ta, tb, to, ga, s);
+    if (wide) return launch_gemm<256, 4, MODE, false, false>(ctx, ta, tb, to, ga, s);
+    return launch_gemm<128, 6, MODE, false, false>(ctx, ta, tb, to, ga, s);
 }
 
 }  // namespace ivit

@@ -78,6 +78,40 @@ IVIT_PTX uint32_t cluster_ctarank() {
 IVIT_PTX void cluster_sync() {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+// shared::cta address -> shared::cluster address of the same offset in CTA `cta_rank` of the cluster
+IVIT_PTX uint32_t mapa(uint32_t smem_addr, uint32_t cta_rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(cta_rank));
+    return r;
+}
+// arrive on an mbarrier that may live in another CTA of the cluster (address from mapa)
+IVIT_PTX void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+IVIT_PTX bool mbar_try_wait_cluster(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+IVIT_PTX void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+    while (!mbar_try_wait_cluster(bar, parity)) {
+    }
+}
+// CTA-pair load (cta_group::2): the tile lands in MY shared memory, the transaction bytes are signalled on an
+// mbarrier that may live in the peer CTA (`cluster_bar` is a shared::cluster address, see mapa).
+IVIT_PTX void tma_load_2d_pair(uint32_t dst_smem, const void* tmap, uint32_t cluster_bar, int32_t c0, int32_t c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst_smem), "l"(tmap), "r"(cluster_bar), "r"(c0), "r"(c1)
+        : "memory");
+}
 // 2D tile store shared -> global (bulk async group).
 IVIT_PTX void tma_store_2d(const void* tmap, uint32_t src_smem, int32_t c0, int32_t c1) {
     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
@@ -116,6 +150,30 @@ IVIT_PTX void mma_commit(uint32_t bar) {
 // Same, arriving on the mbarrier at the same CTA-relative address in every CTA of `cta_mask`.
 IVIT_PTX void mma_commit_mc(uint32_t bar, uint16_t cta_mask) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"(cta_mask) : "memory");
+}
+// ---- CTA pair (cta_group::2): the two CTAs of a cluster, on the two SMs of one TPC, execute one 256-row MMA.  Each
+// holds its own 128 rows of A and HALF of the W tile (the tensor cores read both halves), and each receives the
+// 128 accumulator rows of its A rows in its own TMEM.  Issued by one thread of the even-ranked (leader) CTA.
+IVIT_PTX void tmem_alloc_pair(uint32_t dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+}
+IVIT_PTX void tmem_relinquish_pair() { asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory"); }
+IVIT_PTX void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+IVIT_PTX void mma_i8_ss_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// arrive (when all previously issued pair MMAs have completed) on the mbarrier at this CTA-relative address in
+// every CTA of `cta_mask`
+IVIT_PTX void mma_commit_pair_mc(uint32_t bar, uint16_t cta_mask) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
                  ::"r"(bar), "h"(cta_mask) : "memory");
 }
 IVIT_PTX void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
