@@ -28,7 +28,7 @@ constexpr int GEMM_BK = 128;          // bytes == int8 elements per k-block (one
 constexpr int GEMM_UMMA_K = 32;       // K per tcgen05.mma for 8-bit operands
 constexpr int GEMM_EPI_WARPS_PER_GROUP = 2;   // epilogue warps per TMEM lane group; each takes 1/2 of the tile's columns
 constexpr int GEMM_EPI_THREADS = 128 * GEMM_EPI_WARPS_PER_GROUP;
-constexpr int GEMM_THREADS = 64 + GEMM_EPI_THREADS;
+constexpr int GEMM_THREADS = 96 + GEMM_EPI_THREADS;   // TMA producer, MMA issuer, auxiliary warp, epilogue warps
 
 enum GemmMode { GM_RAW_I32 = 0, GM_CARRIER = 1, GM_RQ_I8 = 2, GM_RQ_I16 = 3 };
 
@@ -323,12 +323,15 @@ gemm_i8_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
     ColParam* col_params = reinterpret_cast<ColParam*>(smem + STAGES * S::STAGE_BYTES + S::OUT_BYTES);
     int32_t* col_bias = reinterpret_cast<int32_t*>(col_params + 2 * BN);
     const uint32_t bar_base = smem_base + STAGES * S::STAGE_BYTES + S::OUT_BYTES + S::PARAM_BYTES;
-    // barrier layout (8 B each): full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], then tmem ptr + flags
+    // barrier layout (8 B each): full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], pfull[2], sfull, sempty, then tmem ptr + flags
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
     auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
     auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + s); };
     auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + 2 + s); };
-    volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + STAGES * S::STAGE_BYTES + S::OUT_BYTES + S::PARAM_BYTES + 8 * (2 * STAGES + 4));
+    auto pfull_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + 4 + s); };     // column constants staged (aux -> epilogue)
+    const uint32_t sfull_bar = bar_base + 8u * (2 * STAGES + 6);                      // epilogue warps done with a tile (-> aux)
+    const uint32_t sempty_bar = bar_base + 8u * (2 * STAGES + 7);                     // staging tile free again (aux -> epilogue)
+    volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + STAGES * S::STAGE_BYTES + S::OUT_BYTES + S::PARAM_BYTES + 8 * (2 * STAGES + 8));
     int* fast_flag = reinterpret_cast<int*>(const_cast<uint32_t*>(tmem_ptr_smem) + 2);   // [2] one per accumulator stage
 
     const int warp = threadIdx.x >> 5;
@@ -358,7 +361,10 @@ gemm_i8_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
         for (int s = 0; s < 2; ++s) {
             ptx::mbar_init(tfull_bar(s), 1);
             ptx::mbar_init(tempty_bar(s), CS * EPI_WARPS); // one arrive per epilogue warp (PAIR: of both CTAs, on the leader's)
+            ptx::mbar_init(pfull_bar(s), 1);
         }
+        ptx::mbar_init(sfull_bar, EPI_WARPS);
+        ptx::mbar_init(sempty_bar, 1);
         ptx::fence_barrier_init();
     }
     if (warp == 1) {
@@ -441,61 +447,94 @@ gemm_i8_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
                 if (++as == 2) { as = 0; aphase ^= 1u; }
             }
         }
+    } else if (warp == 2) {
+        // ================= auxiliary warp: per-tile column constants + TMA store =================
+        // Keeps both off the epilogue warps' critical path: they never execute a CTA barrier, only mbarrier waits
+        // that have normally completed long before.  Constants of tile it live in buffer it & 1.
+        auto stage_params = [&](int tile, int buf) {
+            const int n0 = tile_n0(tile);
+            ColParam* cp = col_params + buf * BN;
+            int32_t* cb = col_bias + buf * BN;
+            int ok = 1, any_tie = 0;
+#pragma unroll 4
+            for (int c = lane; c < BN; c += 32) {
+                const int n = n0 + c;
+                ColParam p;
+                p.m = 0; p.sh = 31; p.c = 0;
+                int32_t b = 0;
+                if (n < args.N) {
+                    if (args.bias) b = __ldg(args.bias + n);
+                    if (MODE == GM_RQ_I8 || MODE == GM_RQ_I16) {
+                        const ivit_dyadic_t d = args.me[n];
+                        // fast form: t = acc*m + (bias*m + 2^(e-1)); q = hi32(t) >> (e-32), needs 32 <= e <= 62
+                        // (whole tile).  An exact tie z*m = (2k+1)*2^(e-1) needs v2(z) = e-1-ctz(m); with
+                        // |z| < 2^acc_bits it is unreachable when e-1-ctz(m) >= acc_bits, else the whole tile
+                        // gets the tie-to-even correction.
+                        const int tz = __ffs(d.m) - 1;
+                        const bool in_range = (d.e >= 32 && d.e <= 62);
+                        ok &= in_range ? 1 : 0;
+                        any_tie |= (in_range && (d.e - 1 - tz < args.acc_bits)) ? 1 : 0;
+                        p.m = d.m;
+                        p.sh = d.e - 32;
+                        if (d.e >= 1 && d.e <= 62) p.c = (long long)b * (long long)d.m + (1LL << (d.e - 1));
+                    } else if (MODE == GM_CARRIER) {
+                        p.m = __float_as_int(args.scale[n]);
+                    }
+                }
+                cp[c] = p;
+                cb[c] = b;
+            }
+            const bool all_ok = __all_sync(0xffffffffu, ok != 0);
+            const bool some_tie = __any_sync(0xffffffffu, any_tie != 0);
+            if (lane == 0) fast_flag[buf] = !all_ok ? 0 : (some_tie ? 2 : 1);
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(pfull_bar(buf));
+        };
+        {
+            int t = tile_first;
+            if (t < num_tiles) stage_params(t, 0);
+            t += tile_step;
+            if (t < num_tiles) stage_params(t, 1);
+        }
+        int it = 0;
+        for (int tile = tile_first; tile < num_tiles; tile += tile_step, ++it) {
+            const int buf = it & 1;
+            ptx::mbar_wait(sfull_bar, (uint32_t)(it & 1));     // every epilogue warp is done with tile `it` (staged output, constants)
+            if (TS && lane == 0) {
+                // staged tile -> global: one TMA store per 128-byte-wide box (coalesced, asynchronous, clips the M / N tails)
+                const int m0 = tile_m0(tile), n0 = tile_n0(tile);
+                constexpr int BOX_COLS = 128 / (OUT_ES ? OUT_ES : 1);
+                constexpr int NBOX = BN / BOX_COLS;
+#pragma unroll
+                for (int bx = 0; bx < NBOX; ++bx)
+                    if (n0 + bx * BOX_COLS < args.N && m0 < args.M)
+                        ptx::tma_store_2d(&tmap_out, out_base + (uint32_t)(bx * GEMM_BM * 128), (n0 + bx * BOX_COLS) * OUT_ES, m0);   // byte-typed map
+                ptx::tma_store_commit();
+            }
+            const int nxt = tile + 2 * tile_step;
+            if (nxt < num_tiles) stage_params(nxt, buf);         // global-load latency overlaps the store
+            if (TS && lane == 0) {
+                ptx::tma_store_wait_read<0>();                   // the store has finished reading the staging tile
+                ptx::mbar_arrive(sempty_bar);
+            }
+            __syncwarp();
+        }
+        if (TS && lane == 0) ptx::tma_store_wait<0>();           // all stores complete before the CTA exits
     } else {
-        // ================= epilogue (warps 2..9) =================
-        // TMEM lane group is fixed by (warp % 4); the two warps that share a lane group split the tile's columns.
-        const int ew = warp - 2;                      // 0..7
+        // ================= epilogue (warps 3..) =================
+        // TMEM lane group is fixed by (warp % 4); the warps that share a lane group split the tile's columns.
+        const int ew = warp - 3;
         const int lane_group = warp & 3;              // TMEM lanes [32*lane_group, +32) are accessible to this warp
         const int col_part = ew >> 2;                 // which 1/GEMM_EPI_WARPS_PER_GROUP of the tile's columns
-        const int et = ew * 32 + lane;                // thread index inside the epilogue group
         constexpr int CW = (MODE == GM_RQ_I16) ? 16 : 32;
-        int as = 0;
-        uint32_t aphase = 0;
-        for (int tile = tile_first; tile < num_tiles; tile += tile_step) {
+        const uint32_t tempty_leader = PAIR ? ptx::mapa(tempty_bar(0), 0) : 0u;   // the leader's MMA warp owns both accumulators
+        int it = 0;
+        for (int tile = tile_first; tile < num_tiles; tile += tile_step, ++it) {
+            const int as = it & 1;
+            const uint32_t aphase = (uint32_t)((it >> 1) & 1);
             const int m0 = tile_m0(tile), n0 = tile_n0(tile);
-            ColParam* cp = col_params + as * BN;
-            int32_t* cb = col_bias + as * BN;
-            // ---- stage the per-column constants of this tile (coalesced global reads) ----
-            if (et == 0) {
-                fast_flag[as] = 1;
-                if (TS) ptx::tma_store_wait_read<0>();        // previous tile's TMA store has finished reading the staging tile
-            }
-            asm volatile("bar.sync 1, %0;" ::"n"(GEMM_EPI_THREADS) : "memory");
-            {
-                int ok = 1, any_tie = 0;
-                for (int c = et; c < BN; c += GEMM_EPI_THREADS) {
-                    const int n = n0 + c;
-                    ColParam p;
-                    p.m = 0; p.sh = 31; p.c = 0;
-                    int32_t b = 0;
-                    if (n < args.N) {
-                        if (args.bias) b = args.bias[n];
-                        if (MODE == GM_RQ_I8 || MODE == GM_RQ_I16) {
-                            const ivit_dyadic_t d = args.me[n];
-                            // fast form: t = acc*m + (bias*m + 2^(e-1)); q = hi32(t) >> (e-32), needs 32 <= e <= 62
-                            // (whole tile).  An exact tie z*m = (2k+1)*2^(e-1) needs v2(z) = e-1-ctz(m); with
-                            // |z| < 2^acc_bits it is unreachable when e-1-ctz(m) >= acc_bits, else the column is
-                            // flagged (bit 8) and gets the tie-to-even correction.
-                            const int tz = __ffs(d.m) - 1;
-                            const bool in_range = (d.e >= 32 && d.e <= 62);
-                            ok &= in_range ? 1 : 0;
-                            any_tie |= (in_range && (d.e - 1 - tz < args.acc_bits)) ? 1 : 0;
-                            p.m = d.m;
-                            p.sh = d.e - 32;
-                            if (d.e >= 1 && d.e <= 62) p.c = (long long)b * (long long)d.m + (1LL << (d.e - 1));
-                        } else if (MODE == GM_CARRIER) {
-                            p.m = __float_as_int(args.scale[n]);
-                        }
-                    }
-                    cp[c] = p;
-                    cb[c] = b;
-                }
-                if (!ok) atomicAnd(&fast_flag[as], 0);                 // bit 0: all columns in the fast range
-                if (any_tie) atomicOr(&fast_flag[as], 2);              // bit 1: some column can reach an exact tie
-            }
-            asm volatile("bar.sync 1, %0;" ::"n"(GEMM_EPI_THREADS) : "memory");
-            const int ff = fast_flag[as];
-            const int fast = !(ff & 1) ? 0 : ((ff & 2) ? 2 : 1);
+            const ColParam* cp = col_params + as * BN;
+            const int32_t* cb = col_bias + as * BN;
 
             const int row = m0 + lane_group * 32 + lane;
             const bool row_ok = row < args.M;
@@ -507,12 +546,17 @@ gemm_i8_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
             uint32_t ra[CW], rb[CW], resa[CW / 2], resb[CW / 2];
             if (MODE == GM_RQ_I16 && c_begin < c_end) load_residual<CW>(args, row, row_ok, n0 + c_begin, resa);
 
+            ptx::mbar_wait(pfull_bar(as), aphase);                       // this tile's column constants are staged
+            const int fast = fast_flag[as];
             ptx::mbar_wait(tfull_bar(as), aphase);
             ptx::tc_fence_after();
 
             if (c_begin < c_end) {
                 tmem_ld_chunk<CW>(t_row + (uint32_t)c_begin, ra);
                 ptx::tmem_ld_wait();
+            }
+            if (TS) ptx::mbar_wait(sempty_bar, (uint32_t)((it & 1) ^ 1));   // previous tile's TMA store has read the staging tile
+            if (c_begin < c_end) {
 #pragma unroll 1
                 for (int c0 = c_begin; c0 < c_end; c0 += 2 * CW) {
                     const bool has1 = (c0 + CW) < c_end;
@@ -535,31 +579,16 @@ gemm_i8_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
                     }
                 }
             }
-            // release the accumulator back to the MMA warp
+            // release the accumulator back to the MMA warp, hand the staged tile / constants buffer to the auxiliary warp
             ptx::tc_fence_before();
+            if (TS) ptx::fence_proxy_async();                            // generic-proxy smem writes -> async proxy (TMA store)
             __syncwarp();
             if (lane == 0) {
-                if (PAIR) ptx::mbar_arrive_cluster(ptx::mapa(tempty_bar(as), 0));   // the leader's MMA warp owns both accumulators
+                if (PAIR) ptx::mbar_arrive_cluster(tempty_leader + 8u * as);
                 else ptx::mbar_arrive(tempty_bar(as));
+                ptx::mbar_arrive(sfull_bar);
             }
-            if (TS) {
-                // staged tile -> global: one elected thread issues a TMA store per 128-byte-wide box
-                // (coalesced, asynchronous, clips the M / N tails)
-                ptx::fence_proxy_async();                          // generic-proxy smem writes -> async proxy
-                asm volatile("bar.sync 2, %0;" ::"n"(GEMM_EPI_THREADS) : "memory");
-                if (et == 0) {
-                    constexpr int BOX_COLS = 128 / (OUT_ES ? OUT_ES : 1);
-                    constexpr int NBOX = BN / BOX_COLS;
-#pragma unroll
-                    for (int bx = 0; bx < NBOX; ++bx)
-                        if (n0 + bx * BOX_COLS < args.N && m0 < args.M)
-                            ptx::tma_store_2d(&tmap_out, out_base + (uint32_t)(bx * GEMM_BM * 128), (n0 + bx * BOX_COLS) * OUT_ES, m0);   // byte-typed map
-                    ptx::tma_store_commit();
-                }
-            }
-            if (++as == 2) { as = 0; aphase ^= 1u; }
         }
-        if (TS && et == 0) ptx::tma_store_wait<0>();               // all stores complete before the CTA exits
     }
 
     ptx::tc_fence_before();

@@ -84,9 +84,11 @@ IVIT_PTX uint32_t mapa(uint32_t smem_addr, uint32_t cta_rank) {
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(cta_rank));
     return r;
 }
-// arrive on an mbarrier that may live in another CTA of the cluster (address from mapa)
+// arrive on an mbarrier that may live in another CTA of the cluster (address from mapa).  No cluster-scope release:
+// the only thing ordered through it here are tcgen05.ld reads, which tcgen05.fence::before_thread_sync orders
+// (a .release.cluster arrive costs a full MEMBAR, ~7 % of the epilogue's issue slots when measured).
 IVIT_PTX void mbar_arrive_cluster(uint32_t cluster_addr) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 IVIT_PTX bool mbar_try_wait_cluster(uint32_t bar, uint32_t parity) {
     uint32_t ok;
