@@ -140,8 +140,13 @@ IVIT_DEVINL long long shiftexp(int32_t d, int32_t x0, float inv_x0, int n) {
 // Early exit (exact): with s = floor(sqrt(V)), the iterate strictly decreases while k > s and never drops below s,
 // so after the first step "k_next >= k" happens exactly when k == s; from there the sequence is either constant
 // (k_next == s) or alternates s+1, s, s+1, ... (only when V == (s+1)^2 - 1).  The value after the remaining steps
-// follows from their parity.  Typical rows converge in 4-5 steps instead of 10.
-IVIT_DEVINL unsigned long long ln_isqrt10(unsigned long long V) {
+// follows from their parity.
+//
+// Closed form (exact) for 2^22 <= V < 2^40: with x = k / sqrt(V), one step gives x' <= (x + 1/x) / 2 (the floors only
+// lower k, never below s).  From k0 = 2^16: x1 <= 16.1 in both directions (sqrt(V) >= 2^11 resp. <= 2^20), then
+// 8.04, 4.08, 2.16, 1.31, 1.037, 1.00066, 1 + 2.2e-7 -- i.e. k - sqrt(V) < 2^20 * 2.2e-7 < 1 after at most 8 steps, so
+// k has reached s by step 8 <= 10 and the result is s, unless V == (s+1)^2 - 1 (alternating case: simulated).
+IVIT_DEVINL unsigned long long ln_isqrt10_loop(unsigned long long V) {
     unsigned long long k = 65536ULL;
     const bool small = V < (1ULL << 52);
     const double Vd = (double)V;
@@ -156,6 +161,16 @@ IVIT_DEVINL unsigned long long ln_isqrt10(unsigned long long V) {
         k = kn;
     }
     return k;
+}
+IVIT_DEVINL unsigned long long ln_isqrt10(unsigned long long V) {
+    if (V >= (1ULL << 22) && V < (1ULL << 40)) {
+        // s = floor(sqrt(V)): fp32 estimate (relative error < 2^-22, s < 2^20 -> off by at most 1) + exact fix-up
+        uint32_t s = (uint32_t)__fsqrt_rn(__ull2float_rn(V));
+        while ((unsigned long long)s * s > V) --s;
+        while ((unsigned long long)(s + 1) * (s + 1) <= V) ++s;
+        if ((unsigned long long)(s + 1) * (s + 1) - 1 != V) return (unsigned long long)s;
+    }
+    return ln_isqrt10_loop(V);
 }
 
 // floor((2^31-1) / S) for 1 <= S <= 2^31-1     quant_modules.py:438, 492

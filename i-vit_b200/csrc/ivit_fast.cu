@@ -96,11 +96,27 @@ gelu_lut_apply_kernel(const int8_t* __restrict__ q, int64_t rows, int cols, cons
 // ------------------------------------------------------------------------------------
 struct alignas(16) LnCol { int32_t m; int32_t sh; long long c; };   // fast requant constants: hi32(z0*m + c) >> sh
 
-template <int NV>
+__device__ __forceinline__ long long mul_wide_s32(int32_t a, int32_t b) {
+    long long r;
+    asm("mul.wide.s32 %0, %1, %2;" : "=l"(r) : "r"(a), "r"(b));
+    return r;
+}
+__device__ __forceinline__ long long mad_wide_s32(int32_t a, int32_t b, long long c) {
+    long long r;
+    asm("mad.wide.s32 %0, %1, %2, %3;" : "=l"(r) : "r"(a), "r"(b), "l"(c));
+    return r;
+}
+
+// LPR lanes per row (32 / LPR rows per warp), NV 16-byte vectors (8 channels) per lane, FULL: C == 8 * NV * LPR.
+// Everything that is per row (the two reductions, mean, integer sqrt, reciprocal factor) is computed redundantly by
+// the row's LPR lanes, so narrow rows-per-warp splits (LPR = 16 for C = 768) halve that overhead per row.
+template <int NV, int LPR, bool FULL>
 __global__ void __launch_bounds__(256)
 layernorm_i16_i8_kernel(const int16_t* __restrict__ x, int64_t rows, int C, const int32_t* __restrict__ bias_int,
                         const ivit_dyadic_t* __restrict__ me, int8_t* __restrict__ out) {
+    constexpr int RPW = 32 / LPR;                                // rows per warp
     const int lane = threadIdx.x & 31;
+    const int sub = lane % LPR, rsel = lane / LPR;
     const int nvec = C >> 3;                                     // vectors of 8 int16
     const int64_t warp0 = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
     const int64_t nwarps = (int64_t)gridDim.x * 8;
@@ -124,15 +140,17 @@ layernorm_i16_i8_kernel(const int16_t* __restrict__ x, int64_t rows, int C, cons
         s_b[(c & 7) * nvec + (c >> 3)] = b;
     }
     const bool fast = __syncthreads_and(ok) != 0;
-    for (int64_t row = warp0; row < rows; row += nwarps) {
-        const uint4* src = reinterpret_cast<const uint4*>(x + row * (int64_t)C);
+    for (int64_t rbase = warp0 * RPW; rbase < rows; rbase += nwarps * RPW) {
+        const int64_t row = rbase + rsel;
+        const bool row_ok = row < rows;
+        const uint4* src = reinterpret_cast<const uint4*>(x + (row_ok ? row : rbase) * (int64_t)C);
         int32_t y[NV][8];
         int32_t sum = 0;                                         // |sum| <= 1024 * 32768 < 2^31
 #pragma unroll
         for (int j = 0; j < NV; ++j) {
-            const int vi = lane + 32 * j;
+            const int vi = sub + LPR * j;
             uint4 t = make_uint4(0, 0, 0, 0);
-            if (vi < nvec) t = __ldg(src + vi);
+            if (FULL || vi < nvec) t = __ldg(src + vi);
             const uint32_t tw[4] = {t.x, t.y, t.z, t.w};
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
@@ -141,45 +159,46 @@ layernorm_i16_i8_kernel(const int16_t* __restrict__ x, int64_t rows, int C, cons
                 sum += y[j][2 * u] + y[j][2 * u + 1];
             }
         }
-        sum = warp_sum_i32(sum);
+#pragma unroll
+        for (int o = LPR / 2; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
         // mu = RNE(sum / C)
-        int32_t qd = sum / C, rem = sum % C;
+        int32_t qd = sum / C, rem = sum - qd * C;
         if (rem < 0) { qd -= 1; rem += C; }
         if (2 * rem > C || (2 * rem == C && (qd & 1))) qd += 1;
         const int32_t mu = qd;
-        unsigned long long V = 0;
+        long long Vs = 0;
 #pragma unroll
         for (int j = 0; j < NV; ++j) {
-            const bool okv = (lane + 32 * j) < nvec;
+            const bool okv = FULL || (sub + LPR * j) < nvec;
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
                 const int32_t d = okv ? y[j][u] - mu : 0;
                 y[j][u] = d;
-                V += (unsigned long long)((long long)d * d);
+                Vs = mad_wide_s32(d, d, Vs);
             }
         }
-        V = (unsigned long long)warp_sum_i64((long long)V);
-        const unsigned long long k = ln_isqrt10(V);
-        const int32_t F = (int32_t)(2147483647ULL / k);          // <= 2^31/64
-        uint2* dst = reinterpret_cast<uint2*>(out + row * (int64_t)C);
+#pragma unroll
+        for (int o = LPR / 2; o > 0; o >>= 1) Vs += __shfl_xor_sync(0xffffffffu, Vs, o);
+        const unsigned long long k = ln_isqrt10((unsigned long long)Vs);
+        const int32_t F = (int32_t)(k <= 0xffffffffULL ? (2147483647u / (uint32_t)k) : 0u);   // floor((2^31-1)/k), <= 2^31/64
+        uint2* dst = reinterpret_cast<uint2*>(out + (row_ok ? row : rbase) * (int64_t)C);
 #pragma unroll
         for (int j = 0; j < NV; ++j) {
-            const int vi = lane + 32 * j;
-            if (vi < nvec) {
+            const int vi = sub + LPR * j;
+            if ((FULL || vi < nvec) && row_ok) {
                 int32_t r[8];
                 if (fast) {
 #pragma unroll
                     for (int u = 0; u < 8; ++u) {
                         const LnCol p = s_c[u * nvec + vi];
-                        const int32_t z0 = (int32_t)(((long long)y[j][u] * (long long)F) >> 1);   // floor(y*F/2), |.| <= 2^30
-                        const long long t = (long long)z0 * (long long)p.m + p.c;
-                        r[u] = (int32_t)(t >> 32) >> p.sh;
+                        const int32_t z0 = (int32_t)(mul_wide_s32(y[j][u], F) >> 1);   // floor(y*F/2), |.| <= 2^30
+                        r[u] = (int32_t)(mad_wide_s32(z0, p.m, p.c) >> 32) >> p.sh;
                     }
                 } else {
 #pragma unroll
                     for (int u = 0; u < 8; ++u) {
                         const LnCol p = s_c[u * nvec + vi];
-                        long long o = (((long long)y[j][u] * (long long)F) >> 1) + (long long)s_b[u * nvec + vi];
+                        long long o = (mul_wide_s32(y[j][u], F) >> 1) + (long long)s_b[u * nvec + vi];
                         o = o > 2147483647LL ? 2147483647LL : (o < -2147483648LL ? -2147483648LL : o);
                         r[u] = requant32_general((int32_t)o, p.m, p.sh + 32);
                     }
@@ -358,10 +377,18 @@ int ivit_layernorm_i16_i8(ivit_ctx* ctx, const int16_t* x, int64_t rows, int C, 
     IVIT_REQUIRE(ctx && x && bias_int && me && out && rows > 0, "ivit_layernorm_i16_i8: bad arguments");
     IVIT_REQUIRE(C % 8 == 0 && C >= 8 && C <= 8 * 32 * 4, "ivit_layernorm_i16_i8: C must be a multiple of 8, <= 1024");
     IVIT_REQUIRE(((uintptr_t)x % 16) == 0 && ((uintptr_t)out % 8) == 0, "ivit_layernorm_i16_i8: x must be 16-byte aligned");
-    const int grid = (int)((rows + 7) / 8 < (int64_t)ctx->num_sms * 4 ? (rows + 7) / 8 : (int64_t)ctx->num_sms * 4);
-    const int nv = (C / 8 + 31) / 32;
-#define LNF(NV) layernorm_i16_i8_kernel<NV><<<grid, 256, 0, st(stream)>>>(x, rows, C, bias_int, me, out)
-    if (nv <= 1) LNF(1); else if (nv <= 2) LNF(2); else if (nv <= 3) LNF(3); else LNF(4);
+    // 16 lanes per row (two rows per warp), up to 8 vectors of 8 channels per lane (C <= 1024)
+    const int nvec = C / 8;
+    const int lpr = 16;
+    const int rpb = 8 * (32 / lpr);                              // rows per 256-thread block and pass
+    const int64_t want = (rows + rpb - 1) / rpb;
+    const int grid = (int)(want < (int64_t)ctx->num_sms * 4 ? want : (int64_t)ctx->num_sms * 4);
+    const int nv = (nvec + lpr - 1) / lpr;
+    const bool full = (nv * lpr == nvec);
+#define LNF(NV, LPR) do { if (full) layernorm_i16_i8_kernel<NV, LPR, true><<<grid, 256, 0, st(stream)>>>(x, rows, C, bias_int, me, out); \
+                          else layernorm_i16_i8_kernel<NV, LPR, false><<<grid, 256, 0, st(stream)>>>(x, rows, C, bias_int, me, out); } while (0)
+    switch (nv) { case 1: LNF(1, 16); break; case 2: LNF(2, 16); break; case 3: LNF(3, 16); break; case 4: LNF(4, 16); break;
+                  case 5: LNF(5, 16); break; case 6: LNF(6, 16); break; case 7: LNF(7, 16); break; default: LNF(8, 16); break; }
 #undef LNF
     IVIT_LAUNCH_OK("layernorm_i16_i8_kernel");
     return IVIT_OK;

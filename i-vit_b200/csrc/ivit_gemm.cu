@@ -323,14 +323,13 @@ gemm_i8_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
     ColParam* col_params = reinterpret_cast<ColParam*>(smem + STAGES * S::STAGE_BYTES + S::OUT_BYTES);
     int32_t* col_bias = reinterpret_cast<int32_t*>(col_params + 2 * BN);
     const uint32_t bar_base = smem_base + STAGES * S::STAGE_BYTES + S::OUT_BYTES + S::PARAM_BYTES;
-    // barrier layout (8 B each): full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], pfull[2], sfull, sempty, then tmem ptr + flags
+    // barrier layout (8 B each): full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], pfull[2], sfull, then tmem ptr + flags
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
     auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
     auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + s); };
     auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + 2 + s); };
     auto pfull_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + 4 + s); };     // column constants staged (aux -> epilogue)
     const uint32_t sfull_bar = bar_base + 8u * (2 * STAGES + 6);                      // epilogue warps done with a tile (-> aux)
-    const uint32_t sempty_bar = bar_base + 8u * (2 * STAGES + 7);                     // staging tile free again (aux -> epilogue)
     volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + STAGES * S::STAGE_BYTES + S::OUT_BYTES + S::PARAM_BYTES + 8 * (2 * STAGES + 8));
     int* fast_flag = reinterpret_cast<int*>(const_cast<uint32_t*>(tmem_ptr_smem) + 2);   // [2] one per accumulator stage
 
@@ -364,7 +363,6 @@ gemm_i8_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
             ptx::mbar_init(pfull_bar(s), 1);
         }
         ptx::mbar_init(sfull_bar, EPI_WARPS);
-        ptx::mbar_init(sempty_bar, 1);
         ptx::fence_barrier_init();
     }
     if (warp == 1) {
@@ -448,9 +446,9 @@ gemm_i8_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
             }
         }
     } else if (warp == 2) {
-        // ================= auxiliary warp: per-tile column constants + TMA store =================
-        // Keeps both off the epilogue warps' critical path: they never execute a CTA barrier, only mbarrier waits
-        // that have normally completed long before.  Constants of tile it live in buffer it & 1.
+        // ================= auxiliary warp: per-tile column constants =================
+        // Keeps the staging (global loads + analysis) off the epilogue warps' critical path: they never execute a CTA
+        // barrier, only mbarrier waits that have normally completed long before.  Constants of tile it live in buffer it & 1.
         auto stage_params = [&](int tile, int buf) {
             const int n0 = tile_n0(tile);
             ColParam* cp = col_params + buf * BN;
@@ -499,27 +497,10 @@ gemm_i8_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
         int it = 0;
         for (int tile = tile_first; tile < num_tiles; tile += tile_step, ++it) {
             const int buf = it & 1;
-            ptx::mbar_wait(sfull_bar, (uint32_t)(it & 1));     // every epilogue warp is done with tile `it` (staged output, constants)
-            if (TS && lane == 0) {
-                // staged tile -> global: one TMA store per 128-byte-wide box (coalesced, asynchronous, clips the M / N tails)
-                const int m0 = tile_m0(tile), n0 = tile_n0(tile);
-                constexpr int BOX_COLS = 128 / (OUT_ES ? OUT_ES : 1);
-                constexpr int NBOX = BN / BOX_COLS;
-#pragma unroll
-                for (int bx = 0; bx < NBOX; ++bx)
-                    if (n0 + bx * BOX_COLS < args.N && m0 < args.M)
-                        ptx::tma_store_2d(&tmap_out, out_base + (uint32_t)(bx * GEMM_BM * 128), (n0 + bx * BOX_COLS) * OUT_ES, m0);   // byte-typed map
-                ptx::tma_store_commit();
-            }
+            ptx::mbar_wait(sfull_bar, (uint32_t)(it & 1));     // every epilogue warp is done with the constants of tile `it`
             const int nxt = tile + 2 * tile_step;
-            if (nxt < num_tiles) stage_params(nxt, buf);         // global-load latency overlaps the store
-            if (TS && lane == 0) {
-                ptx::tma_store_wait_read<0>();                   // the store has finished reading the staging tile
-                ptx::mbar_arrive(sempty_bar);
-            }
-            __syncwarp();
+            if (nxt < num_tiles) stage_params(nxt, buf);
         }
-        if (TS && lane == 0) ptx::tma_store_wait<0>();           // all stores complete before the CTA exits
     } else {
         // ================= epilogue (warps 3..) =================
         // TMEM lane group is fixed by (warp % 4); the warps that share a lane group split the tile's columns.
@@ -555,7 +536,10 @@ gemm_i8_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
                 tmem_ld_chunk<CW>(t_row + (uint32_t)c_begin, ra);
                 ptx::tmem_ld_wait();
             }
-            if (TS) ptx::mbar_wait(sempty_bar, (uint32_t)((it & 1) ^ 1));   // previous tile's TMA store has read the staging tile
+            if (TS) {                                                    // my previous tile's TMA stores have read my staging rows
+                if (lane == 0) ptx::tma_store_wait_read<0>();
+                __syncwarp();
+            }
             if (c_begin < c_end) {
 #pragma unroll 1
                 for (int c0 = c_begin; c0 < c_end; c0 += 2 * CW) {
@@ -579,7 +563,7 @@ gemm_i8_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
                     }
                 }
             }
-            // release the accumulator back to the MMA warp, hand the staged tile / constants buffer to the auxiliary warp
+            // release the accumulator back to the MMA warp and the constants buffer to the auxiliary warp
             ptx::tc_fence_before();
             if (TS) ptx::fence_proxy_async();                            // generic-proxy smem writes -> async proxy (TMA store)
             __syncwarp();
@@ -587,8 +571,25 @@ gemm_i8_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
                 if (PAIR) ptx::mbar_arrive_cluster(tempty_leader + 8u * as);
                 else ptx::mbar_arrive(tempty_bar(as));
                 ptx::mbar_arrive(sfull_bar);
+                if (TS) {
+                    // my 32 rows x CPART columns of the staged tile -> global: one TMA store per 128-byte-wide box
+                    // (32-row boxes; coalesced, asynchronous, clips the M / N tails).  Each warp stores and later waits
+                    // for its own rows only, one tile later: no CTA-wide synchronisation around the store.
+                    constexpr int BOX_COLS = 128 / (OUT_ES ? OUT_ES : 1);
+                    constexpr int NBOX_W = CPART / BOX_COLS;             // boxes per warp
+                    const int r0 = m0 + lane_group * 32;
+#pragma unroll
+                    for (int b = 0; b < NBOX_W; ++b) {
+                        const int bx = col_part * NBOX_W + b;
+                        if (n0 + bx * BOX_COLS < args.N && r0 < args.M)
+                            ptx::tma_store_2d(&tmap_out, out_base + (uint32_t)(bx * GEMM_BM * 128 + lane_group * 32 * 128),
+                                              (n0 + bx * BOX_COLS) * OUT_ES, r0);   // byte-typed map
+                    }
+                    ptx::tma_store_commit();
+                }
             }
         }
+        if (TS && lane == 0) ptx::tma_store_wait<0>();               // all my stores complete before the CTA exits
     }
 
     ptx::tc_fence_before();
@@ -745,8 +746,8 @@ static int dispatch_bn(ivit_ctx* ctx, const int8_t* A, int64_t lda, const int8_t
         const bool ts = ((uintptr_t)ga.out % 16 == 0) && ((ga.out_ld * ES) % 16 == 0) && ga.mode_bits == 8 * ES && ga.N % 8 == 0 &&
                         (!ga.residual || (((uintptr_t)ga.residual % 4) == 0 && ga.res_ld % 2 == 0));
         if (ts) {
-            // byte-typed view of the output: inner dim = N*ES bytes, box = 128 bytes x 128 rows, 128B swizzle
-            rc = make_tmap_2d_u8(ctx, &to, ga.out, (uint64_t)ga.N * ES, (uint64_t)ga.M, (uint64_t)ga.out_ld * ES, 128, GEMM_BM);
+            // byte-typed view of the output: inner dim = N*ES bytes, box = 128 bytes x 32 rows (one epilogue warp), 128B swizzle
+            rc = make_tmap_2d_u8(ctx, &to, ga.out, (uint64_t)ga.N * ES, (uint64_t)ga.M, (uint64_t)ga.out_ld * ES, 128, GEMM_BM / 4);
             if (rc) return rc;
             if (pair) return launch_gemm<256, (ES == 1 ? 5 : 4), MODE, true, true>(ctx, ta, tb, to, ga, s);
             if (wide) return launch_gemm<256, 3, MODE, true, false>(ctx, ta, tb, to, ga, s);

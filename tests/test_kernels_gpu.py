@@ -426,3 +426,62 @@ def test_embed_tokens_fast_matches_general(K):
         b = K.embed_tokens_fast(dev(pe), dev(cls), dev(pos), B, N, C, (m, e), (m1, e1))
         assert_equal(a, want, "embed_tokens")
         assert_equal(b, want, "embed_tokens_fast")
+
+
+def _four_squares(n, rng):
+    """n = a^2 + b^2 + c^2 + d^2 by randomised greedy search (n < 2^40)."""
+    import math
+    for c in range(6):                              # n - c^2 - d^2 = x^2 or 2 x^2 (powers of two, squares, their neighbours)
+        for d in range(6):
+            r = n - c * c - d * d
+            if r < 0:
+                continue
+            x = math.isqrt(r)
+            if x * x == r:
+                return x, 0, c, d
+            if r % 2 == 0 and math.isqrt(r // 2) ** 2 == r // 2:
+                return math.isqrt(r // 2), math.isqrt(r // 2), c, d
+    for _ in range(20000):
+        a = math.isqrt(n) - int(rng.integers(0, 6))
+        r1 = n - a * a
+        if r1 < 0:
+            continue
+        b = math.isqrt(r1) - int(rng.integers(0, 12))
+        r2 = r1 - b * b
+        if b < 0 or r2 < 0:
+            continue
+        c = math.isqrt(r2) - int(rng.integers(0, 12))
+        r3 = r2 - c * c
+        if c < 0 or r3 < 0:
+            continue
+        d = math.isqrt(r3)
+        if d * d == r3:
+            return a, b, c, d
+    return None
+
+
+def test_layernorm_isqrt_edge_variances(K):
+    """The 10-step integer sqrt (quant_modules.py:366-370) has a closed form for 2^22 <= V < 2^40 except when
+    V = (s+1)^2 - 1 (the iteration then alternates s, s+1); rows [+-a, +-b, +-c, +-d] give V = 2(a^2+b^2+c^2+d^2)
+    exactly (mean 0), so every even V is reachable: alternating cases, range boundaries, tiny and huge variances."""
+    import math
+    rng = np.random.default_rng(77)
+    targets = []
+    for s in [2048, 2050, 2052, 4096, 4100, 65530, 65534, 65536, 65538, 65540, 100000, 300000, 724000, 1048570, 1048574]:     # even s: V = s(s+2) is even
+        targets += [s * (s + 2), s * s, s * s + 2, s * (s + 2) - 2]
+    targets += [2 ** 22, 2 ** 22 - 2, 2 ** 22 + 2, 2 ** 32, 2 ** 32 - 2, 2 ** 32 + 2, 2 ** 40 - 2, 2 ** 40, 2 ** 40 + 2, 2, 8, 200, 2 ** 41 + 6]
+    targets += [int(v) * 2 for v in rng.integers(1, 2 ** 39, 60)]
+    rows = []
+    for V in targets:
+        fs = _four_squares(V // 2, rng)
+        if fs is None:
+            continue
+        a, b, c, d = fs
+        rows.append([a, -a, b, -b, c, -c, d, -d])
+    assert len(rows) > 80
+    q = np.array(rows, dtype=np.int64)
+    assert (np.abs(q) < 2 ** 31).all()
+    bq = rng.integers(-1000, 1000, 8).astype(np.int64)
+    want = O.layernorm(q, bq)
+    got = K.layernorm(dev(q.astype(np.int32)), dev(bq.astype(np.int32)))
+    assert_equal(got, want, "layernorm isqrt edge cases")
