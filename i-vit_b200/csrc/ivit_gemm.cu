@@ -323,13 +323,13 @@ gemm_i8_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
     ColParam* col_params = reinterpret_cast<ColParam*>(smem + STAGES * S::STAGE_BYTES + S::OUT_BYTES);
     int32_t* col_bias = reinterpret_cast<int32_t*>(col_params + 2 * BN);
     const uint32_t bar_base = smem_base + STAGES * S::STAGE_BYTES + S::OUT_BYTES + S::PARAM_BYTES;
-    // barrier layout (8 B each): full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], pfull[2], sfull, then tmem ptr + flags
+    // barrier layout (8 B each): full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], pfull[2], sfull[2], then tmem ptr + flags
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
     auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
     auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + s); };
     auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + 2 + s); };
     auto pfull_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + 4 + s); };     // column constants staged (aux -> epilogue)
-    const uint32_t sfull_bar = bar_base + 8u * (2 * STAGES + 6);                      // epilogue warps done with a tile (-> aux)
+    auto sfull_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + 6 + s); };     // epilogue warps done with a constants buffer (-> aux)
     volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + STAGES * S::STAGE_BYTES + S::OUT_BYTES + S::PARAM_BYTES + 8 * (2 * STAGES + 8));
     int* fast_flag = reinterpret_cast<int*>(const_cast<uint32_t*>(tmem_ptr_smem) + 2);   // [2] one per accumulator stage
 
@@ -361,8 +361,8 @@ gemm_i8_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
             ptx::mbar_init(tfull_bar(s), 1);
             ptx::mbar_init(tempty_bar(s), CS * EPI_WARPS); // one arrive per epilogue warp (PAIR: of both CTAs, on the leader's)
             ptx::mbar_init(pfull_bar(s), 1);
+            ptx::mbar_init(sfull_bar(s), EPI_WARPS);
         }
-        ptx::mbar_init(sfull_bar, EPI_WARPS);
         ptx::fence_barrier_init();
     }
     if (warp == 1) {
@@ -449,25 +449,41 @@ gemm_i8_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
         // ================= auxiliary warp: per-tile column constants =================
         // Keeps the staging (global loads + analysis) off the epilogue warps' critical path: they never execute a CTA
         // barrier, only mbarrier waits that have normally completed long before.  Constants of tile it live in buffer it & 1.
-        auto stage_params = [&](int tile, int buf) {
+        // The global loads for tile it+2 are issued BEFORE waiting for the epilogue warps to finish tile it (whose buffer
+        // they will overwrite), so that only the analysis + shared-memory stores remain once the buffer is free.
+        constexpr int CPL = BN / 32;                             // columns per lane
+        int32_t pb[CPL];
+        ivit_dyadic_t pd[CPL];
+        float pscale[CPL];
+        auto load_params = [&](int tile) {
             const int n0 = tile_n0(tile);
+#pragma unroll
+            for (int j = 0; j < CPL; ++j) {
+                const int n = n0 + lane + 32 * j;
+                pb[j] = 0; pd[j].m = 0; pd[j].e = 63; pscale[j] = 0.f;
+                if (n < args.N) {
+                    if (args.bias) pb[j] = __ldg(args.bias + n);
+                    if (MODE == GM_RQ_I8 || MODE == GM_RQ_I16) pd[j] = args.me[n];
+                    else if (MODE == GM_CARRIER) pscale[j] = __ldg(args.scale + n);
+                }
+            }
+        };
+        auto store_params = [&](int buf) {
             ColParam* cp = col_params + buf * BN;
             int32_t* cb = col_bias + buf * BN;
             int ok = 1, any_tie = 0;
-#pragma unroll 4
-            for (int c = lane; c < BN; c += 32) {
-                const int n = n0 + c;
+#pragma unroll
+            for (int j = 0; j < CPL; ++j) {
                 ColParam p;
                 p.m = 0; p.sh = 31; p.c = 0;
-                int32_t b = 0;
-                if (n < args.N) {
-                    if (args.bias) b = __ldg(args.bias + n);
-                    if (MODE == GM_RQ_I8 || MODE == GM_RQ_I16) {
-                        const ivit_dyadic_t d = args.me[n];
+                const int32_t b = pb[j];
+                if (MODE == GM_RQ_I8 || MODE == GM_RQ_I16) {
+                    const ivit_dyadic_t d = pd[j];
+                    if (d.m != 0) {
                         // fast form: t = acc*m + (bias*m + 2^(e-1)); q = hi32(t) >> (e-32), needs 32 <= e <= 62
                         // (whole tile).  An exact tie z*m = (2k+1)*2^(e-1) needs v2(z) = e-1-ctz(m); with
                         // |z| < 2^acc_bits it is unreachable when e-1-ctz(m) >= acc_bits, else the whole tile
-                        // gets the tie-to-even correction.
+                        // gets the tie-to-even correction.  (m == 0: column past N, or a zero multiplier -> q = 0.)
                         const int tz = __ffs(d.m) - 1;
                         const bool in_range = (d.e >= 32 && d.e <= 62);
                         ok &= in_range ? 1 : 0;
@@ -475,12 +491,12 @@ gemm_i8_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
                         p.m = d.m;
                         p.sh = d.e - 32;
                         if (d.e >= 1 && d.e <= 62) p.c = (long long)b * (long long)d.m + (1LL << (d.e - 1));
-                    } else if (MODE == GM_CARRIER) {
-                        p.m = __float_as_int(args.scale[n]);
                     }
+                } else if (MODE == GM_CARRIER) {
+                    p.m = __float_as_int(pscale[j]);
                 }
-                cp[c] = p;
-                cb[c] = b;
+                cp[lane + 32 * j] = p;
+                cb[lane + 32 * j] = b;
             }
             const bool all_ok = __all_sync(0xffffffffu, ok != 0);
             const bool some_tie = __any_sync(0xffffffffu, any_tie != 0);
@@ -490,16 +506,17 @@ gemm_i8_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
         };
         {
             int t = tile_first;
-            if (t < num_tiles) stage_params(t, 0);
+            if (t < num_tiles) { load_params(t); store_params(0); }
             t += tile_step;
-            if (t < num_tiles) stage_params(t, 1);
+            if (t < num_tiles) { load_params(t); store_params(1); }
         }
         int it = 0;
         for (int tile = tile_first; tile < num_tiles; tile += tile_step, ++it) {
             const int buf = it & 1;
-            ptx::mbar_wait(sfull_bar, (uint32_t)(it & 1));     // every epilogue warp is done with the constants of tile `it`
             const int nxt = tile + 2 * tile_step;
-            if (nxt < num_tiles) stage_params(nxt, buf);
+            if (nxt < num_tiles) load_params(nxt);
+            ptx::mbar_wait(sfull_bar(buf), (uint32_t)((it >> 1) & 1));   // every epilogue warp is done with the constants of tile `it`
+            if (nxt < num_tiles) store_params(buf);
         }
     } else {
         // ================= epilogue (warps 3..) =================
@@ -536,9 +553,14 @@ gemm_i8_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
                 tmem_ld_chunk<CW>(t_row + (uint32_t)c_begin, ra);
                 ptx::tmem_ld_wait();
             }
+            // boxes (128 bytes wide) per epilogue warp; 0: the warps of a lane group share one box (BN = 128, int8) and
+            // pair up through a 64-thread named barrier around its store
+            constexpr int BOX_COLS = 128 / (OUT_ES ? OUT_ES : 1);
+            constexpr int NBOX_W = CPART / BOX_COLS;
             if (TS) {                                                    // my previous tile's TMA stores have read my staging rows
-                if (lane == 0) ptx::tma_store_wait_read<0>();
-                __syncwarp();
+                if (lane == 0 && (NBOX_W > 0 || col_part == 0)) ptx::tma_store_wait_read<0>();
+                if (NBOX_W == 0) asm volatile("bar.sync %0, %1;" ::"r"(1 + lane_group), "n"(32 * GEMM_EPI_WARPS_PER_GROUP) : "memory");
+                else __syncwarp();
             }
             if (c_begin < c_end) {
 #pragma unroll 1
@@ -568,19 +590,23 @@ gemm_i8_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
             if (TS) ptx::fence_proxy_async();                            // generic-proxy smem writes -> async proxy (TMA store)
             __syncwarp();
             if (lane == 0) {
+                // constants buffer first: a warp can only reach tile it+2 (same buffer) after the MMA warp has seen
+                // every warp's accumulator release for tile it, which this orders after the buffer release
+                ptx::mbar_arrive(sfull_bar(as));
                 if (PAIR) ptx::mbar_arrive_cluster(tempty_leader + 8u * as);
                 else ptx::mbar_arrive(tempty_bar(as));
-                ptx::mbar_arrive(sfull_bar);
-                if (TS) {
-                    // my 32 rows x CPART columns of the staged tile -> global: one TMA store per 128-byte-wide box
-                    // (32-row boxes; coalesced, asynchronous, clips the M / N tails).  Each warp stores and later waits
-                    // for its own rows only, one tile later: no CTA-wide synchronisation around the store.
-                    constexpr int BOX_COLS = 128 / (OUT_ES ? OUT_ES : 1);
-                    constexpr int NBOX_W = CPART / BOX_COLS;             // boxes per warp
+            }
+            if (TS) {
+                // my 32 rows x CPART columns of the staged tile -> global: one TMA store per 128-byte-wide box
+                // (32-row boxes; coalesced, asynchronous, clips the M / N tails).  Each warp stores and later waits
+                // for its own rows only, one tile later: no CTA-wide synchronisation around the store.
+                if (NBOX_W == 0) asm volatile("bar.sync %0, %1;" ::"r"(1 + lane_group), "n"(32 * GEMM_EPI_WARPS_PER_GROUP) : "memory");
+                if (lane == 0 && (NBOX_W > 0 || col_part == 0)) {
                     const int r0 = m0 + lane_group * 32;
+                    constexpr int NB = NBOX_W > 0 ? NBOX_W : 1;
 #pragma unroll
-                    for (int b = 0; b < NBOX_W; ++b) {
-                        const int bx = col_part * NBOX_W + b;
+                    for (int b = 0; b < NB; ++b) {
+                        const int bx = (NBOX_W > 0 ? col_part * NBOX_W : 0) + b;
                         if (n0 + bx * BOX_COLS < args.N && r0 < args.M)
                             ptx::tma_store_2d(&tmap_out, out_base + (uint32_t)(bx * GEMM_BM * 128 + lane_group * 32 * 128),
                                               (n0 + bx * BOX_COLS) * OUT_ES, r0);   // byte-typed map
