@@ -89,6 +89,7 @@ struct GemmArgs {
     const float* scale;
     void* out;
     long long out_ld;
+    int debug;                        // IVIT_GEMM_DEBUG diagnostics (wrong results): 1 epilogue does no work, 2 producer loads nothing
 };
 
 struct alignas(16) ColParam {         // per output column, staged in shared memory per tile
@@ -392,7 +393,9 @@ gemm_i8_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
                     ptx::mbar_wait(empty_bar(stage), phase ^ 1u);    // the MMAs that read this stage have retired
                     const uint32_t a_dst = stage_base + stage * S::STAGE_BYTES;
                     const uint32_t b_dst = a_dst + S::A_BYTES;
-                    if (PAIR) {
+                    if (args.debug & 2) {                            // diagnostics: mainloop without operand traffic
+                        if (ry == 0) ptx::mbar_arrive(full_bar(stage));
+                    } else if (PAIR) {
                         // the leader's barrier collects the bytes of both CTAs' loads
                         if (ry == 0) ptx::mbar_arrive_expect_tx(full_bar(stage), 2 * S::STAGE_BYTES);
                         ptx::tma_load_2d_pair(a_dst, &tmap_a, full0 + 8u * stage, kb * GEMM_BK, m0);
@@ -549,7 +552,8 @@ gemm_i8_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
             ptx::mbar_wait(tfull_bar(as), aphase);
             ptx::tc_fence_after();
 
-            if (c_begin < c_end) {
+            const bool work = (c_begin < c_end) && !(args.debug & 1);    // debug & 1: diagnostics, epilogue does nothing
+            if (work) {
                 tmem_ld_chunk<CW>(t_row + (uint32_t)c_begin, ra);
                 ptx::tmem_ld_wait();
             }
@@ -562,7 +566,7 @@ gemm_i8_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
                 if (NBOX_W == 0) asm volatile("bar.sync %0, %1;" ::"r"(1 + lane_group), "n"(32 * GEMM_EPI_WARPS_PER_GROUP) : "memory");
                 else __syncwarp();
             }
-            if (c_begin < c_end) {
+            if (work) {
 #pragma unroll 1
                 for (int c0 = c_begin; c0 < c_end; c0 += 2 * CW) {
                     const bool has1 = (c0 + CW) < c_end;
@@ -813,6 +817,8 @@ extern "C" int ivit_gemm_i8(ivit_ctx* ctx, const int8_t* A, int64_t lda, const i
         ga.scalar_mode = !uni ? 0 : (tie ? 2 : 1);
     }
     ga.scale = epi->scale; ga.out = out; ga.out_ld = epi->out_ld;
+    static const char* dbg_env = getenv("IVIT_GEMM_DEBUG");
+    ga.debug = dbg_env ? atoi(dbg_env) : 0;
     int mode;
     switch (epi->mode) {
         case IVIT_EPI_RAW_I32:
