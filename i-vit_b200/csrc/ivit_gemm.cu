@@ -37,7 +37,7 @@ enum GemmMode { GM_RAW_I32 = 0, GM_CARRIER = 1, GM_RQ_I8 = 2, GM_RQ_I16 = 3 };
 //     t = (z << ls) * m + half';   q = hi32(t) >> rs        with (ls, rs, half') = (32-e, 0, 2^31)   for e <  32
 //                                                                               (0, e-32, 2^(e-1))  for e >= 32
 // (scaling z by 2^(32-e) scales numerator and denominator alike, |z << ls| < 2^31).  `tie` says whether an exact
-// .5 tie is reachable (e-1-ctz(m) <= 15); then tie <=> lo32(t) == 0 && (hi32(t) & himask) == 0 and q -= q & 1.
+// .5 tie is reachable (0 <= e-1-ctz(m) <= 15); then tie <=> lo32(t) == 0 && (hi32(t) & himask) == 0 and q -= q & 1.
 // kind 0: e outside [16, 62] -> general out-of-line form.
 struct ScalarRq {
     int32_t m, e;
@@ -54,7 +54,8 @@ static ScalarRq make_scalar_rq(ivit_dyadic_t d) {
         if (d.e < 32) { r.ls = 32 - d.e; r.rs = 0; r.half = 1LL << 31; }
         else { r.ls = 0; r.rs = d.e - 32; r.half = 1LL << (d.e - 1); }
         r.himask = (1 << r.rs) - 1;
-        r.tie = (d.e - 1 - __builtin_ctz((unsigned)d.m) <= 15) ? 1 : 0;
+        const int t = d.e - 1 - __builtin_ctz((unsigned)d.m);     // t < 0: z*m/2^e is an integer, nothing to round
+        r.tie = (t >= 0 && t <= 15) ? 1 : 0;
     }
     return r;
 }
@@ -85,7 +86,8 @@ struct GemmArgs {
     int two_stage;
     ScalarRq rq2, rqr;                // second-stage / residual dyadics, pre-analysed on the host (known by value)
     int acc_bits;                     // |acc + bias| < 2^acc_bits (tie analysis of the per-column requant)
-    int scalar_mode;                  // 1: rq2/rqr unified form, no ties; 2: unified with tie correction; 0: general
+    int scalar_mode;                  // 1: rq2/rqr unified form, no ties; 2: unified with tie correction; 0: general;
+                                      // 3: mode 1 with both stages present and a wrap-free 32-bit sum (straight-line)
     const float* scale;
     void* out;
     long long out_ld;
@@ -237,7 +239,14 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&r)[CW], const ui
     auto resid = [&](int j) -> int32_t {
         return (j & 1) ? ((int32_t)rr[j >> 1] >> 16) : (int32_t)(int16_t)(rr[j >> 1] & 0xffff);
     };
-    if (args.scalar_mode == 1) {                                   // both scalar dyadics in unified form, no ties
+    if (args.scalar_mode == 3) {
+        // the residual-block epilogue of the models (attn.proj / mlp.fc2): two-stage + residual, both scalar dyadics in
+        // unified form without reachable ties, and |each term| < 2^30 so that the 32-bit sum cannot wrap (host-checked).
+        // One straight-line block per chunk: no per-element conditions, the compiler interleaves the 16 chains.
+#pragma unroll
+        for (int j = 0; j < CW; ++j)
+            q[j] = scalar_rq_fast<false>(args.rq2, clamp_bits<16>(q[j])) + scalar_rq_fast<false>(args.rqr, resid(j));
+    } else if (args.scalar_mode == 1) {                            // both scalar dyadics in unified form, no ties
 #pragma unroll
         for (int j = 0; j < CW; ++j) {
             int32_t v = q[j];
@@ -815,6 +824,8 @@ extern "C" int ivit_gemm_i8(ivit_ctx* ctx, const int8_t* A, int64_t lda, const i
         const bool uni = (!use2 || ga.rq2.kind == 1) && (!user || ga.rqr.kind == 1);
         const bool tie = (use2 && ga.rq2.tie) || (user && ga.rqr.tie);
         ga.scalar_mode = !uni ? 0 : (tie ? 2 : 1);
+        // |RNE(z*m/2^e)| <= 2^15 * 2^31 / 2^e + 1 < 2^30 for e >= 18: the sum of the two terms fits 32 bits
+        if (ga.scalar_mode == 1 && use2 && user && ga.rq2.e >= 18 && ga.rqr.e >= 18) ga.scalar_mode = 3;
     }
     ga.scale = epi->scale; ga.out = out; ga.out_ld = epi->out_ld;
     static const char* dbg_env = getenv("IVIT_GEMM_DEBUG");
