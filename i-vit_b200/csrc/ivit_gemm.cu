@@ -26,9 +26,11 @@ namespace ivit {
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 128;          // bytes == int8 elements per k-block (one 128 B swizzle row)
 constexpr int GEMM_UMMA_K = 32;       // K per tcgen05.mma for 8-bit operands
-constexpr int GEMM_EPI_WARPS_PER_GROUP = 2;   // epilogue warps per TMEM lane group; each takes 1/2 of the tile's columns
-constexpr int GEMM_EPI_THREADS = 128 * GEMM_EPI_WARPS_PER_GROUP;
-constexpr int GEMM_THREADS = 96 + GEMM_EPI_THREADS;   // TMA producer, MMA issuer, auxiliary warp, epilogue warps
+// epilogue warps per TMEM lane group (each takes 1/WPG of the tile's columns): the 16-bit epilogue with its residual
+// loads is latency-bound and gets twice the warps of the others
+__host__ __device__ constexpr int gemm_wpg(int mode) { return mode == 3 /* GM_RQ_I16 */ ? 4 : 2; }
+// TMA producer, MMA issuer, auxiliary warp, epilogue warps
+__host__ __device__ constexpr int gemm_threads(int mode) { return 96 + 128 * gemm_wpg(mode); }
 
 enum GemmMode { GM_RAW_I32 = 0, GM_CARRIER = 1, GM_RQ_I8 = 2, GM_RQ_I16 = 3 };
 
@@ -317,13 +319,14 @@ struct GemmSmem {
 // 128 x 32 + BN x 32: the un-paired kernel saturates the SM's shared-memory data pipe (tensor-core operand reads +
 // epilogue LDS/STS ~ 93 % of peak wavefronts, profiles/ncu_full_r1g), which is what bounds it, not the tensor pipe.
 template <int BN, int STAGES, int MODE, bool TS, bool PAIR>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+__global__ void __launch_bounds__(gemm_threads(MODE), 1)
 gemm_i8_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                        const __grid_constant__ CUtensorMap tmap_out, const GemmArgs args) {
     constexpr int OUT_ES = !TS ? 0 : (MODE == GM_RQ_I8 ? 1 : 2);
     using S = GemmSmem<BN, STAGES, OUT_ES, PAIR>;
     constexpr uint32_t TMEM_COLS = 2 * BN;            // double-buffered accumulator (256 or 512)
-    constexpr int EPI_WARPS = GEMM_EPI_THREADS / 32;
+    constexpr int WPG = gemm_wpg(MODE);
+    constexpr int EPI_WARPS = 4 * WPG;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* smem = smem_raw + (smem_base - ptx::smem_u32(smem_raw));
@@ -535,7 +538,7 @@ gemm_i8_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
         // TMEM lane group is fixed by (warp % 4); the warps that share a lane group split the tile's columns.
         const int ew = warp - 3;
         const int lane_group = warp & 3;              // TMEM lanes [32*lane_group, +32) are accessible to this warp
-        const int col_part = ew >> 2;                 // which 1/GEMM_EPI_WARPS_PER_GROUP of the tile's columns
+        const int col_part = ew >> 2;                 // which 1/WPG of the tile's columns
         constexpr int CW = (MODE == GM_RQ_I16) ? 16 : 32;
         const uint32_t tempty_leader = PAIR ? ptx::mapa(tempty_bar(0), 0) : 0u;   // the leader's MMA warp owns both accumulators
         int it = 0;
@@ -548,7 +551,7 @@ gemm_i8_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
 
             const int row = m0 + lane_group * 32 + lane;
             const bool row_ok = row < args.M;
-            constexpr int CPART = BN / GEMM_EPI_WARPS_PER_GROUP;
+            constexpr int CPART = BN / WPG;
             const int c_begin = col_part * CPART;
             const int c_end = min(c_begin + CPART, args.N - n0);         // exclusive, may be <= c_begin
             const uint32_t t_row = tmem_base + ((uint32_t)(lane_group * 32) << 16) + (uint32_t)(as * BN);
@@ -566,13 +569,17 @@ gemm_i8_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
                 tmem_ld_chunk<CW>(t_row + (uint32_t)c_begin, ra);
                 ptx::tmem_ld_wait();
             }
-            // boxes (128 bytes wide) per epilogue warp; 0: the warps of a lane group share one box (BN = 128, int8) and
-            // pair up through a 64-thread named barrier around its store
+            // boxes (128 bytes wide) per epilogue warp; 0: WPB = 2 warps of a lane group share one box (128-wide tiles)
+            // and pair up through a 64-thread named barrier around its store (the even one of the two issues it)
             constexpr int BOX_COLS = 128 / (OUT_ES ? OUT_ES : 1);
             constexpr int NBOX_W = CPART / BOX_COLS;
+            constexpr int WPB = NBOX_W > 0 ? 1 : BOX_COLS / CPART;     // warps per box
+            static_assert(!TS || WPB <= 2, "at most two epilogue warps per 128-byte box");
+            const int box_bar = 1 + lane_group * 2 + (col_part >> 1);   // named barrier of my box (WPB == 2)
+            const bool box_leader = (NBOX_W > 0) || ((col_part & 1) == 0);
             if (TS) {                                                    // my previous tile's TMA stores have read my staging rows
-                if (lane == 0 && (NBOX_W > 0 || col_part == 0)) ptx::tma_store_wait_read<0>();
-                if (NBOX_W == 0) asm volatile("bar.sync %0, %1;" ::"r"(1 + lane_group), "n"(32 * GEMM_EPI_WARPS_PER_GROUP) : "memory");
+                if (lane == 0 && box_leader) ptx::tma_store_wait_read<0>();
+                if (NBOX_W == 0) asm volatile("bar.sync %0, 64;" ::"r"(box_bar) : "memory");
                 else __syncwarp();
             }
             if (work) {
@@ -613,13 +620,13 @@ gemm_i8_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
                 // my 32 rows x CPART columns of the staged tile -> global: one TMA store per 128-byte-wide box
                 // (32-row boxes; coalesced, asynchronous, clips the M / N tails).  Each warp stores and later waits
                 // for its own rows only, one tile later: no CTA-wide synchronisation around the store.
-                if (NBOX_W == 0) asm volatile("bar.sync %0, %1;" ::"r"(1 + lane_group), "n"(32 * GEMM_EPI_WARPS_PER_GROUP) : "memory");
-                if (lane == 0 && (NBOX_W > 0 || col_part == 0)) {
+                if (NBOX_W == 0) asm volatile("bar.sync %0, 64;" ::"r"(box_bar) : "memory");
+                if (lane == 0 && box_leader) {
                     const int r0 = m0 + lane_group * 32;
                     constexpr int NB = NBOX_W > 0 ? NBOX_W : 1;
 #pragma unroll
                     for (int b = 0; b < NB; ++b) {
-                        const int bx = (NBOX_W > 0 ? col_part * NBOX_W : 0) + b;
+                        const int bx = (NBOX_W > 0 ? col_part * NBOX_W : col_part / WPB) + b;
                         if (n0 + bx * BOX_COLS < args.N && r0 < args.M)
                             ptx::tma_store_2d(&tmap_out, out_base + (uint32_t)(bx * GEMM_BM * 128 + lane_group * 32 * 128),
                                               (n0 + bx * BOX_COLS) * OUT_ES, r0);   // byte-typed map
@@ -738,7 +745,7 @@ static int launch_gemm(ivit_ctx* ctx, const CUtensorMap& ta, const CUtensorMap& 
     static bool attr_set = false;                     // per instantiation
     static int max_clusters = 0;
     cudaLaunchConfig_t cfg = {};
-    cfg.blockDim = dim3(GEMM_THREADS);
+    cfg.blockDim = dim3(gemm_threads(MODE));
     cfg.dynamicSmemBytes = S::TOTAL;
     cfg.stream = s;
     cudaLaunchAttribute attr[1];
