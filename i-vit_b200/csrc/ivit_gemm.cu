@@ -26,9 +26,9 @@ namespace ivit {
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 128;          // bytes == int8 elements per k-block (one 128 B swizzle row)
 constexpr int GEMM_UMMA_K = 32;       // K per tcgen05.mma for 8-bit operands
-// epilogue warps per TMEM lane group (each takes 1/WPG of the tile's columns): the 16-bit epilogue with its residual
-// loads is latency-bound and gets twice the warps of the others
-__host__ __device__ constexpr int gemm_wpg(int mode) { return mode == 3 /* GM_RQ_I16 */ ? 4 : 2; }
+// epilogue warps per TMEM lane group (each takes 1/WPG of the tile's columns).  4 (16 epilogue warps, 96 registers)
+// was measured slower than 2 for every epilogue, including the residual one (profiles/gemm_bench_r18.log).
+__host__ __device__ constexpr int gemm_wpg(int mode) { return (void)mode, 2; }
 // TMA producer, MMA issuer, auxiliary warp, epilogue warps
 __host__ __device__ constexpr int gemm_threads(int mode) { return 96 + 128 * gemm_wpg(mode); }
 
@@ -93,6 +93,7 @@ struct GemmArgs {
     const float* scale;
     void* out;
     long long out_ld;
+    int res_async;                    // residual rows are 16-byte aligned: prefetched into the staging tile with cp.async
     int debug;                        // IVIT_GEMM_DEBUG diagnostics (wrong results): 1 epilogue does no work, 2 producer loads nothing
 };
 
@@ -152,6 +153,28 @@ __device__ __forceinline__ void sts_swz(uint32_t out_base, int trow, int byte_of
     const uint32_t box = (uint32_t)byte_off >> 7, chunk = ((uint32_t)byte_off >> 4) & 7u;
     const uint32_t addr = out_base + box * (uint32_t)(GEMM_BM * 128) + (uint32_t)trow * 128u + ((chunk ^ ((uint32_t)trow & 7u)) << 4);
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+__device__ __forceinline__ uint32_t swz_addr(uint32_t out_base, int trow, int byte_off) {
+    const uint32_t box = (uint32_t)byte_off >> 7, chunk = ((uint32_t)byte_off >> 4) & 7u;
+    return out_base + box * (uint32_t)(GEMM_BM * 128) + (uint32_t)trow * 128u + ((chunk ^ ((uint32_t)trow & 7u)) << 4);
+}
+// 16 bytes global -> shared, asynchronous (LDGSTS); src_bytes = 0 zero-fills without reading
+__device__ __forceinline__ void cp_async_16(uint32_t dst_smem, const void* src, int src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst_smem), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+// residual of one CW-column chunk of my row, from the staging tile (where residual_prefetch put it, in the layout of
+// the output that later overwrites it in place)
+template <int CW>
+__device__ __forceinline__ void load_residual_smem(uint32_t out_base, int trow, int tcol, uint32_t (&rr)[CW / 2]) {
+#pragma unroll
+    for (int j = 0; j < CW / 8; ++j) {
+        const uint32_t a = swz_addr(out_base, trow, (tcol + 8 * j) * 2);
+        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                     : "=r"(rr[4 * j]), "=r"(rr[4 * j + 1]), "=r"(rr[4 * j + 2]), "=r"(rr[4 * j + 3]) : "r"(a) : "memory");
+    }
 }
 
 template <int MODE, int CW, bool TS>
@@ -556,8 +579,38 @@ gemm_i8_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
             const int c_end = min(c_begin + CPART, args.N - n0);         // exclusive, may be <= c_begin
             const uint32_t t_row = tmem_base + ((uint32_t)(lane_group * 32) << 16) + (uint32_t)(as * BN);
 
+            // boxes (128 bytes wide) per epilogue warp; 0: WPB = 2 warps of a lane group share one box (128-wide tiles)
+            // and pair up through a 64-thread named barrier around its store (the even one of the two issues it)
+            constexpr int BOX_COLS = 128 / (OUT_ES ? OUT_ES : 1);
+            constexpr int NBOX_W = CPART / BOX_COLS;
+            constexpr int WPB = NBOX_W > 0 ? 1 : BOX_COLS / CPART;     // warps per box
+            static_assert(!TS || WPB <= 2, "at most two epilogue warps per 128-byte box");
+            const int box_bar = 1 + lane_group * 2 + (col_part >> 1);   // named barrier of my box (WPB == 2)
+            const bool box_leader = (NBOX_W > 0) || ((col_part & 1) == 0);
+            auto wait_staging_free = [&]() {                             // my previous tile's TMA stores have read my staging rows
+                if (lane == 0 && box_leader) ptx::tma_store_wait_read<0>();
+                if (NBOX_W == 0) asm volatile("bar.sync %0, 64;" ::"r"(box_bar) : "memory");
+                else __syncwarp();
+            };
+            const int trow = lane_group * 32 + lane;
+            // Residual of my row segment: ALL of it is requested now, asynchronously (cp.async, 16 bytes each), into the
+            // staging tile at the very place the output will overwrite -- one memory round trip per tile, overlapped
+            // with the wait for the accumulator, instead of one exposed round trip per 16-column chunk.
+            const bool res_smem = TS && MODE == GM_RQ_I16 && args.residual != nullptr && args.res_async;
             uint32_t ra[CW], rb[CW], resa[CW / 2], resb[CW / 2];
-            if (MODE == GM_RQ_I16 && c_begin < c_end) load_residual<CW>(args, row, row_ok, n0 + c_begin, resa);
+            if (res_smem) {
+                wait_staging_free();
+                const int16_t* rsrc = reinterpret_cast<const int16_t*>(args.residual) + (long long)(row_ok ? row : 0) * args.res_ld + n0;
+#pragma unroll
+                for (int j = 0; j < CPART / 8; ++j) {
+                    const int c = c_begin + 8 * j;
+                    const bool ok = row_ok && (n0 + c + 8 <= args.N);     // N % 8 == 0 on this path: all or nothing
+                    cp_async_16(swz_addr(out_base, trow, c * 2), ok ? (const void*)(rsrc + c) : args.residual, ok ? 16 : 0);
+                }
+                cp_async_commit();
+            } else if (MODE == GM_RQ_I16 && c_begin < c_end) {
+                load_residual<CW>(args, row, row_ok, n0 + c_begin, resa);
+            }
 
             ptx::mbar_wait(pfull_bar(as), aphase);                       // this tile's column constants are staged
             const int fast = fast_flag[as];
@@ -569,18 +622,11 @@ gemm_i8_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
                 tmem_ld_chunk<CW>(t_row + (uint32_t)c_begin, ra);
                 ptx::tmem_ld_wait();
             }
-            // boxes (128 bytes wide) per epilogue warp; 0: WPB = 2 warps of a lane group share one box (128-wide tiles)
-            // and pair up through a 64-thread named barrier around its store (the even one of the two issues it)
-            constexpr int BOX_COLS = 128 / (OUT_ES ? OUT_ES : 1);
-            constexpr int NBOX_W = CPART / BOX_COLS;
-            constexpr int WPB = NBOX_W > 0 ? 1 : BOX_COLS / CPART;     // warps per box
-            static_assert(!TS || WPB <= 2, "at most two epilogue warps per 128-byte box");
-            const int box_bar = 1 + lane_group * 2 + (col_part >> 1);   // named barrier of my box (WPB == 2)
-            const bool box_leader = (NBOX_W > 0) || ((col_part & 1) == 0);
-            if (TS) {                                                    // my previous tile's TMA stores have read my staging rows
-                if (lane == 0 && box_leader) ptx::tma_store_wait_read<0>();
-                if (NBOX_W == 0) asm volatile("bar.sync %0, 64;" ::"r"(box_bar) : "memory");
-                else __syncwarp();
+            if (res_smem) {
+                cp_async_wait_all();                                     // my own copies: no barrier needed to read them back
+                if (work) load_residual_smem<CW>(out_base, trow, c_begin, resa);
+            } else if (TS) {
+                wait_staging_free();
             }
             if (work) {
 #pragma unroll 1
@@ -589,7 +635,10 @@ gemm_i8_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
                     const bool has2 = (c0 + 2 * CW) < c_end;
                     if (has1) {
                         tmem_ld_chunk<CW>(t_row + (uint32_t)(c0 + CW), rb);
-                        if (MODE == GM_RQ_I16) load_residual<CW>(args, row, row_ok, n0 + c0 + CW, resb);
+                        if (MODE == GM_RQ_I16) {
+                            if (res_smem) load_residual_smem<CW>(out_base, trow, c0 + CW, resb);
+                            else load_residual<CW>(args, row, row_ok, n0 + c0 + CW, resb);
+                        }
                     }
                     epilogue_chunk<MODE, CW, TS>(ra, resa, cp + c0, cb + c0, args, row, row_ok, n0 + c0, fast,
                                                  out_base, lane_group * 32 + lane, c0);
@@ -597,7 +646,10 @@ gemm_i8_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
                     if (has1) {
                         if (has2) {
                             tmem_ld_chunk<CW>(t_row + (uint32_t)(c0 + 2 * CW), ra);
-                            if (MODE == GM_RQ_I16) load_residual<CW>(args, row, row_ok, n0 + c0 + 2 * CW, resa);
+                            if (MODE == GM_RQ_I16) {
+                                if (res_smem) load_residual_smem<CW>(out_base, trow, c0 + 2 * CW, resa);
+                                else load_residual<CW>(args, row, row_ok, n0 + c0 + 2 * CW, resa);
+                            }
                         }
                         epilogue_chunk<MODE, CW, TS>(rb, resb, cp + c0 + CW, cb + c0 + CW, args, row, row_ok, n0 + c0 + CW, fast,
                                                      out_base, lane_group * 32 + lane, c0 + CW);
@@ -835,6 +887,7 @@ extern "C" int ivit_gemm_i8(ivit_ctx* ctx, const int8_t* A, int64_t lda, const i
         if (ga.scalar_mode == 1 && use2 && user && ga.rq2.e >= 18 && ga.rqr.e >= 18) ga.scalar_mode = 3;
     }
     ga.scale = epi->scale; ga.out = out; ga.out_ld = epi->out_ld;
+    ga.res_async = (epi->residual && ((uintptr_t)epi->residual % 16) == 0 && epi->res_ld % 8 == 0) ? 1 : 0;
     static const char* dbg_env = getenv("IVIT_GEMM_DEBUG");
     ga.debug = dbg_env ? atoi(dbg_env) : 0;
     int mode;
