@@ -341,11 +341,15 @@ struct GemmSmem {
 // runs its own epilogue.  Per MMA an SM's shared memory then feeds 128 x 32 B of A + BN/2 x 32 B of W instead of
 // 128 x 32 + BN x 32: the un-paired kernel saturates the SM's shared-memory data pipe (tensor-core operand reads +
 // epilogue LDS/STS ~ 93 % of peak wavefronts, profiles/ncu_full_r1g), which is what bounds it, not the tensor pipe.
-template <int BN, int STAGES, int MODE, bool TS, bool PAIR>
+// OM (output mode): 0 direct global stores from registers; 1 output staged in shared memory and written by TMA;
+//                   2 direct stores, the staging tile instead holds the int16 residual, prefetched per tile by cp.async
+template <int BN, int STAGES, int MODE, int OM, bool PAIR>
 __global__ void __launch_bounds__(gemm_threads(MODE), 1)
 gemm_i8_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                        const __grid_constant__ CUtensorMap tmap_out, const GemmArgs args) {
-    constexpr int OUT_ES = !TS ? 0 : (MODE == GM_RQ_I8 ? 1 : 2);
+    constexpr bool TS = (OM == 1), RSM = (OM == 2);
+    static_assert(!RSM || MODE == GM_RQ_I16, "residual staging belongs to the 16-bit epilogue");
+    constexpr int OUT_ES = (OM == 0) ? 0 : (MODE == GM_RQ_I8 ? 1 : 2);
     using S = GemmSmem<BN, STAGES, OUT_ES, PAIR>;
     constexpr uint32_t TMEM_COLS = 2 * BN;            // double-buffered accumulator (256 or 512)
     constexpr int WPG = gemm_wpg(MODE);
@@ -593,13 +597,13 @@ gemm_i8_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
                 else __syncwarp();
             };
             const int trow = lane_group * 32 + lane;
-            // Residual of my row segment: ALL of it is requested now, asynchronously (cp.async, 16 bytes each), into the
-            // staging tile at the very place the output will overwrite -- one memory round trip per tile, overlapped
-            // with the wait for the accumulator, instead of one exposed round trip per 16-column chunk.
-            const bool res_smem = TS && MODE == GM_RQ_I16 && args.residual != nullptr && args.res_async;
+            // OM == 2: the residual of my row segment -- ALL of it -- is requested now, asynchronously (cp.async, 16 bytes
+            // each), into my own rows of the staging tile: one memory round trip per tile, overlapped with the wait for
+            // the accumulator, instead of one exposed round trip per 16-column chunk.  The rows are private to this
+            // thread (it consumed the previous tile's copy itself), so no synchronisation is involved.
+            constexpr bool res_smem = RSM;
             uint32_t ra[CW], rb[CW], resa[CW / 2], resb[CW / 2];
             if (res_smem) {
-                wait_staging_free();
                 const int16_t* rsrc = reinterpret_cast<const int16_t*>(args.residual) + (long long)(row_ok ? row : 0) * args.res_ld + n0;
 #pragma unroll
                 for (int j = 0; j < CPART / 8; ++j) {
@@ -786,14 +790,14 @@ int make_tmap_2d_u8(ivit_ctx* ctx, CUtensorMap* tm, const void* base, uint64_t i
     return IVIT_OK;
 }
 
-template <int BN, int STAGES, int MODE, bool TS, bool PAIR>
+template <int BN, int STAGES, int MODE, int OM, bool PAIR>
 static int launch_gemm(ivit_ctx* ctx, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const GemmArgs& ga,
                        cudaStream_t s) {
-    constexpr int OUT_ES = !TS ? 0 : (MODE == GM_RQ_I8 ? 1 : 2);
+    constexpr int OUT_ES = (OM == 0) ? 0 : (MODE == GM_RQ_I8 ? 1 : 2);
     constexpr int CS = PAIR ? 2 : 1;
     using S = GemmSmem<BN, STAGES, OUT_ES, PAIR>;
     static_assert(S::TOTAL <= 227 * 1024, "shared memory budget");
-    auto kern = gemm_i8_tcgen05_kernel<BN, STAGES, MODE, TS, PAIR>;
+    auto kern = gemm_i8_tcgen05_kernel<BN, STAGES, MODE, OM, PAIR>;
     static bool attr_set = false;                     // per instantiation
     static int max_clusters = 0;
     cudaLaunchConfig_t cfg = {};
@@ -843,19 +847,29 @@ static int dispatch_bn(ivit_ctx* ctx, const int8_t* A, int64_t lda, const int8_t
         constexpr int ES = (MODE == GM_RQ_I8) ? 1 : 2;
         const bool ts = ((uintptr_t)ga.out % 16 == 0) && ((ga.out_ld * ES) % 16 == 0) && ga.mode_bits == 8 * ES && ga.N % 8 == 0 &&
                         (!ga.residual || (((uintptr_t)ga.residual % 4) == 0 && ga.res_ld % 2 == 0));
+        if constexpr (MODE == GM_RQ_I16) {
+            // residual epilogue: direct 16-byte stores, residual prefetched through shared memory (cp.async)
+            const bool rsm = ga.residual && ga.res_async && ((uintptr_t)ga.out % 16 == 0) && ((ga.out_ld * ES) % 16 == 0) &&
+                             ga.mode_bits == 16 && ga.N % 8 == 0 && wide;
+            if (rsm) {
+                to = ta;
+                if (pair) return launch_gemm<256, 4, MODE, 2, true>(ctx, ta, tb, to, ga, s);
+                return launch_gemm<256, 3, MODE, 2, false>(ctx, ta, tb, to, ga, s);
+            }
+        }
         if (ts) {
             // byte-typed view of the output: inner dim = N*ES bytes, box = 128 bytes x 32 rows (one epilogue warp), 128B swizzle
             rc = make_tmap_2d_u8(ctx, &to, ga.out, (uint64_t)ga.N * ES, (uint64_t)ga.M, (uint64_t)ga.out_ld * ES, 128, GEMM_BM / 4);
             if (rc) return rc;
-            if (pair) return launch_gemm<256, (ES == 1 ? 5 : 4), MODE, true, true>(ctx, ta, tb, to, ga, s);
-            if (wide) return launch_gemm<256, 3, MODE, true, false>(ctx, ta, tb, to, ga, s);
-            return launch_gemm<128, 5, MODE, true, false>(ctx, ta, tb, to, ga, s);
+            if (pair) return launch_gemm<256, (ES == 1 ? 5 : 4), MODE, 1, true>(ctx, ta, tb, to, ga, s);
+            if (wide) return launch_gemm<256, 3, MODE, 1, false>(ctx, ta, tb, to, ga, s);
+            return launch_gemm<128, 5, MODE, 1, false>(ctx, ta, tb, to, ga, s);
         }
     }
     to = ta;
-    if (pair) return launch_gemm<256, 6, MODE, false, true>(ctx, ta, tb, to, ga, s);
-    if (wide) return launch_gemm<256, 4, MODE, false, false>(ctx, ta, tb, to, ga, s);
-    return launch_gemm<128, 6, MODE, false, false>(ctx, ta, tb, to, ga, s);
+    if (pair) return launch_gemm<256, 6, MODE, 0, true>(ctx, ta, tb, to, ga, s);
+    if (wide) return launch_gemm<256, 4, MODE, 0, false>(ctx, ta, tb, to, ga, s);
+    return launch_gemm<128, 6, MODE, 0, false>(ctx, ta, tb, to, ga, s);
 }
 
 }  // namespace ivit
