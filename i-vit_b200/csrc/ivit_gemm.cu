@@ -849,8 +849,10 @@ static int dispatch_bn(ivit_ctx* ctx, const int8_t* A, int64_t lda, const int8_t
                         (!ga.residual || (((uintptr_t)ga.residual % 4) == 0 && ga.res_ld % 2 == 0));
         if constexpr (MODE == GM_RQ_I16) {
             // residual epilogue: direct 16-byte stores, residual prefetched through shared memory (cp.async)
-            const bool rsm = ga.residual && ga.res_async && ((uintptr_t)ga.out % 16 == 0) && ((ga.out_ld * ES) % 16 == 0) &&
-                             ga.mode_bits == 16 && ga.N % 8 == 0 && wide;
+            // (measured slower than the TMA-store form with register residuals, profiles/gemm_bench_r20.log: opt-in)
+            static const char* rsm_env = getenv("IVIT_GEMM_RSM");
+            const bool rsm = rsm_env && rsm_env[0] == '1' && ga.residual && ga.res_async && ((uintptr_t)ga.out % 16 == 0) &&
+                             ((ga.out_ld * ES) % 16 == 0) && ga.mode_bits == 16 && ga.N % 8 == 0 && wide;
             if (rsm) {
                 to = ta;
                 if (pair) return launch_gemm<256, 4, MODE, 2, true>(ctx, ta, tb, to, ga, s);

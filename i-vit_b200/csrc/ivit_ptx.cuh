@@ -90,11 +90,13 @@ IVIT_PTX uint32_t mapa(uint32_t smem_addr, uint32_t cta_rank) {
 IVIT_PTX void mbar_arrive_cluster(uint32_t cluster_addr) {
     asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
+// wait on a local mbarrier that peers arrive on.  Plain (cta-scope) acquire like the arrive above: a cluster-scope
+// acquire makes ptxas put an L1 invalidation (CCTL.IVALL) into the spin loop.
 IVIT_PTX bool mbar_try_wait_cluster(uint32_t bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(ok)
         : "r"(bar), "r"(parity)
