@@ -10,6 +10,8 @@
 //
 // ivit_bmm_i32: QuantMatMul.forward's contraction (quant_modules.py:223-228) for the
 // operator-level API (raw int32 result, strided batched views, int8 or int16 A).
+#include <stdlib.h>
+
 #include "ivit_common.cuh"
 #include "ivit_internal.h"
 
@@ -401,6 +403,14 @@ extern "C" int ivit_attention_i8(ivit_ctx* ctx, const int8_t* qkv, const ivit_at
     a.sum32 = (((long long)(-ap->x0)) << ap->n) < (1LL << 23) ? 1 : 0;
     a.half_s = (ap->me_s.e >= 1 && ap->me_s.e <= 62) ? (1LL << (ap->me_s.e - 1)) : 0;
     a.half_o = (ap->me_o.e >= 1 && ap->me_o.e <= 62) ? (1LL << (ap->me_o.e - 1)) : 0;
+    // DeiT path on the tcgen05 tensor cores (ivit_attn_tc.cu) when its preconditions hold; IVIT_ATTN_TC=0 disables
+    {
+        static const char* tc_env = getenv("IVIT_ATTN_TC");
+        const long long e0 = ((long long)(-ap->x0)) << ap->n;              // largest exponential, E(0)
+        const bool tc = !(tc_env && tc_env[0] == '0') && ap->head_dim == 64 && !swin && p16 && fast && ap->n_tok <= 224 &&
+                        e0 >= (1LL << 15) && e0 < (1LL << 23) && ctx->encode_tiled != nullptr;
+        if (tc) return launch_attention_tc(ctx, qkv, ap, a.half_s, a.half_o, out, s);
+    }
     if (swin && ap->n_tok > 64) return fail(IVIT_ENOTSUP, "ivit_attention_i8: bias/mask path supports n_tok <= 64 (window attention)");
     int rc;
     if (ap->head_dim == 64) rc = (ap->n_tok <= 64) ? dispatch_attention<64, 2>(grid, qkv, a, out, s, swin, p16, fast)

@@ -1,0 +1,365 @@
+// Fused integer attention on the 5th-generation tensor cores (tcgen05, sm_100a) for the DeiT path:
+// head_dim 64, 16-bit probabilities, no relative-position bias / mask, n_tok <= 224.
+//
+//   S = Q K^T  -> qact_attn1 (dyadic requant to int8) -> Shiftmax (IntSoftmax) -> P V -> attn.qact2
+//   reference call order: vit_quant.py:59-83; Shiftmax: quant_modules.py:469-497
+//
+// One CTA per (image, head), two CTAs per SM, 288 threads:
+//   warp 0      TMEM allocator; one thread drives TMA (Q m-tile, K: 64-byte rows, 64B swizzle) and the MMAs:
+//               S[128 x NS] = Q K^T as 2 x tcgen05.mma.kind::i8 (K = 32 each) into TMEM columns [0, NS),
+//               later O_hi / O_lo [128 x 64] = P_hi V / P_lo V (u8 x s8, one MMA per 32 keys and byte plane)
+//               into TMEM columns [0, 64) / [64, 128) -- the S columns are dead by then.
+//   warps 1-8   "softmax" warps, two per TMEM lane group (each owns half of the columns of its 32 rows).  One
+//               thread = one query row: tcgen05.ld hands it its scores, so row max and row sum are thread-local
+//               (one shared-memory exchange with the partner thread of the other column half, no shuffles):
+//                 pass 1  scores -> requant -> int8, four per register (<= 28 registers), running packed max
+//                 pass 2  exponent LUT over max - q (257 entries, exact: the domain is int8 - int8), row sum, F
+//                 pass 3  P = (E * F) >> 16, split into a high and a low byte plane, written to shared memory
+//                         in the K-major 128B-swizzled layout the MMA reads as its A operand
+//               then the output rows: (O_hi << 8) + O_lo -> requant -> int8 -> 32 bytes per thread to global.
+//   V is transposed once per head by the softmax warps into a K-major tile (keys contiguous); keys >= n_tok are
+//   zero there, so the probabilities of padding columns never need masking in the second product.
+//
+// The mma.sync kernel in ivit_attn.cu stays as the general path (Swin bias / mask, 8-bit P, head_dim 32, slow-form
+// requants); this one is selected by the host when its preconditions hold, and computes bit-identical results.
+#include "ivit_common.cuh"
+#include "ivit_internal.h"
+#include "ivit_ptx.cuh"
+
+namespace ivit {
+
+struct AttnTcArgs {
+    int n_seq, n_tok, H;
+    int ns;                       // n_tok rounded up to 16: N of the score MMA
+    int h0;                       // columns [0, h0) belong to column-half 0, [h0, ns) to half 1 (multiples of 16)
+    int32_t m_s, sh_s, m_o, sh_o; // FAST requants: hi32(z*m + half) >> sh
+    long long half_s, half_o;
+    int32_t x0;
+    float inv_x0;
+    int n;
+};
+
+constexpr int ATC_THREADS = 288;
+constexpr int ATC_MAXCH = 7;          // 16-column chunks per column half (n_tok <= 224)
+constexpr int ATC_SQ = 0;             // 128 rows x 64 B
+constexpr int ATC_SK = 8192;          // 224 rows x 64 B
+constexpr int ATC_SVT = 22528;        // 2 k-blocks x (64 rows x 128 B)
+constexpr int ATC_SP = 38912;         // [plane 2][k-block 2][128 rows x 128 B]
+constexpr int ATC_SE = 104448;        // 260 x int32
+constexpr int ATC_SRED = 105488;      // max[2][128] int32, sum[2][128] uint32
+constexpr int ATC_BAR = 107536;       // 6 mbarriers + tmem pointer
+constexpr int ATC_SMEM = 107536 + 64 + 1024;   // + alignment slack
+
+__device__ __forceinline__ uint64_t umma_desc_k_sw64(uint32_t smem_addr) {
+    // K-major, 64-byte rows, 64B swizzle (what a TMA box {64 B, rows} with CU_TENSOR_MAP_SWIZZLE_64B writes):
+    // 8-row x 64 B swizzle atoms, SBO = 512 B, descriptor version 1, layout type 4 (cute SmemDescriptor)
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(512u >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)4 << 61;
+    return d;
+}
+
+__global__ void __launch_bounds__(ATC_THREADS, 2)
+attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
+                    const int8_t* __restrict__ qkv, const AttnTcArgs p, int8_t* __restrict__ out) {
+    extern __shared__ uint8_t atc_smem_raw[];
+    const uint32_t base = (ptx::smem_u32(atc_smem_raw) + 1023u) & ~1023u;
+    uint8_t* smem = atc_smem_raw + (base - ptx::smem_u32(atc_smem_raw));
+    const uint32_t sQ = base + ATC_SQ, sK = base + ATC_SK, sVt = base + ATC_SVT, sP = base + ATC_SP;
+    int32_t* sE = reinterpret_cast<int32_t*>(smem + ATC_SE);
+    int32_t* sRedMax = reinterpret_cast<int32_t*>(smem + ATC_SRED);              // [2][128]
+    uint32_t* sRedSum = reinterpret_cast<uint32_t*>(smem + ATC_SRED + 1024);     // [2][128]
+    const uint32_t bar = base + ATC_BAR;
+    const uint32_t q_full = bar, k_full = bar + 8, s_full = bar + 16, p_ready = bar + 24, o_full = bar + 32, o_done = bar + 40;
+    volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + ATC_BAR + 48);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int b = blockIdx.x / p.H, h = blockIdx.x % p.H;
+    const int n_tok = p.n_tok;
+    const int HD = p.H * 64;
+    const int n_mt = (n_tok + 127) >> 7;
+
+    if (tid == 0) {
+        ptx::prefetch_tensormap(&tmap_q);
+        ptx::prefetch_tensormap(&tmap_k);
+        ptx::mbar_init(q_full, 1);
+        ptx::mbar_init(k_full, 1);
+        ptx::mbar_init(s_full, 1);
+        ptx::mbar_init(p_ready, 8);
+        ptx::mbar_init(o_full, 1);
+        ptx::mbar_init(o_done, 8);
+        ptx::fence_barrier_init();
+    }
+    if (warp == 0) {
+        ptx::tmem_alloc(ptx::smem_u32(const_cast<uint32_t*>(tmem_ptr_smem)), 256);
+        ptx::tmem_relinquish();
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+
+    if (warp == 0) {
+        // ================= control warp: TMA + MMA issue =================
+        if (lane == 0) {
+            const uint32_t idesc_s = ptx::umma_idesc_i8(128, p.ns, 1, 1);
+            const uint32_t idesc_pv = ptx::umma_idesc_i8(128, 64, 0, 1);        // A = unsigned byte planes of P
+            const int nk32 = (n_tok + 31) >> 5;
+            ptx::mbar_arrive_expect_tx(k_full, 224 * 64);
+            ptx::tma_load_3d(sK, &tmap_k, k_full, HD + h * 64, 0, b);
+            for (int mt = 0; mt < n_mt; ++mt) {
+                if (mt > 0) ptx::mbar_wait(o_done, (uint32_t)((mt - 1) & 1));   // TMEM columns and the Q tile are free again
+                ptx::mbar_arrive_expect_tx(q_full, 128 * 64);
+                ptx::tma_load_3d(sQ, &tmap_q, q_full, h * 64, mt * 128, b);
+                ptx::mbar_wait(q_full, (uint32_t)(mt & 1));
+                if (mt == 0) ptx::mbar_wait(k_full, 0);
+                ptx::tc_fence_after();
+                const uint64_t dq = umma_desc_k_sw64(sQ), dk = umma_desc_k_sw64(sK);
+#pragma unroll
+                for (int k = 0; k < 2; ++k)
+                    ptx::mma_i8_ss(tmem_base, dq + (uint64_t)(2 * k), dk + (uint64_t)(2 * k), idesc_s, k ? 1u : 0u);
+                ptx::mma_commit(s_full);
+                // probabilities (and, the first time, V^T) are in shared memory; every S column has been read
+                ptx::mbar_wait(p_ready, (uint32_t)(mt & 1));
+                ptx::tc_fence_after();
+#pragma unroll 1
+                for (int plane = 0; plane < 2; ++plane) {                       // 0: high bytes -> cols [0,64), 1: low -> [64,128)
+#pragma unroll 1
+                    for (int kk = 0; kk < nk32; ++kk) {
+                        const uint64_t da = ptx::umma_desc_k_sw128(sP + (uint32_t)((plane * 2 + (kk >> 2)) * 16384)) + (uint64_t)(2 * (kk & 3));
+                        const uint64_t db = ptx::umma_desc_k_sw128(sVt + (uint32_t)((kk >> 2) * 8192)) + (uint64_t)(2 * (kk & 3));
+                        ptx::mma_i8_ss(tmem_base + (uint32_t)(plane * 64), da, db, idesc_pv, kk ? 1u : 0u);
+                    }
+                }
+                ptx::mma_commit(o_full);
+            }
+        }
+    } else {
+        // ================= softmax warps =================
+        const int sw = warp - 1;                       // 0..7
+        const int lg = warp & 3;                       // TMEM lanes [32*lg, +32)
+        const int half = sw >> 2;                      // column half
+        const int st = sw * 32 + lane;                 // 0..255
+        const int trow = lg * 32 + lane;               // row inside the m-tile
+        const int pair_bar = 1 + lg;                   // named barrier of the two warps sharing my rows
+
+        // ---- exponent LUT: sE[k] = int_exp_shift(-k), k = max - q in [0, 255] ----
+        for (int k = st; k < 256; k += 256) sE[k] = (int32_t)shiftexp(-k, p.x0, p.inv_x0, p.n);
+        // ---- V^T: byte (d, key) at [key >> 7][d][128 B row, 16-byte chunks XOR-swizzled by d & 7]; keys >= n_tok are 0
+        if (st < 224) {
+            const int key = st;
+            uint4 v[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) v[j] = make_uint4(0, 0, 0, 0);
+            if (key < n_tok) {
+                const uint4* src = reinterpret_cast<const uint4*>(qkv + ((long long)b * n_tok + key) * (3LL * HD) + 2 * HD + h * 64);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) v[j] = __ldg(src + j);
+            }
+            const uint32_t kb = (uint32_t)(key >> 7), kc = (uint32_t)(key & 127);
+            const uint32_t colbase = sVt + kb * 8192u + (kc & 15u);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const uint32_t w[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
+#pragma unroll
+                for (int u = 0; u < 16; ++u) {
+                    const uint32_t d = (uint32_t)(16 * j + u);
+                    const uint32_t byte = (w[u >> 2] >> (8 * (u & 3))) & 0xffu;
+                    const uint32_t a = colbase + d * 128u + (((kc >> 4) ^ (d & 7u)) << 4);
+                    asm volatile("st.shared.u8 [%0], %1;" ::"r"(a), "r"(byte) : "memory");
+                }
+            }
+        }
+        asm volatile("bar.sync 5, 256;" ::: "memory");  // LUT visible to all softmax warps (V^T is published with p_ready)
+
+        const int c_begin = half ? p.h0 : 0;
+        const int c_end = half ? p.ns : p.h0;
+        const int nch = (c_end - c_begin) >> 4;        // 16-column chunks of my half (<= ATC_MAXCH)
+        const uint32_t t_row = tmem_base + ((uint32_t)(lg * 32) << 16);
+
+        for (int mt = 0; mt < n_mt; ++mt) {
+            const int row = mt * 128 + trow;
+            ptx::mbar_wait(s_full, (uint32_t)(mt & 1));
+            ptx::tc_fence_after();
+            // ---- pass 1: scores -> int8, packed four per register ----
+            uint32_t sc[ATC_MAXCH * 4];
+            uint32_t mxw = 0x80808080u;
+#pragma unroll
+            for (int c = 0; c < ATC_MAXCH; ++c) {
+                if (c < nch) {
+                    uint32_t r[16];
+                    ptx::tmem_ld_32x32b_x16(t_row + (uint32_t)(c_begin + 16 * c), r);
+                    ptx::tmem_ld_wait();
+#pragma unroll
+                    for (int w = 0; w < 4; ++w) {
+                        int32_t v[4];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e)
+                            v[e] = (int32_t)(((long long)(int32_t)r[4 * w + e] * (long long)p.m_s + p.half_s) >> 32) >> p.sh_s;
+                        uint32_t hi2, pk;
+                        asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, %3;" : "=r"(hi2) : "r"(v[3]), "r"(v[2]), "r"(0));
+                        asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, %3;" : "=r"(pk) : "r"(v[1]), "r"(v[0]), "r"(hi2));
+                        const int col0 = c_begin + 16 * c + 4 * w;
+                        if (col0 + 4 > n_tok) {                                // padding columns: never raise the max
+#pragma unroll
+                            for (int e = 0; e < 4; ++e)
+                                if (col0 + e >= n_tok) pk = (pk & ~(0xffu << (8 * e))) | (0x80u << (8 * e));
+                        }
+                        sc[4 * c + w] = pk;
+                        mxw = __vmaxs4(mxw, pk);
+                    }
+                } else {
+#pragma unroll
+                    for (int w = 0; w < 4; ++w) sc[4 * c + w] = 0x80808080u;
+                }
+            }
+            int32_t mx = max(max((int32_t)(int8_t)(mxw & 0xff), (int32_t)(int8_t)((mxw >> 8) & 0xff)),
+                             max((int32_t)(int8_t)((mxw >> 16) & 0xff), (int32_t)mxw >> 24));
+            sRedMax[half * 128 + trow] = mx;
+            asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+            mx = max(mx, sRedMax[(half ^ 1) * 128 + trow]);
+            // ---- pass 2: exponentials, row sum (E <= |x0| << n < 2^23, <= 112 terms per thread: 32-bit) ----
+            const int32_t* pE = sE + (mx + 128);                              // E(max - q) = pE[-(q + 128)]
+            uint32_t sum = 0;
+#pragma unroll
+            for (int c = 0; c < ATC_MAXCH; ++c) {
+                if (c < nch) {
+#pragma unroll
+                    for (int w = 0; w < 4; ++w) {
+                        const uint32_t u = sc[4 * c + w] ^ 0x80808080u;       // q + 128 per byte
+                        uint32_t E0 = (uint32_t)pE[-(int32_t)(u & 0xff)], E1 = (uint32_t)pE[-(int32_t)((u >> 8) & 0xff)];
+                        uint32_t E2 = (uint32_t)pE[-(int32_t)((u >> 16) & 0xff)], E3 = (uint32_t)pE[-(int32_t)(u >> 24)];
+                        const int col0 = c_begin + 16 * c + 4 * w;
+                        if (col0 + 4 > n_tok) {                                // padding columns do not count
+                            if (col0 + 0 >= n_tok) E0 = 0;
+                            if (col0 + 1 >= n_tok) E1 = 0;
+                            if (col0 + 2 >= n_tok) E2 = 0;
+                            if (col0 + 3 >= n_tok) E3 = 0;
+                        }
+                        sum += (E0 + E1) + (E2 + E3);
+                    }
+                }
+            }
+            sRedSum[half * 128 + trow] = sum;
+            asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+            unsigned long long S = (unsigned long long)sum + sRedSum[(half ^ 1) * 128 + trow];
+            const uint32_t S32 = S > 2147483647ULL ? 2147483647u : (uint32_t)S;   // clamp_max_(2**31-1)
+            const uint32_t F = 2147483647u / (S32 ? S32 : 1u);                    // <= 65535 (host-checked: E(0) >= 2^15)
+            const uint32_t Fs = F << 16;                                          // P = (E*F) >> 16 == umulhi(E, F << 16)
+            // ---- pass 3: probabilities, byte planes -> A operand tiles ----
+            if (mt > 0) { /* sP of the previous m-tile was consumed before o_full, which this thread has waited for */ }
+#pragma unroll
+            for (int c = 0; c < ATC_MAXCH; ++c) {
+                if (c < nch) {
+                    uint32_t lo[4], hi[4];
+#pragma unroll
+                    for (int w = 0; w < 4; ++w) {
+                        const uint32_t u = sc[4 * c + w] ^ 0x80808080u;
+                        const uint32_t P0 = __umulhi((uint32_t)pE[-(int32_t)(u & 0xff)], Fs);
+                        const uint32_t P1 = __umulhi((uint32_t)pE[-(int32_t)((u >> 8) & 0xff)], Fs);
+                        const uint32_t P2 = __umulhi((uint32_t)pE[-(int32_t)((u >> 16) & 0xff)], Fs);
+                        const uint32_t P3 = __umulhi((uint32_t)pE[-(int32_t)(u >> 24)], Fs);
+                        lo[w] = __byte_perm(__byte_perm(P0, P1, 0x0040), __byte_perm(P2, P3, 0x0040), 0x5410);
+                        hi[w] = __byte_perm(__byte_perm(P0, P1, 0x0051), __byte_perm(P2, P3, 0x0051), 0x5410);
+                    }
+                    const int key0 = c_begin + 16 * c;                          // 16 keys = one 16-byte chunk of my row
+                    const uint32_t off = (uint32_t)((key0 >> 7) * 16384) + (uint32_t)trow * 128u +
+                                         (((((uint32_t)key0 >> 4) & 7u) ^ ((uint32_t)trow & 7u)) << 4);
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sP + off), "r"(hi[0]), "r"(hi[1]), "r"(hi[2]), "r"(hi[3]) : "memory");
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sP + 32768u + off), "r"(lo[0]), "r"(lo[1]), "r"(lo[2]), "r"(lo[3]) : "memory");
+                }
+            }
+            ptx::tc_fence_before();                  // my tcgen05.ld of S are complete (wait::ld) and ordered before the arrive
+            ptx::fence_proxy_async();                // P (and V^T) written through the generic proxy -> visible to the MMA
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(p_ready);
+            // ---- output rows: (O_hi << 8) + O_lo -> attn.qact2 -> int8 ----
+            ptx::mbar_wait(o_full, (uint32_t)(mt & 1));
+            ptx::tc_fence_after();
+            uint4* dst = reinterpret_cast<uint4*>(out + ((long long)b * n_tok + row) * (long long)HD + h * 64 + 32 * half);
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {                                      // 16 of my 32 output channels at a time
+                uint32_t oh[16], ol[16];
+                ptx::tmem_ld_32x32b_x16(t_row + (uint32_t)(32 * half + 16 * q), oh);
+                ptx::tmem_ld_32x32b_x16(t_row + (uint32_t)(64 + 32 * half + 16 * q), ol);
+                ptx::tmem_ld_wait();
+                if (q == 1) {                                                  // last TMEM read of this m-tile
+                    ptx::tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) ptx::mbar_arrive(o_done);
+                }
+                uint32_t ow[4];
+#pragma unroll
+                for (int w = 0; w < 4; ++w) {
+                    int32_t o[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const int32_t z = ((int32_t)oh[4 * w + e] << 8) + (int32_t)ol[4 * w + e];
+                        o[e] = (int32_t)(((long long)z * (long long)p.m_o + p.half_o) >> 32) >> p.sh_o;
+                    }
+                    uint32_t hi2;
+                    asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, %3;" : "=r"(hi2) : "r"(o[3]), "r"(o[2]), "r"(0));
+                    asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, %3;" : "=r"(ow[w]) : "r"(o[1]), "r"(o[0]), "r"(hi2));
+                }
+                if (row < n_tok) dst[q] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+            }
+        }
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc(tmem_base, 256);
+    }
+}
+
+// 3D uint8 tensor map over the packed qkv activations: {3*H*64 bytes, n_tok, n_seq}, box {64 B, rows, 1}, 64B swizzle.
+// Rows past n_tok are out of bounds of dimension 1 and read as zeros (per image, not into the next image).
+typedef CUresult (*EncodeTiledFn3)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static int make_tmap_qkv(ivit_ctx* ctx, CUtensorMap* tm, const void* base, int n_seq, int n_tok, int ld, uint32_t box_rows) {
+    if (!ctx->encode_tiled) return fail(IVIT_ECUDA, "cuTensorMapEncodeTiled entry point unavailable");
+    cuuint64_t gdim[3] = {(cuuint64_t)ld, (cuuint64_t)n_tok, (cuuint64_t)n_seq};
+    cuuint64_t gstride[2] = {(cuuint64_t)ld, (cuuint64_t)ld * (cuuint64_t)n_tok};
+    cuuint32_t box[3] = {64, box_rows, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = reinterpret_cast<EncodeTiledFn3>(ctx->encode_tiled)(
+        tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<void*>(base), gdim, gstride, box, estr,
+        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(IVIT_ECUDA, "cuTensorMapEncodeTiled (qkv) failed (CUresult %d)", (int)r);
+    return IVIT_OK;
+}
+
+// Preconditions (checked by the caller): head_dim 64, 16-bit P, no bias / mask, both requants in the fast form,
+// n_tok <= 224, 2^15 <= |x0| << n < 2^23, qkv 16-byte aligned with n_heads * 192 bytes per token.
+int launch_attention_tc(ivit_ctx* ctx, const int8_t* qkv, const ivit_attn_params* ap, long long half_s, long long half_o,
+                        int8_t* out, cudaStream_t s) {
+    AttnTcArgs a;
+    a.n_seq = ap->n_seq; a.n_tok = ap->n_tok; a.H = ap->n_heads;
+    a.ns = (ap->n_tok + 15) & ~15;
+    a.h0 = (((a.ns >> 4) + 1) >> 1) << 4;
+    a.m_s = ap->me_s.m; a.sh_s = ap->me_s.e - 32; a.m_o = ap->me_o.m; a.sh_o = ap->me_o.e - 32;
+    a.half_s = half_s; a.half_o = half_o;
+    a.x0 = ap->x0; a.inv_x0 = 1.0f / (float)ap->x0; a.n = ap->n;
+    const int ld = 3 * ap->n_heads * 64;
+    CUtensorMap tq, tk;
+    int rc = make_tmap_qkv(ctx, &tq, qkv, ap->n_seq, ap->n_tok, ld, 128);
+    if (rc) return rc;
+    rc = make_tmap_qkv(ctx, &tk, qkv, ap->n_seq, ap->n_tok, ld, 224);
+    if (rc) return rc;
+    static bool attr_set = false;
+    if (!attr_set) {
+        IVIT_CUDA_OK(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATC_SMEM));
+        attr_set = true;
+    }
+    attention_tc_kernel<<<ap->n_seq * ap->n_heads, ATC_THREADS, ATC_SMEM, s>>>(tq, tk, qkv, a, out);
+    IVIT_LAUNCH_OK("attention_tc_kernel");
+    return IVIT_OK;
+}
+
+}  // namespace ivit

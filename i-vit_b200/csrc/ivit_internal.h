@@ -20,6 +20,9 @@ namespace ivit {
 int fail(int code, const char* fmt, ...);
 int fail_cuda(cudaError_t e, const char* what);
 inline cudaStream_t st(ivit_stream s) { return reinterpret_cast<cudaStream_t>(s); }
+// tcgen05 attention (ivit_attn_tc.cu); preconditions are checked by ivit_attention_i8
+int launch_attention_tc(ivit_ctx* ctx, const int8_t* qkv, const ivit_attn_params* ap, long long half_s, long long half_o,
+                        int8_t* out, cudaStream_t s);
 inline int dtype_size(int dt) {
     switch (dt) {
         case IVIT_I8: case IVIT_U8: return 1;
