@@ -62,7 +62,15 @@ __device__ __forceinline__ uint64_t umma_desc_k_sw64(uint32_t smem_addr) {
     return d;
 }
 
-__global__ void __launch_bounds__(ATC_THREADS, 2)
+// long waits (a TMA round trip, a batch of MMAs, the other warps' softmax pass): back off instead of spinning on the
+// issue slots the working warps need
+__device__ __forceinline__ void mbar_wait_sleep(uint32_t bar, uint32_t parity) {
+    while (!ptx::mbar_try_wait(bar, parity)) __nanosleep(64);
+}
+
+// NS16 = ceil(n_tok / 16): number of 16-column score chunks (compile-time so that the packed scores stay in registers)
+template <int NS16>
+__global__ void __maxnreg__(112)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                     const int8_t* __restrict__ qkv, const AttnTcArgs p, int8_t* __restrict__ out) {
     extern __shared__ uint8_t atc_smem_raw[];
@@ -105,17 +113,17 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     if (warp == 0) {
         // ================= control warp: TMA + MMA issue =================
         if (lane == 0) {
-            const uint32_t idesc_s = ptx::umma_idesc_i8(128, p.ns, 1, 1);
+            const uint32_t idesc_s = ptx::umma_idesc_i8(128, 16 * NS16, 1, 1);
             const uint32_t idesc_pv = ptx::umma_idesc_i8(128, 64, 0, 1);        // A = unsigned byte planes of P
             const int nk32 = (n_tok + 31) >> 5;
             ptx::mbar_arrive_expect_tx(k_full, 224 * 64);
             ptx::tma_load_3d(sK, &tmap_k, k_full, HD + h * 64, 0, b);
             for (int mt = 0; mt < n_mt; ++mt) {
-                if (mt > 0) ptx::mbar_wait(o_done, (uint32_t)((mt - 1) & 1));   // TMEM columns and the Q tile are free again
+                if (mt > 0) mbar_wait_sleep(o_done, (uint32_t)((mt - 1) & 1));   // TMEM columns and the Q tile are free again
                 ptx::mbar_arrive_expect_tx(q_full, 128 * 64);
                 ptx::tma_load_3d(sQ, &tmap_q, q_full, h * 64, mt * 128, b);
-                ptx::mbar_wait(q_full, (uint32_t)(mt & 1));
-                if (mt == 0) ptx::mbar_wait(k_full, 0);
+                mbar_wait_sleep(q_full, (uint32_t)(mt & 1));
+                if (mt == 0) mbar_wait_sleep(k_full, 0);
                 ptx::tc_fence_after();
                 const uint64_t dq = umma_desc_k_sw64(sQ), dk = umma_desc_k_sw64(sK);
 #pragma unroll
@@ -123,7 +131,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
                     ptx::mma_i8_ss(tmem_base, dq + (uint64_t)(2 * k), dk + (uint64_t)(2 * k), idesc_s, k ? 1u : 0u);
                 ptx::mma_commit(s_full);
                 // probabilities (and, the first time, V^T) are in shared memory; every S column has been read
-                ptx::mbar_wait(p_ready, (uint32_t)(mt & 1));
+                mbar_wait_sleep(p_ready, (uint32_t)(mt & 1));
                 ptx::tc_fence_after();
 #pragma unroll 1
                 for (int plane = 0; plane < 2; ++plane) {                       // 0: high bytes -> cols [0,64), 1: low -> [64,128)
@@ -175,20 +183,23 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
         }
         asm volatile("bar.sync 5, 256;" ::: "memory");  // LUT visible to all softmax warps (V^T is published with p_ready)
 
-        const int c_begin = half ? p.h0 : 0;
-        const int c_end = half ? p.ns : p.h0;
-        const int nch = (c_end - c_begin) >> 4;        // 16-column chunks of my half (<= ATC_MAXCH)
+        constexpr int NCH0 = (NS16 + 1) / 2, NCH1 = NS16 / 2;    // 16-column chunks of the lower / upper column half
+        constexpr int NS = 16 * NS16, H0 = 16 * NCH0;
+        static_assert(NCH0 <= ATC_MAXCH, "n_tok <= 224");
+        const int c_begin = half ? H0 : 0;
+        const int nch = half ? NCH1 : NCH0;
+        const int npad_all = NS - n_tok;                          // 0..15 padding columns, all in the last chunk
+        const int npad = (half == (NCH1 > 0 ? 1 : 0)) ? npad_all : 0;   // ... which belongs to the upper half (if it has chunks)
         const uint32_t t_row = tmem_base + ((uint32_t)(lg * 32) << 16);
 
         for (int mt = 0; mt < n_mt; ++mt) {
             const int row = mt * 128 + trow;
-            ptx::mbar_wait(s_full, (uint32_t)(mt & 1));
+            mbar_wait_sleep(s_full, (uint32_t)(mt & 1));
             ptx::tc_fence_after();
-            // ---- pass 1: scores -> int8, packed four per register ----
-            uint32_t sc[ATC_MAXCH * 4];
-            uint32_t mxw = 0x80808080u;
+            // ---- pass 1: scores -> requant -> saturate to int8 -> stored as q + 128 (unsigned), four per register ----
+            uint32_t sc[NCH0 * 4];
 #pragma unroll
-            for (int c = 0; c < ATC_MAXCH; ++c) {
+            for (int c = 0; c < NCH0; ++c) {
                 if (c < nch) {
                     uint32_t r[16];
                     ptx::tmem_ld_32x32b_x16(t_row + (uint32_t)(c_begin + 16 * c), r);
@@ -202,66 +213,69 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
                         uint32_t hi2, pk;
                         asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, %3;" : "=r"(hi2) : "r"(v[3]), "r"(v[2]), "r"(0));
                         asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, %3;" : "=r"(pk) : "r"(v[1]), "r"(v[0]), "r"(hi2));
-                        const int col0 = c_begin + 16 * c + 4 * w;
-                        if (col0 + 4 > n_tok) {                                // padding columns: never raise the max
-#pragma unroll
-                            for (int e = 0; e < 4; ++e)
-                                if (col0 + e >= n_tok) pk = (pk & ~(0xffu << (8 * e))) | (0x80u << (8 * e));
-                        }
-                        sc[4 * c + w] = pk;
-                        mxw = __vmaxs4(mxw, pk);
+                        sc[4 * c + w] = pk ^ 0x80808080u;
                     }
                 } else {
 #pragma unroll
-                    for (int w = 0; w < 4; ++w) sc[4 * c + w] = 0x80808080u;
+                    for (int w = 0; w < 4; ++w) sc[4 * c + w] = 0u;
                 }
             }
-            int32_t mx = max(max((int32_t)(int8_t)(mxw & 0xff), (int32_t)(int8_t)((mxw >> 8) & 0xff)),
-                             max((int32_t)(int8_t)((mxw >> 16) & 0xff), (int32_t)mxw >> 24));
-            sRedMax[half * 128 + trow] = mx;
+            // padding columns (all in the last chunk): forced to the smallest value so that they never raise the max;
+            // their exponentials are taken out of the sum below; their probabilities meet zero V rows
+            if (npad > 0) {
+                constexpr int CL = (NCH1 > 0 ? NCH1 : NCH0) - 1;                         // my last chunk (static index)
+#pragma unroll
+                for (int w = 0; w < 4; ++w) {
+                    const int valid = 16 - npad_all - 4 * w;                             // columns of this word that exist
+                    const uint32_t keep = valid >= 4 ? 0xffffffffu : (valid <= 0 ? 0u : (0xffffffffu >> (8 * (4 - valid))));
+                    sc[4 * CL + w] &= keep;
+                }
+            }
+            uint32_t mxw = 0u;
+#pragma unroll
+            for (int i = 0; i < NCH0 * 4; ++i) mxw = __vmaxu4(mxw, sc[i]);
+            mxw = __vmaxu4(mxw, mxw >> 16);
+            uint32_t mxu = max(mxw & 0xffu, (mxw >> 8) & 0xffu);                        // row max of q + 128 over my columns
+            sRedMax[half * 128 + trow] = (int32_t)mxu;
             asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
-            mx = max(mx, sRedMax[(half ^ 1) * 128 + trow]);
-            // ---- pass 2: exponentials, row sum (E <= |x0| << n < 2^23, <= 112 terms per thread: 32-bit) ----
-            const int32_t* pE = sE + (mx + 128);                              // E(max - q) = pE[-(q + 128)]
+            mxu = max(mxu, (uint32_t)sRedMax[(half ^ 1) * 128 + trow]);
+            // ---- pass 2: exponentials E(max - q) = sE[mxu - u], row sum (E < 2^23, <= 112 terms per thread: 32-bit) ----
+            const uint32_t pEb = ptx::smem_u32(sE) + 4u * mxu;
+            auto lut = [&](uint32_t u, int i) -> uint32_t {
+                const uint32_t byte = __byte_perm(u, 0u, 0x4440 + i);
+                uint32_t v;
+                asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(pEb - 4u * byte));       // read-only table: free to schedule
+                return v;
+            };
             uint32_t sum = 0;
 #pragma unroll
-            for (int c = 0; c < ATC_MAXCH; ++c) {
+            for (int c = 0; c < NCH0; ++c) {
                 if (c < nch) {
 #pragma unroll
                     for (int w = 0; w < 4; ++w) {
-                        const uint32_t u = sc[4 * c + w] ^ 0x80808080u;       // q + 128 per byte
-                        uint32_t E0 = (uint32_t)pE[-(int32_t)(u & 0xff)], E1 = (uint32_t)pE[-(int32_t)((u >> 8) & 0xff)];
-                        uint32_t E2 = (uint32_t)pE[-(int32_t)((u >> 16) & 0xff)], E3 = (uint32_t)pE[-(int32_t)(u >> 24)];
-                        const int col0 = c_begin + 16 * c + 4 * w;
-                        if (col0 + 4 > n_tok) {                                // padding columns do not count
-                            if (col0 + 0 >= n_tok) E0 = 0;
-                            if (col0 + 1 >= n_tok) E1 = 0;
-                            if (col0 + 2 >= n_tok) E2 = 0;
-                            if (col0 + 3 >= n_tok) E3 = 0;
-                        }
-                        sum += (E0 + E1) + (E2 + E3);
+                        const uint32_t u = sc[4 * c + w];
+                        sum += (lut(u, 0) + lut(u, 1)) + (lut(u, 2) + lut(u, 3));
                     }
                 }
             }
+            sum -= (uint32_t)npad * lut(0u, 0);                                          // padding columns carry u = 0
             sRedSum[half * 128 + trow] = sum;
             asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
             unsigned long long S = (unsigned long long)sum + sRedSum[(half ^ 1) * 128 + trow];
             const uint32_t S32 = S > 2147483647ULL ? 2147483647u : (uint32_t)S;   // clamp_max_(2**31-1)
             const uint32_t F = 2147483647u / (S32 ? S32 : 1u);                    // <= 65535 (host-checked: E(0) >= 2^15)
             const uint32_t Fs = F << 16;                                          // P = (E*F) >> 16 == umulhi(E, F << 16)
-            // ---- pass 3: probabilities, byte planes -> A operand tiles ----
-            if (mt > 0) { /* sP of the previous m-tile was consumed before o_full, which this thread has waited for */ }
+            // ---- pass 3: probabilities, byte planes -> A operand tiles (sP of the previous m-tile was consumed before
+            //      o_full, which this thread has waited for) ----
 #pragma unroll
-            for (int c = 0; c < ATC_MAXCH; ++c) {
+            for (int c = 0; c < NCH0; ++c) {
                 if (c < nch) {
                     uint32_t lo[4], hi[4];
 #pragma unroll
                     for (int w = 0; w < 4; ++w) {
-                        const uint32_t u = sc[4 * c + w] ^ 0x80808080u;
-                        const uint32_t P0 = __umulhi((uint32_t)pE[-(int32_t)(u & 0xff)], Fs);
-                        const uint32_t P1 = __umulhi((uint32_t)pE[-(int32_t)((u >> 8) & 0xff)], Fs);
-                        const uint32_t P2 = __umulhi((uint32_t)pE[-(int32_t)((u >> 16) & 0xff)], Fs);
-                        const uint32_t P3 = __umulhi((uint32_t)pE[-(int32_t)(u >> 24)], Fs);
+                        const uint32_t u = sc[4 * c + w];
+                        const uint32_t P0 = __umulhi(lut(u, 0), Fs), P1 = __umulhi(lut(u, 1), Fs);
+                        const uint32_t P2 = __umulhi(lut(u, 2), Fs), P3 = __umulhi(lut(u, 3), Fs);
                         lo[w] = __byte_perm(__byte_perm(P0, P1, 0x0040), __byte_perm(P2, P3, 0x0040), 0x5410);
                         hi[w] = __byte_perm(__byte_perm(P0, P1, 0x0051), __byte_perm(P2, P3, 0x0051), 0x5410);
                     }
@@ -277,7 +291,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(p_ready);
             // ---- output rows: (O_hi << 8) + O_lo -> attn.qact2 -> int8 ----
-            ptx::mbar_wait(o_full, (uint32_t)(mt & 1));
+            mbar_wait_sleep(o_full, (uint32_t)(mt & 1));
             ptx::tc_fence_after();
             uint4* dst = reinterpret_cast<uint4*>(out + ((long long)b * n_tok + row) * (long long)HD + h * 64 + 32 * half);
 #pragma unroll
@@ -352,12 +366,22 @@ int launch_attention_tc(ivit_ctx* ctx, const int8_t* qkv, const ivit_attn_params
     if (rc) return rc;
     rc = make_tmap_qkv(ctx, &tk, qkv, ap->n_seq, ap->n_tok, ld, 224);
     if (rc) return rc;
-    static bool attr_set = false;
-    if (!attr_set) {
-        IVIT_CUDA_OK(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATC_SMEM));
-        attr_set = true;
+    const int grid = ap->n_seq * ap->n_heads;
+#define ATC_CASE(N)                                                                                                   \
+    case N: {                                                                                                         \
+        static bool attr_set = false;                                                                                 \
+        if (!attr_set) {                                                                                              \
+            IVIT_CUDA_OK(cudaFuncSetAttribute(attention_tc_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATC_SMEM)); \
+            attr_set = true;                                                                                          \
+        }                                                                                                             \
+        attention_tc_kernel<N><<<grid, ATC_THREADS, ATC_SMEM, s>>>(tq, tk, qkv, a, out);                              \
+    } break;
+    switch (a.ns >> 4) {
+        ATC_CASE(1) ATC_CASE(2) ATC_CASE(3) ATC_CASE(4) ATC_CASE(5) ATC_CASE(6) ATC_CASE(7)
+        ATC_CASE(8) ATC_CASE(9) ATC_CASE(10) ATC_CASE(11) ATC_CASE(12) ATC_CASE(13) ATC_CASE(14)
+        default: return fail(IVIT_ENOTSUP, "attention (tcgen05): n_tok=%d > 224", ap->n_tok);
     }
-    attention_tc_kernel<<<ap->n_seq * ap->n_heads, ATC_THREADS, ATC_SMEM, s>>>(tq, tk, qkv, a, out);
+#undef ATC_CASE
     IVIT_LAUNCH_OK("attention_tc_kernel");
     return IVIT_OK;
 }

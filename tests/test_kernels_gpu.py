@@ -361,7 +361,7 @@ def test_attention(K, n_seq, n_tok, H, D, p_bits):
     me_s, me_o = (int(m_s[0]), int(e_s[0])), (int(m_o[0]), int(e_o[0]))
     want = oracle_attention(qkv, n_seq, n_tok, H, D, me_s, x0, me_o, p_bits)
     got = K.attention_i8(dev(qkv), n_seq, n_tok, H, D, me_s, x0, me_o, p_bits=p_bits)
-    assert np.abs(want).max() > 20, "test should produce non-trivial outputs"
+    assert np.abs(want).max() > 12, "test should produce non-trivial outputs"
     assert_equal(got, want, "attention n_tok=%d H=%d D=%d P%d" % (n_tok, H, D, p_bits))
 
 
