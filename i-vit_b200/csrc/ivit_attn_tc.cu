@@ -22,6 +22,8 @@
 //
 // The mma.sync kernel in ivit_attn.cu stays as the general path (Swin bias / mask, 8-bit P, head_dim 32, slow-form
 // requants); this one is selected by the host when its preconditions hold, and computes bit-identical results.
+#include <stdlib.h>
+
 #include "ivit_common.cuh"
 #include "ivit_internal.h"
 #include "ivit_ptx.cuh"
@@ -37,6 +39,7 @@ struct AttnTcArgs {
     int32_t x0;
     float inv_x0;
     int n;
+    int sleep_ns;                 // back-off between mbarrier polls (IVIT_ATTN_SLEEP, default 0: plain polling)
 };
 
 constexpr int ATC_THREADS = 288;
@@ -45,10 +48,11 @@ constexpr int ATC_SQ = 0;             // 128 rows x 64 B
 constexpr int ATC_SK = 8192;          // 224 rows x 64 B
 constexpr int ATC_SVT = 22528;        // 2 k-blocks x (64 rows x 128 B)
 constexpr int ATC_SP = 38912;         // [plane 2][k-block 2][128 rows x 128 B]
-constexpr int ATC_SE = 104448;        // 260 x int32
-constexpr int ATC_SRED = 105488;      // max[2][128] int32, sum[2][128] uint32
-constexpr int ATC_BAR = 107536;       // 6 mbarriers + tmem pointer
-constexpr int ATC_SMEM = 107536 + 64 + 1024;   // + alignment slack
+constexpr int ATC_LUTC = 8;           // copies of the exponent table (lane & 7 picks one): 2.1 instead of 3.5 bank conflicts per lookup
+constexpr int ATC_SE = 104448;        // [256][ATC_LUTC] int32
+constexpr int ATC_SRED = 0;           // max[2][128] int32, sum[2][128] uint32: aliases the Q tile (dead between S and the next load)
+constexpr int ATC_BAR = ATC_SE + 256 * ATC_LUTC * 4;   // 6 mbarriers + tmem pointer
+constexpr int ATC_SMEM = ATC_BAR + 64 + 1024;  // + alignment slack; two CTAs per SM need <= 115200
 
 __device__ __forceinline__ uint64_t umma_desc_k_sw64(uint32_t smem_addr) {
     // K-major, 64-byte rows, 64B swizzle (what a TMA box {64 B, rows} with CU_TENSOR_MAP_SWIZZLE_64B writes):
@@ -64,8 +68,9 @@ __device__ __forceinline__ uint64_t umma_desc_k_sw64(uint32_t smem_addr) {
 
 // long waits (a TMA round trip, a batch of MMAs, the other warps' softmax pass): back off instead of spinning on the
 // issue slots the working warps need
-__device__ __forceinline__ void mbar_wait_sleep(uint32_t bar, uint32_t parity) {
-    while (!ptx::mbar_try_wait(bar, parity)) __nanosleep(64);
+__device__ __forceinline__ void mbar_wait_sleep(uint32_t bar, uint32_t parity, int ns) {
+    while (!ptx::mbar_try_wait(bar, parity))
+        if (ns > 0) __nanosleep((unsigned)ns);
 }
 
 // NS16 = ceil(n_tok / 16): number of 16-column score chunks (compile-time so that the packed scores stay in registers)
@@ -119,11 +124,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
             ptx::mbar_arrive_expect_tx(k_full, 224 * 64);
             ptx::tma_load_3d(sK, &tmap_k, k_full, HD + h * 64, 0, b);
             for (int mt = 0; mt < n_mt; ++mt) {
-                if (mt > 0) mbar_wait_sleep(o_done, (uint32_t)((mt - 1) & 1));   // TMEM columns and the Q tile are free again
+                if (mt > 0) mbar_wait_sleep(o_done, (uint32_t)((mt - 1) & 1), p.sleep_ns);   // TMEM columns and the Q tile are free again
                 ptx::mbar_arrive_expect_tx(q_full, 128 * 64);
                 ptx::tma_load_3d(sQ, &tmap_q, q_full, h * 64, mt * 128, b);
-                mbar_wait_sleep(q_full, (uint32_t)(mt & 1));
-                if (mt == 0) mbar_wait_sleep(k_full, 0);
+                mbar_wait_sleep(q_full, (uint32_t)(mt & 1), p.sleep_ns);
+                if (mt == 0) mbar_wait_sleep(k_full, 0, p.sleep_ns);
                 ptx::tc_fence_after();
                 const uint64_t dq = umma_desc_k_sw64(sQ), dk = umma_desc_k_sw64(sK);
 #pragma unroll
@@ -131,7 +136,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
                     ptx::mma_i8_ss(tmem_base, dq + (uint64_t)(2 * k), dk + (uint64_t)(2 * k), idesc_s, k ? 1u : 0u);
                 ptx::mma_commit(s_full);
                 // probabilities (and, the first time, V^T) are in shared memory; every S column has been read
-                mbar_wait_sleep(p_ready, (uint32_t)(mt & 1));
+                mbar_wait_sleep(p_ready, (uint32_t)(mt & 1), p.sleep_ns);
                 ptx::tc_fence_after();
 #pragma unroll 1
                 for (int plane = 0; plane < 2; ++plane) {                       // 0: high bytes -> cols [0,64), 1: low -> [64,128)
@@ -155,7 +160,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
         const int pair_bar = 1 + lg;                   // named barrier of the two warps sharing my rows
 
         // ---- exponent LUT: sE[k] = int_exp_shift(-k), k = max - q in [0, 255] ----
-        for (int k = st; k < 256; k += 256) sE[k] = (int32_t)shiftexp(-k, p.x0, p.inv_x0, p.n);
+        {
+            const int32_t e = (int32_t)shiftexp(-st, p.x0, p.inv_x0, p.n);
+#pragma unroll
+            for (int j = 0; j < ATC_LUTC; ++j) sE[st * ATC_LUTC + j] = e;
+        }
         // ---- V^T: byte (d, key) at [key >> 7][d][128 B row, 16-byte chunks XOR-swizzled by d & 7]; keys >= n_tok are 0
         if (st < 224) {
             const int key = st;
@@ -194,7 +203,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
 
         for (int mt = 0; mt < n_mt; ++mt) {
             const int row = mt * 128 + trow;
-            mbar_wait_sleep(s_full, (uint32_t)(mt & 1));
+            mbar_wait_sleep(s_full, (uint32_t)(mt & 1), p.sleep_ns);
             ptx::tc_fence_after();
             // ---- pass 1: scores -> requant -> saturate to int8 -> stored as q + 128 (unsigned), four per register ----
             uint32_t sc[NCH0 * 4];
@@ -240,11 +249,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
             asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
             mxu = max(mxu, (uint32_t)sRedMax[(half ^ 1) * 128 + trow]);
             // ---- pass 2: exponentials E(max - q) = sE[mxu - u], row sum (E < 2^23, <= 112 terms per thread: 32-bit) ----
-            const uint32_t pEb = ptx::smem_u32(sE) + 4u * mxu;
+            const uint32_t pEb = ptx::smem_u32(sE) + (uint32_t)(4 * ATC_LUTC) * mxu + 4u * ((uint32_t)lane & (ATC_LUTC - 1));
             auto lut = [&](uint32_t u, int i) -> uint32_t {
                 const uint32_t byte = __byte_perm(u, 0u, 0x4440 + i);
                 uint32_t v;
-                asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(pEb - 4u * byte));       // read-only table: free to schedule
+                asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(pEb - (uint32_t)(4 * ATC_LUTC) * byte));   // read-only table: free to schedule
                 return v;
             };
             uint32_t sum = 0;
@@ -291,7 +300,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(p_ready);
             // ---- output rows: (O_hi << 8) + O_lo -> attn.qact2 -> int8 ----
-            mbar_wait_sleep(o_full, (uint32_t)(mt & 1));
+            mbar_wait_sleep(o_full, (uint32_t)(mt & 1), p.sleep_ns);
             ptx::tc_fence_after();
             uint4* dst = reinterpret_cast<uint4*>(out + ((long long)b * n_tok + row) * (long long)HD + h * 64 + 32 * half);
 #pragma unroll
@@ -360,6 +369,8 @@ int launch_attention_tc(ivit_ctx* ctx, const int8_t* qkv, const ivit_attn_params
     a.m_s = ap->me_s.m; a.sh_s = ap->me_s.e - 32; a.m_o = ap->me_o.m; a.sh_o = ap->me_o.e - 32;
     a.half_s = half_s; a.half_o = half_o;
     a.x0 = ap->x0; a.inv_x0 = 1.0f / (float)ap->x0; a.n = ap->n;
+    static const char* sleep_env = getenv("IVIT_ATTN_SLEEP");
+    a.sleep_ns = sleep_env ? atoi(sleep_env) : 0;
     const int ld = 3 * ap->n_heads * 64;
     CUtensorMap tq, tk;
     int rc = make_tmap_qkv(ctx, &tq, qkv, ap->n_seq, ap->n_tok, ld, 128);
