@@ -42,7 +42,7 @@ struct AttnTcArgs {
     int sleep_ns;                 // back-off between mbarrier polls (IVIT_ATTN_SLEEP, default 0: plain polling)
 };
 
-constexpr int ATC_THREADS = 288;
+constexpr int ATC_THREADS = 256;
 constexpr int ATC_MAXCH = 7;          // 16-column chunks per column half (n_tok <= 224)
 constexpr int ATC_SQ = 0;             // 128 rows x 64 B
 constexpr int ATC_SK = 8192;          // 224 rows x 64 B
@@ -75,7 +75,7 @@ __device__ __forceinline__ void mbar_wait_sleep(uint32_t bar, uint32_t parity, i
 
 // NS16 = ceil(n_tok / 16): number of 16-column score chunks (compile-time so that the packed scores stay in registers)
 template <int NS16>
-__global__ void __maxnreg__(112)
+__global__ void __launch_bounds__(ATC_THREADS, 2)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                     const int8_t* __restrict__ qkv, const AttnTcArgs p, int8_t* __restrict__ out) {
     extern __shared__ uint8_t atc_smem_raw[];
@@ -115,44 +115,20 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
 
-    if (warp == 0) {
-        // ================= control warp: TMA + MMA issue =================
-        if (lane == 0) {
-            const uint32_t idesc_s = ptx::umma_idesc_i8(128, 16 * NS16, 1, 1);
-            const uint32_t idesc_pv = ptx::umma_idesc_i8(128, 64, 0, 1);        // A = unsigned byte planes of P
-            const int nk32 = (n_tok + 31) >> 5;
-            ptx::mbar_arrive_expect_tx(k_full, 224 * 64);
-            ptx::tma_load_3d(sK, &tmap_k, k_full, HD + h * 64, 0, b);
-            for (int mt = 0; mt < n_mt; ++mt) {
-                if (mt > 0) mbar_wait_sleep(o_done, (uint32_t)((mt - 1) & 1), p.sleep_ns);   // TMEM columns and the Q tile are free again
-                ptx::mbar_arrive_expect_tx(q_full, 128 * 64);
-                ptx::tma_load_3d(sQ, &tmap_q, q_full, h * 64, mt * 128, b);
-                mbar_wait_sleep(q_full, (uint32_t)(mt & 1), p.sleep_ns);
-                if (mt == 0) mbar_wait_sleep(k_full, 0, p.sleep_ns);
-                ptx::tc_fence_after();
-                const uint64_t dq = umma_desc_k_sw64(sQ), dk = umma_desc_k_sw64(sK);
-#pragma unroll
-                for (int k = 0; k < 2; ++k)
-                    ptx::mma_i8_ss(tmem_base, dq + (uint64_t)(2 * k), dk + (uint64_t)(2 * k), idesc_s, k ? 1u : 0u);
-                ptx::mma_commit(s_full);
-                // probabilities (and, the first time, V^T) are in shared memory; every S column has been read
-                mbar_wait_sleep(p_ready, (uint32_t)(mt & 1), p.sleep_ns);
-                ptx::tc_fence_after();
-#pragma unroll 1
-                for (int plane = 0; plane < 2; ++plane) {                       // 0: high bytes -> cols [0,64), 1: low -> [64,128)
-#pragma unroll 1
-                    for (int kk = 0; kk < nk32; ++kk) {
-                        const uint64_t da = ptx::umma_desc_k_sw128(sP + (uint32_t)((plane * 2 + (kk >> 2)) * 16384)) + (uint64_t)(2 * (kk & 3));
-                        const uint64_t db = ptx::umma_desc_k_sw128(sVt + (uint32_t)((kk >> 2) * 8192)) + (uint64_t)(2 * (kk & 3));
-                        ptx::mma_i8_ss(tmem_base + (uint32_t)(plane * 64), da, db, idesc_pv, kk ? 1u : 0u);
-                    }
-                }
-                ptx::mma_commit(o_full);
-            }
-        }
-    } else {
+    // ---- control duties (TMA, MMA issue) are folded into thread 0 between its own softmax phases: eight warps per CTA
+    //      keep two CTAs per SM at 128 registers (a ninth warp makes the SM sub-partitions uneven and halves occupancy)
+    const uint32_t idesc_s = ptx::umma_idesc_i8(128, 16 * NS16, 1, 1);
+    const uint32_t idesc_pv = ptx::umma_idesc_i8(128, 64, 0, 1);                // A = unsigned byte planes of P
+    const int nk32 = (n_tok + 31) >> 5;
+    if (tid == 0) {
+        ptx::mbar_arrive_expect_tx(k_full, 224 * 64);
+        ptx::tma_load_3d(sK, &tmap_k, k_full, HD + h * 64, 0, b);
+        ptx::mbar_arrive_expect_tx(q_full, 128 * 64);
+        ptx::tma_load_3d(sQ, &tmap_q, q_full, h * 64, 0, b);
+    }
+    {
         // ================= softmax warps =================
-        const int sw = warp - 1;                       // 0..7
+        const int sw = warp;                           // 0..7
         const int lg = warp & 3;                       // TMEM lanes [32*lg, +32)
         const int half = sw >> 2;                      // column half
         const int st = sw * 32 + lane;                 // 0..255
@@ -190,7 +166,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
                 }
             }
         }
-        asm volatile("bar.sync 5, 256;" ::: "memory");  // LUT visible to all softmax warps (V^T is published with p_ready)
+        __syncthreads();                                 // LUT visible to all warps (V^T is published with p_ready)
 
         constexpr int NCH0 = (NS16 + 1) / 2, NCH1 = NS16 / 2;    // 16-column chunks of the lower / upper column half
         constexpr int NS = 16 * NS16, H0 = 16 * NCH0;
@@ -203,6 +179,22 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
 
         for (int mt = 0; mt < n_mt; ++mt) {
             const int row = mt * 128 + trow;
+            if (tid == 0) {
+                if (mt > 0) {                                                    // TMEM columns and the Q tile are free again
+                    mbar_wait_sleep(o_done, (uint32_t)((mt - 1) & 1), p.sleep_ns);
+                    ptx::mbar_arrive_expect_tx(q_full, 128 * 64);
+                    ptx::tma_load_3d(sQ, &tmap_q, q_full, h * 64, mt * 128, b);
+                }
+                mbar_wait_sleep(q_full, (uint32_t)(mt & 1), p.sleep_ns);
+                if (mt == 0) mbar_wait_sleep(k_full, 0, p.sleep_ns);
+                ptx::tc_fence_after();
+                const uint64_t dq = umma_desc_k_sw64(sQ), dk = umma_desc_k_sw64(sK);
+#pragma unroll
+                for (int k = 0; k < 2; ++k)
+                    ptx::mma_i8_ss(tmem_base, dq + (uint64_t)(2 * k), dk + (uint64_t)(2 * k), idesc_s, k ? 1u : 0u);
+                ptx::mma_commit(s_full);
+            }
+            __syncwarp();
             mbar_wait_sleep(s_full, (uint32_t)(mt & 1), p.sleep_ns);
             ptx::tc_fence_after();
             // ---- pass 1: scores -> requant -> saturate to int8 -> stored as q + 128 (unsigned), four per register ----
@@ -299,6 +291,22 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
             ptx::fence_proxy_async();                // P (and V^T) written through the generic proxy -> visible to the MMA
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(p_ready);
+            if (tid == 0) {
+                // probabilities (and, the first time, V^T) are in shared memory; every S column has been read
+                mbar_wait_sleep(p_ready, (uint32_t)(mt & 1), p.sleep_ns);
+                ptx::tc_fence_after();
+#pragma unroll 1
+                for (int plane = 0; plane < 2; ++plane) {                       // 0: high bytes -> cols [0,64), 1: low -> [64,128)
+#pragma unroll 1
+                    for (int kk = 0; kk < nk32; ++kk) {
+                        const uint64_t da = ptx::umma_desc_k_sw128(sP + (uint32_t)((plane * 2 + (kk >> 2)) * 16384)) + (uint64_t)(2 * (kk & 3));
+                        const uint64_t db = ptx::umma_desc_k_sw128(sVt + (uint32_t)((kk >> 2) * 8192)) + (uint64_t)(2 * (kk & 3));
+                        ptx::mma_i8_ss(tmem_base + (uint32_t)(plane * 64), da, db, idesc_pv, kk ? 1u : 0u);
+                    }
+                }
+                ptx::mma_commit(o_full);
+            }
+            __syncwarp();
             // ---- output rows: (O_hi << 8) + O_lo -> attn.qact2 -> int8 ----
             mbar_wait_sleep(o_full, (uint32_t)(mt & 1), p.sleep_ns);
             ptx::tc_fence_after();
@@ -383,6 +391,7 @@ int launch_attention_tc(ivit_ctx* ctx, const int8_t* qkv, const ivit_attn_params
         static bool attr_set = false;                                                                                 \
         if (!attr_set) {                                                                                              \
             IVIT_CUDA_OK(cudaFuncSetAttribute(attention_tc_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATC_SMEM)); \
+            IVIT_CUDA_OK(cudaFuncSetAttribute(attention_tc_kernel<N>, cudaFuncAttributePreferredSharedMemoryCarveout, 100)); \
             attr_set = true;                                                                                          \
         }                                                                                                             \
         attention_tc_kernel<N><<<grid, ATC_THREADS, ATC_SMEM, s>>>(tq, tk, qkv, a, out);                              \
