@@ -135,13 +135,6 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
         const int trow = lg * 32 + lane;               // row inside the m-tile
         const int pair_bar = 1 + lg;                   // named barrier of the two warps sharing my rows
 
-        // ---- exponent LUT: sE[k] = int_exp_shift(-k), k = max - q in [0, 255] ----
-        {
-            const int32_t e = (int32_t)shiftexp(-st, p.x0, p.inv_x0, p.n);
-#pragma unroll
-            for (int j = 0; j < ATC_LUTC; ++j) sE[st * ATC_LUTC + j] = e;
-        }
-        // ---- V^T: byte (d, key) at [key >> 7][d][128 B row, 16-byte chunks XOR-swizzled by d & 7]; keys >= n_tok are 0
         if (st < 224) {
             const int key = st;
             uint4 v[4];
@@ -151,6 +144,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
                 const uint4* src = reinterpret_cast<const uint4*>(qkv + ((long long)b * n_tok + key) * (3LL * HD) + 2 * HD + h * 64);
 #pragma unroll
                 for (int j = 0; j < 4; ++j) v[j] = __ldg(src + j);
+            }
+            // ---- exponent LUT while the V row is in flight: sE[k][copy] = int_exp_shift(-k), k = max - q in [0, 255] ----
+            {
+                const int32_t e = (int32_t)shiftexp(-st, p.x0, p.inv_x0, p.n);
+#pragma unroll
+                for (int j = 0; j < ATC_LUTC; ++j) sE[st * ATC_LUTC + j] = e;
             }
             const uint32_t kb = (uint32_t)(key >> 7), kc = (uint32_t)(key & 127);
             const uint32_t colbase = sVt + kb * 8192u + (kc & 15u);
@@ -165,6 +164,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
                     asm volatile("st.shared.u8 [%0], %1;" ::"r"(a), "r"(byte) : "memory");
                 }
             }
+        }
+        else {
+            const int32_t e = (int32_t)shiftexp(-st, p.x0, p.inv_x0, p.n);
+#pragma unroll
+            for (int j = 0; j < ATC_LUTC; ++j) sE[st * ATC_LUTC + j] = e;
         }
         __syncthreads();                                 // LUT visible to all warps (V^T is published with p_ready)
 
@@ -197,6 +201,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
             __syncwarp();
             mbar_wait_sleep(s_full, (uint32_t)(mt & 1), p.sleep_ns);
             ptx::tc_fence_after();
+            // my 32 rows of this m-tile lie past the sequence (upper lane groups of the last m-tile): nothing to compute, the
+            // MMA reads whatever is in their P rows and nobody stores the result (both warps of a lane group agree)
+            const bool act = (mt * 128 + lg * 32) < n_tok;
+            if (act) {
             // ---- pass 1: scores -> requant -> saturate to int8 -> stored as q + 128 (unsigned), four per register ----
             uint32_t sc[NCH0 * 4];
 #pragma unroll
@@ -287,6 +295,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
                     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sP + 32768u + off), "r"(lo[0]), "r"(lo[1]), "r"(lo[2]), "r"(lo[3]) : "memory");
                 }
             }
+            }
             ptx::tc_fence_before();                  // my tcgen05.ld of S are complete (wait::ld) and ordered before the arrive
             ptx::fence_proxy_async();                // P (and V^T) written through the generic proxy -> visible to the MMA
             __syncwarp();
@@ -311,6 +320,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
             mbar_wait_sleep(o_full, (uint32_t)(mt & 1), p.sleep_ns);
             ptx::tc_fence_after();
             uint4* dst = reinterpret_cast<uint4*>(out + ((long long)b * n_tok + row) * (long long)HD + h * 64 + 32 * half);
+            if (!act) {
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive(o_done);
+                continue;
+            }
 #pragma unroll
             for (int q = 0; q < 2; ++q) {                                      // 16 of my 32 output channels at a time
                 uint32_t oh[16], ol[16];
