@@ -190,9 +190,11 @@ layernorm_i16_i8_kernel(const int16_t* __restrict__ x, int64_t rows, int C, cons
                 if (fast) {
 #pragma unroll
                     for (int u = 0; u < 8; ++u) {
-                        const LnCol p = s_c[u * nvec + vi];
-                        const int32_t z0 = (int32_t)(mul_wide_s32(y[j][u], F) >> 1);   // floor(y*F/2), |.| <= 2^30
-                        r[u] = (int32_t)(mad_wide_s32(z0, p.m, p.c) >> 32) >> p.sh;
+                        const int4 pw = *reinterpret_cast<const int4*>(&s_c[u * nvec + vi]);   // one 16-byte load: {m, sh, c}
+                        const long long pc = (long long)(((unsigned long long)(uint32_t)pw.w << 32) | (uint32_t)pw.z);
+                        int32_t z0 = (int32_t)(mul_wide_s32(y[j][u], F) >> 1);         // floor(y*F/2), |.| <= 2^30
+                        asm("" : "+r"(z0));                                            // a plain 32-bit value from here on
+                        r[u] = (int32_t)(((long long)z0 * (long long)pw.x + pc) >> 32) >> pw.y;   // IMAD.HI with 64-bit addend
                     }
                 } else {
 #pragma unroll
