@@ -50,9 +50,10 @@ constexpr int ATC_SVT = 22528;        // 2 k-blocks x (64 rows x 128 B)
 constexpr int ATC_SP = 38912;         // [plane 2][k-block 2][128 rows x 128 B]
 constexpr int ATC_LUTC = 8;           // copies of the exponent table (lane & 7 picks one): 2.1 instead of 3.5 bank conflicts per lookup
 constexpr int ATC_SE = 104448;        // [256][ATC_LUTC] int32
-constexpr int ATC_SRED = 0;           // max[2][128] int32, sum[2][128] uint32: aliases the Q tile (dead between S and the next load)
 constexpr int ATC_BAR = ATC_SE + 256 * ATC_LUTC * 4;   // 6 mbarriers + tmem pointer
-constexpr int ATC_SMEM = ATC_BAR + 64 + 1024;  // + alignment slack; two CTAs per SM need <= 115200
+constexpr int ATC_SRED = ATC_BAR + 64;         // sum[2][128] uint32, max[2][128] uint8
+constexpr int ATC_SMEM = ATC_SRED + 1024 + 256 + 1024;  // + alignment slack; two CTAs per SM need <= 115200
+static_assert(ATC_SMEM <= 115200, "two CTAs per SM");
 
 __device__ __forceinline__ uint64_t umma_desc_k_sw64(uint32_t smem_addr) {
     // K-major, 64-byte rows, 64B swizzle (what a TMA box {64 B, rows} with CU_TENSOR_MAP_SWIZZLE_64B writes):
@@ -83,8 +84,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     uint8_t* smem = atc_smem_raw + (base - ptx::smem_u32(atc_smem_raw));
     const uint32_t sQ = base + ATC_SQ, sK = base + ATC_SK, sVt = base + ATC_SVT, sP = base + ATC_SP;
     int32_t* sE = reinterpret_cast<int32_t*>(smem + ATC_SE);
-    int32_t* sRedMax = reinterpret_cast<int32_t*>(smem + ATC_SRED);              // [2][128]
-    uint32_t* sRedSum = reinterpret_cast<uint32_t*>(smem + ATC_SRED + 1024);     // [2][128]
+    uint32_t* sRedSum = reinterpret_cast<uint32_t*>(smem + ATC_SRED);            // [2][128]
+    uint8_t* sRedMax = smem + ATC_SRED + 1024;                                   // [2][128]
     const uint32_t bar = base + ATC_BAR;
     const uint32_t q_full = bar, k_full = bar + 8, s_full = bar + 16, p_ready = bar + 24, o_full = bar + 32, o_done = bar + 40;
     volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + ATC_BAR + 48);
@@ -184,11 +185,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
         for (int mt = 0; mt < n_mt; ++mt) {
             const int row = mt * 128 + trow;
             if (tid == 0) {
-                if (mt > 0) {                                                    // TMEM columns and the Q tile are free again
-                    mbar_wait_sleep(o_done, (uint32_t)((mt - 1) & 1), p.sleep_ns);
-                    ptx::mbar_arrive_expect_tx(q_full, 128 * 64);
-                    ptx::tma_load_3d(sQ, &tmap_q, q_full, h * 64, mt * 128, b);
-                }
+                if (mt > 0) mbar_wait_sleep(o_done, (uint32_t)((mt - 1) & 1), p.sleep_ns);   // TMEM columns are free again
                 mbar_wait_sleep(q_full, (uint32_t)(mt & 1), p.sleep_ns);
                 if (mt == 0) mbar_wait_sleep(k_full, 0, p.sleep_ns);
                 ptx::tc_fence_after();
@@ -201,6 +198,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
             __syncwarp();
             mbar_wait_sleep(s_full, (uint32_t)(mt & 1), p.sleep_ns);
             ptx::tc_fence_after();
+            if (tid == 0 && mt + 1 < n_mt) {                 // the score MMAs have consumed the Q tile: fetch the next one now
+                ptx::mbar_arrive_expect_tx(q_full, 128 * 64);
+                ptx::tma_load_3d(sQ, &tmap_q, q_full, h * 64, (mt + 1) * 128, b);
+            }
             // my 32 rows of this m-tile lie past the sequence (upper lane groups of the last m-tile): nothing to compute, the
             // MMA reads whatever is in their P rows and nobody stores the result (both warps of a lane group agree)
             const bool act = (mt * 128 + lg * 32) < n_tok;
@@ -245,7 +246,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
             for (int i = 0; i < NCH0 * 4; ++i) mxw = __vmaxu4(mxw, sc[i]);
             mxw = __vmaxu4(mxw, mxw >> 16);
             uint32_t mxu = max(mxw & 0xffu, (mxw >> 8) & 0xffu);                        // row max of q + 128 over my columns
-            sRedMax[half * 128 + trow] = (int32_t)mxu;
+            sRedMax[half * 128 + trow] = (uint8_t)mxu;
             asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
             mxu = max(mxu, (uint32_t)sRedMax[(half ^ 1) * 128 + trow]);
             // ---- pass 2: exponentials E(max - q) = sE[mxu - u], row sum (E < 2^23, <= 112 terms per thread: 32-bit) ----
