@@ -46,7 +46,7 @@ constexpr int ATC_THREADS = 256;
 constexpr int ATC_MAXCH = 7;          // 16-column chunks per column half (n_tok <= 224)
 constexpr int ATC_SQ = 0;             // 128 rows x 64 B
 constexpr int ATC_SK = 8192;          // 224 rows x 64 B
-constexpr int ATC_SVT = 22528;        // 2 k-blocks x (64 rows x 128 B)
+constexpr int ATC_SVT = 22528;        // V as loaded: 224 keys x 64 B (N-major B operand of the second product), 16 KB reserved
 constexpr int ATC_SP = 38912;         // [plane 2][k-block 2][128 rows x 128 B]
 constexpr int ATC_LUTC = 8;           // copies of the exponent table (lane & 7 picks one): 2.1 instead of 3.5 bank conflicts per lookup
 constexpr int ATC_SE = 104448;        // [256][ATC_LUTC] int32
@@ -58,6 +58,19 @@ static_assert(ATC_SMEM <= 115200, "two CTAs per SM");
 __device__ __forceinline__ uint64_t umma_desc_k_sw64(uint32_t smem_addr) {
     // K-major, 64-byte rows, 64B swizzle (what a TMA box {64 B, rows} with CU_TENSOR_MAP_SWIZZLE_64B writes):
     // 8-row x 64 B swizzle atoms, SBO = 512 B, descriptor version 1, layout type 4 (cute SmemDescriptor)
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(512u >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)4 << 61;
+    return d;
+}
+
+// B operand of P V: V[key][d] exactly as TMA writes it (64-byte rows of d, 64B swizzle) is an N-major ("MN-major")
+// tile in UMMA terms: 64 contiguous N values per row, 8-key groups 512 B apart (SBO), one N atom (LBO unused).
+// cute: make_umma_desc<Major::MN>, LayoutType::B64 = Swizzle<2,4,3> o ((4,n),(8,k)):((1,LBO),(4,SBO)) in 16-byte units.
+__device__ __forceinline__ uint64_t umma_desc_mn_sw64(uint32_t smem_addr) {
     uint64_t d = 0;
     d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
     d |= (uint64_t)1 << 16;
@@ -119,11 +132,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     // ---- control duties (TMA, MMA issue) are folded into thread 0 between its own softmax phases: eight warps per CTA
     //      keep two CTAs per SM at 128 registers (a ninth warp makes the SM sub-partitions uneven and halves occupancy)
     const uint32_t idesc_s = ptx::umma_idesc_i8(128, 16 * NS16, 1, 1);
-    const uint32_t idesc_pv = ptx::umma_idesc_i8(128, 64, 0, 1);                // A = unsigned byte planes of P
+    const uint32_t idesc_pv = ptx::umma_idesc_i8(128, 64, 0, 1) | (1u << 16);   // A = unsigned byte planes of P; B (V) N-major
     const int nk32 = (n_tok + 31) >> 5;
     if (tid == 0) {
-        ptx::mbar_arrive_expect_tx(k_full, 224 * 64);
+        ptx::mbar_arrive_expect_tx(k_full, 2 * 224 * 64);                       // K and V tiles (same box, keys >= n_tok read as zeros)
         ptx::tma_load_3d(sK, &tmap_k, k_full, HD + h * 64, 0, b);
+        ptx::tma_load_3d(sVt, &tmap_k, k_full, 2 * HD + h * 64, 0, b);
         ptx::mbar_arrive_expect_tx(q_full, 128 * 64);
         ptx::tma_load_3d(sQ, &tmap_q, q_full, h * 64, 0, b);
     }
@@ -136,42 +150,13 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
         const int trow = lg * 32 + lane;               // row inside the m-tile
         const int pair_bar = 1 + lg;                   // named barrier of the two warps sharing my rows
 
-        if (st < 224) {
-            const int key = st;
-            uint4 v[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) v[j] = make_uint4(0, 0, 0, 0);
-            if (key < n_tok) {
-                const uint4* src = reinterpret_cast<const uint4*>(qkv + ((long long)b * n_tok + key) * (3LL * HD) + 2 * HD + h * 64);
-#pragma unroll
-                for (int j = 0; j < 4; ++j) v[j] = __ldg(src + j);
-            }
-            // ---- exponent LUT while the V row is in flight: sE[k][copy] = int_exp_shift(-k), k = max - q in [0, 255] ----
-            {
-                const int32_t e = (int32_t)shiftexp(-st, p.x0, p.inv_x0, p.n);
-#pragma unroll
-                for (int j = 0; j < ATC_LUTC; ++j) sE[st * ATC_LUTC + j] = e;
-            }
-            const uint32_t kb = (uint32_t)(key >> 7), kc = (uint32_t)(key & 127);
-            const uint32_t colbase = sVt + kb * 8192u + (kc & 15u);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const uint32_t w[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
-#pragma unroll
-                for (int u = 0; u < 16; ++u) {
-                    const uint32_t d = (uint32_t)(16 * j + u);
-                    const uint32_t byte = (w[u >> 2] >> (8 * (u & 3))) & 0xffu;
-                    const uint32_t a = colbase + d * 128u + (((kc >> 4) ^ (d & 7u)) << 4);
-                    asm volatile("st.shared.u8 [%0], %1;" ::"r"(a), "r"(byte) : "memory");
-                }
-            }
-        }
-        else {
+        // ---- exponent LUT: sE[k][copy] = int_exp_shift(-k), k = max - q in [0, 255] ----
+        {
             const int32_t e = (int32_t)shiftexp(-st, p.x0, p.inv_x0, p.n);
 #pragma unroll
             for (int j = 0; j < ATC_LUTC; ++j) sE[st * ATC_LUTC + j] = e;
         }
-        __syncthreads();                                 // LUT visible to all warps (V^T is published with p_ready)
+        __syncthreads();                                 // LUT visible to all warps
 
         constexpr int NCH0 = (NS16 + 1) / 2, NCH1 = NS16 / 2;    // 16-column chunks of the lower / upper column half
         constexpr int NS = 16 * NS16, H0 = 16 * NCH0;
@@ -298,11 +283,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
             }
             }
             ptx::tc_fence_before();                  // my tcgen05.ld of S are complete (wait::ld) and ordered before the arrive
-            ptx::fence_proxy_async();                // P (and V^T) written through the generic proxy -> visible to the MMA
+            ptx::fence_proxy_async();                // P written through the generic proxy -> visible to the MMA
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(p_ready);
             if (tid == 0) {
-                // probabilities (and, the first time, V^T) are in shared memory; every S column has been read
+                // probabilities are in shared memory; every S column has been read
                 mbar_wait_sleep(p_ready, (uint32_t)(mt & 1), p.sleep_ns);
                 ptx::tc_fence_after();
 #pragma unroll 1
@@ -310,7 +295,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
 #pragma unroll 1
                     for (int kk = 0; kk < nk32; ++kk) {
                         const uint64_t da = ptx::umma_desc_k_sw128(sP + (uint32_t)((plane * 2 + (kk >> 2)) * 16384)) + (uint64_t)(2 * (kk & 3));
-                        const uint64_t db = ptx::umma_desc_k_sw128(sVt + (uint32_t)((kk >> 2) * 8192)) + (uint64_t)(2 * (kk & 3));
+                        const uint64_t db = umma_desc_mn_sw64(sVt + (uint32_t)(kk * 2048));       // 32 keys x 64 B per MMA
                         ptx::mma_i8_ss(tmem_base + (uint32_t)(plane * 64), da, db, idesc_pv, kk ? 1u : 0u);
                     }
                 }
