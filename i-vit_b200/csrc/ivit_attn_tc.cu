@@ -43,6 +43,8 @@ struct AttnTcArgs {
 };
 
 constexpr int ATC_THREADS = 256;
+constexpr int ATC_CTRL = 128;         // control thread: lane 0 of warp 4 -- the upper column half has one chunk less, so this warp
+                                      // reaches the hand-over points first and the MMAs go out as soon as the last warp arrives
 constexpr int ATC_MAXCH = 7;          // 16-column chunks per column half (n_tok <= 224)
 constexpr int ATC_SQ = 0;             // 128 rows x 64 B
 constexpr int ATC_SK = 8192;          // 224 rows x 64 B
@@ -129,12 +131,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
 
-    // ---- control duties (TMA, MMA issue) are folded into thread 0 between its own softmax phases: eight warps per CTA
+    // ---- control duties (TMA, MMA issue) are folded into one thread (ATC_CTRL) between its own softmax phases: eight warps per CTA
     //      keep two CTAs per SM at 128 registers (a ninth warp makes the SM sub-partitions uneven and halves occupancy)
     const uint32_t idesc_s = ptx::umma_idesc_i8(128, 16 * NS16, 1, 1);
     const uint32_t idesc_pv = ptx::umma_idesc_i8(128, 64, 0, 1) | (1u << 16);   // A = unsigned byte planes of P; B (V) N-major
     const int nk32 = (n_tok + 31) >> 5;
-    if (tid == 0) {
+    if (tid == ATC_CTRL) {
         ptx::mbar_arrive_expect_tx(k_full, 2 * 224 * 64);                       // K and V tiles (same box, keys >= n_tok read as zeros)
         ptx::tma_load_3d(sK, &tmap_k, k_full, HD + h * 64, 0, b);
         ptx::tma_load_3d(sVt, &tmap_k, k_full, 2 * HD + h * 64, 0, b);
@@ -169,7 +171,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
 
         for (int mt = 0; mt < n_mt; ++mt) {
             const int row = mt * 128 + trow;
-            if (tid == 0) {
+            if (tid == ATC_CTRL) {
                 if (mt > 0) mbar_wait_sleep(o_done, (uint32_t)((mt - 1) & 1), p.sleep_ns);   // TMEM columns are free again
                 mbar_wait_sleep(q_full, (uint32_t)(mt & 1), p.sleep_ns);
                 if (mt == 0) mbar_wait_sleep(k_full, 0, p.sleep_ns);
@@ -183,7 +185,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
             __syncwarp();
             mbar_wait_sleep(s_full, (uint32_t)(mt & 1), p.sleep_ns);
             ptx::tc_fence_after();
-            if (tid == 0 && mt + 1 < n_mt) {                 // the score MMAs have consumed the Q tile: fetch the next one now
+            if (tid == ATC_CTRL && mt + 1 < n_mt) {                 // the score MMAs have consumed the Q tile: fetch the next one now
                 ptx::mbar_arrive_expect_tx(q_full, 128 * 64);
                 ptx::tma_load_3d(sQ, &tmap_q, q_full, h * 64, (mt + 1) * 128, b);
             }
@@ -286,7 +288,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
             ptx::fence_proxy_async();                // P written through the generic proxy -> visible to the MMA
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(p_ready);
-            if (tid == 0) {
+            if (tid == ATC_CTRL) {
                 // probabilities are in shared memory; every S column has been read
                 mbar_wait_sleep(p_ready, (uint32_t)(mt & 1), p.sleep_ns);
                 ptx::tc_fence_after();
