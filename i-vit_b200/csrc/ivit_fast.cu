@@ -13,6 +13,8 @@
 //   IntLayerNorm + QuantAct (quant_modules.py:353-386): int16 rows -> int8, 16-byte vector
 //       loads, per-channel constants (bias, m, e) held in registers across the rows a warp
 //       processes (a lane always owns the same channels).
+#include <stdlib.h>
+
 #include "ivit_common.cuh"
 #include "ivit_internal.h"
 
@@ -41,53 +43,94 @@ __global__ void gelu_lut_build_kernel(int32_t x0, float inv_x0, int n, const ivi
 
 // ------------------------------------------------------------------------------------
 // LUT application.  One warp per row; the row lives in registers as 16-byte vectors.
+// Three rows per warp are in flight, one in each stage of
+//     (a) global loads of the row            (b) row max -> load of its 256-byte table line
+//     (c) table line -> shared memory, one byte lookup per element, 16-byte stores
+// so that neither the row's memory round trip nor the dependent table-line load is exposed (the single-row form
+// spent 2/3 of its warp time waiting on them: long-scoreboard stalls, profiles/ncu_full_r1h).
 // ------------------------------------------------------------------------------------
 template <int MAXV>
 __global__ void __launch_bounds__(256)
 gelu_lut_apply_kernel(const int8_t* __restrict__ q, int64_t rows, int cols, const int8_t* __restrict__ lut,
                       int8_t* __restrict__ out) {
-    __shared__ __align__(16) uint8_t s_lut[8][256];
+    __shared__ __align__(256) uint8_t s_lut[8][256];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int nvec = cols >> 4;
     const int64_t warp0 = (int64_t)blockIdx.x * 8 + w;
     const int64_t nwarps = (int64_t)gridDim.x * 8;
-    for (int64_t row = warp0; row < rows; row += nwarps) {
+    uint4 v[3][MAXV];
+    uint2 line[3];
+    auto stage_a = [&](int64_t row, uint4 (&vv)[MAXV]) {                 // loads of one row
+        if (row >= rows) return;
         const uint4* src = reinterpret_cast<const uint4*>(q + row * (int64_t)cols);
-        uint4 v[MAXV];
-        uint32_t mxw = 0x80808080u;                              // four int8 -128
 #pragma unroll
         for (int j = 0; j < MAXV; ++j) {
             const int vi = lane + 32 * j;
-            if (vi < nvec) {
-                v[j] = __ldg(src + vi);
-                mxw = __vmaxs4(mxw, v[j].x); mxw = __vmaxs4(mxw, v[j].y);
-                mxw = __vmaxs4(mxw, v[j].z); mxw = __vmaxs4(mxw, v[j].w);
+            vv[j] = make_uint4(0x80808080u, 0x80808080u, 0x80808080u, 0x80808080u);   // four int8 -128: neutral for the max
+            if (vi < nvec) vv[j] = __ldg(src + vi);
+        }
+    };
+    auto stage_b = [&](int64_t row, const uint4 (&vv)[MAXV], uint2& ln) {   // row max -> its table line (8 bytes per lane)
+        if (row >= rows) return;
+        // signed byte max with the native 16x2 SIMD max: a signed 16-bit compare is decided by its high byte, so
+        // max.s16x2 over the words gives the max of bytes 3 and 1, over the words shifted left by 8 that of bytes 2 and 0
+        uint32_t mo = 0x80008000u, me_ = 0x80008000u;
+#pragma unroll
+        for (int j = 0; j < MAXV; ++j) {
+            const uint32_t in[4] = {vv[j].x, vv[j].y, vv[j].z, vv[j].w};
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                mo = __vmaxs2(mo, in[u]);
+                me_ = __vmaxs2(me_, in[u] << 8);
             }
         }
-        int32_t mx = max(max((int32_t)(int8_t)(mxw & 0xff), (int32_t)(int8_t)((mxw >> 8) & 0xff)),
-                         max((int32_t)(int8_t)((mxw >> 16) & 0xff), (int32_t)(int8_t)(mxw >> 24)));
+        int32_t mx = max(max((int32_t)mo >> 24, (int32_t)(mo << 16) >> 24), max((int32_t)me_ >> 24, (int32_t)(me_ << 16) >> 24));
         mx = warp_max_i32(mx);
+        ln = __ldg(reinterpret_cast<const uint2*>(lut + (mx + 128) * 256) + lane);
+    };
+    // The warp's table line sits at a 256-byte aligned shared address and is stored permuted by 0x80, so that the RAW
+    // input byte is the index: the lookup address is one PRMT (byte k of the word | upper bytes of the base), the
+    // lookup one LDS.U8, and four results are merged by three PRMTs -- 3.25 instructions per element.
+    const uint32_t tl_base = (uint32_t)__cvta_generic_to_shared(&s_lut[w][0]);
+    auto stage_c = [&](int64_t row, const uint4 (&vv)[MAXV], const uint2& ln) {
+        if (row >= rows) return;
+        __syncwarp();                                            // the previous row's lookups are done
+        reinterpret_cast<uint2*>(s_lut[w])[lane ^ 16] = ln;      // entry (q + 128) -> index (q & 0xff)
         __syncwarp();
-        // this row's 256-byte table line -> shared memory (8 bytes per lane)
-        reinterpret_cast<uint2*>(s_lut[w])[lane] = __ldg(reinterpret_cast<const uint2*>(lut + (mx + 128) * 256) + lane);
-        __syncwarp();
-        const uint8_t* tl = s_lut[w];
         uint4* dst = reinterpret_cast<uint4*>(out + row * (int64_t)cols);
 #pragma unroll
         for (int j = 0; j < MAXV; ++j) {
             const int vi = lane + 32 * j;
             if (vi < nvec) {
-                uint32_t in[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
+                const uint32_t in[4] = {vv[j].x, vv[j].y, vv[j].z, vv[j].w};
                 uint32_t o[4];
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
-                    const uint32_t x = in[u] ^ 0x80808080u;       // q + 128 per byte
-                    o[u] = (uint32_t)tl[x & 0xff] | ((uint32_t)tl[(x >> 8) & 0xff] << 8) |
-                           ((uint32_t)tl[(x >> 16) & 0xff] << 16) | ((uint32_t)tl[x >> 24] << 24);
+                    uint32_t t[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        asm("ld.shared.u8 %0, [%1];" : "=r"(t[k]) : "r"(__byte_perm(in[u], tl_base, 0x7650 + k)));
+                    o[u] = __byte_perm(__byte_perm(t[0], t[1], 0x0040), __byte_perm(t[2], t[3], 0x0040), 0x5410);
                 }
                 dst[vi] = make_uint4(o[0], o[1], o[2], o[3]);
             }
         }
+    };
+    // rows of this warp: r_i = warp0 + i * nwarps.  Iteration i runs (a) on r_{i+2}, (b) on r_{i+1}, (c) on r_i;
+    // the loop is unrolled by three so that the register slots rotate statically.
+    stage_a(warp0, v[0]);
+    stage_a(warp0 + nwarps, v[1]);
+    stage_b(warp0, v[0], line[0]);
+    for (int64_t row = warp0; row < rows; row += 3 * nwarps) {
+        stage_a(row + 2 * nwarps, v[2]);
+        stage_b(row + nwarps, v[1], line[1]);
+        stage_c(row, v[0], line[0]);
+        stage_a(row + 3 * nwarps, v[0]);
+        stage_b(row + 2 * nwarps, v[2], line[2]);
+        stage_c(row + nwarps, v[1], line[1]);
+        stage_a(row + 4 * nwarps, v[1]);
+        stage_b(row + 3 * nwarps, v[0], line[0]);
+        stage_c(row + 2 * nwarps, v[2], line[2]);
     }
 }
 
@@ -107,11 +150,33 @@ __device__ __forceinline__ long long mad_wide_s32(int32_t a, int32_t b, long lon
     return r;
 }
 
+// dp2a with signed 16-bit halves of a and unsigned / signed bytes 0, 1 of b:  a.lo * b.b0 + a.hi * b.b1 + c
+__device__ __forceinline__ int32_t dp2a_lo_su(uint32_t a, uint32_t b, int32_t c) {
+    int32_t d;
+    asm("dp2a.lo.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+__device__ __forceinline__ int32_t dp2a_lo_ss(uint32_t a, uint32_t b, int32_t c) {
+    int32_t d;
+    asm("dp2a.lo.s32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+
 // LPR lanes per row (32 / LPR rows per warp), NV 16-byte vectors (8 channels) per lane, FULL: C == 8 * NV * LPR.
 // Everything that is per row (the two reductions, mean, integer sqrt, reciprocal factor) is computed redundantly by
 // the row's LPR lanes, so narrow rows-per-warp splits (LPR = 16 for C = 768) halve that overhead per row.
-template <int NV, int LPR, bool FULL>
-__global__ void __launch_bounds__(256)
+//
+// The row stays PACKED in registers (NV x 4 words of two int16) and is read in one statistics pass built on the
+// 16 x 8-bit dot product (IDP.2A), two channels per instruction and 32-bit accumulators only:
+//     sum = SUM x                       dp2a(w, {1, 1})
+//     ssq = SUM x^2 = 256 * SUM x*xh + SUM x*xl     x = 256*xh + xl, xh signed high byte, xl unsigned low byte:
+//                                       dp2a.s32.s32(w, {xh0, xh1}) and dp2a.s32.u32(w, {xl0, xl1}); |terms| < 2^23
+//     V   = SUM (x - mu)^2 = ssq - mu * (2 * sum - C * mu)          exact in 64 bits (|.| < 2^42)
+// and the second pass unpacks and centres in one instruction, y = dp2a(w, {1, 0} or {0, 1}, -mu).
+// PRE: the next pair of rows is loaded into a second register set before this pair's arithmetic (2 blocks per SM);
+// otherwise the kernel is compiled for MINB blocks per SM and relies on occupancy to cover the loads.
+template <int NV, int LPR, bool FULL, int MINB, bool PRE>
+__global__ void __launch_bounds__(256, MINB)
 layernorm_i16_i8_kernel(const int16_t* __restrict__ x, int64_t rows, int C, const int32_t* __restrict__ bias_int,
                         const ivit_dyadic_t* __restrict__ me, int8_t* __restrict__ out) {
     constexpr int RPW = 32 / LPR;                                // rows per warp
@@ -125,6 +190,19 @@ layernorm_i16_i8_kernel(const int16_t* __restrict__ x, int64_t rows, int C, cons
     //   RNE((floor(y*F/2) + b) * m / 2^e) == hi32(floor(y*F/2)*m + (b*m + 2^(e-1))) >> (e-32)
     __shared__ LnCol s_c[1024];
     __shared__ int32_t s_b[1024];
+    auto load_row = [&](int64_t rbase, uint4 (&w)[NV]) {
+        const int64_t row = rbase + rsel;
+        const uint4* src = reinterpret_cast<const uint4*>(x + (row < rows ? row : rows - 1) * (int64_t)C);
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+            const int vi = sub + LPR * j;
+            w[j] = make_uint4(0, 0, 0, 0);
+            if (FULL || vi < nvec) w[j] = __ldg(src + vi);
+        }
+    };
+    uint4 w[NV], wn[PRE ? NV : 1];
+    int64_t rbase = warp0 * RPW;
+    if (rbase < rows) load_row(rbase, w);                        // first rows in flight while the constants are staged
     int ok = 1;
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
         const int32_t b = bias_int[c];
@@ -140,45 +218,41 @@ layernorm_i16_i8_kernel(const int16_t* __restrict__ x, int64_t rows, int C, cons
         s_b[(c & 7) * nvec + (c >> 3)] = b;
     }
     const bool fast = __syncthreads_and(ok) != 0;
-    for (int64_t rbase = warp0 * RPW; rbase < rows; rbase += nwarps * RPW) {
+    const float inv_c = 1.0f / (float)C;
+    for (; rbase < rows; rbase += nwarps * RPW) {
         const int64_t row = rbase + rsel;
         const bool row_ok = row < rows;
-        const uint4* src = reinterpret_cast<const uint4*>(x + (row_ok ? row : rbase) * (int64_t)C);
-        int32_t y[NV][8];
+        const int64_t rnext = rbase + nwarps * RPW;
+        if constexpr (PRE) { if (rnext < rows) load_row(rnext, wn); }   // in flight during this pair's arithmetic
+        // ---- statistics over the packed row ----
         int32_t sum = 0;                                         // |sum| <= 1024 * 32768 < 2^31
+        int32_t sh = 0, sl = 0;                                  // SUM x*xh (|.| <= 128 ch * 2^22), SUM x*xl (<= 128 ch * 2^23)
 #pragma unroll
         for (int j = 0; j < NV; ++j) {
-            const int vi = sub + LPR * j;
-            uint4 t = make_uint4(0, 0, 0, 0);
-            if (FULL || vi < nvec) t = __ldg(src + vi);
-            const uint32_t tw[4] = {t.x, t.y, t.z, t.w};
+            const uint32_t tw[4] = {w[j].x, w[j].y, w[j].z, w[j].w};
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-                y[j][2 * u] = (int32_t)(int16_t)(tw[u] & 0xffff);
-                y[j][2 * u + 1] = (int32_t)tw[u] >> 16;
-                sum += y[j][2 * u] + y[j][2 * u + 1];
+                sum = dp2a_lo_ss(tw[u], 0x0101u, sum);
+                sh = dp2a_lo_ss(tw[u], __byte_perm(tw[u], 0u, 0x4431), sh);     // bytes {xh0, xh1}
+                sl = dp2a_lo_su(tw[u], __byte_perm(tw[u], 0u, 0x4420), sl);     // bytes {xl0, xl1}
             }
         }
+        long long ssq = (long long)sh * 256 + (long long)sl;
 #pragma unroll
-        for (int o = LPR / 2; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-        // mu = RNE(sum / C)
-        int32_t qd = sum / C, rem = sum - qd * C;
-        if (rem < 0) { qd -= 1; rem += C; }
+        for (int o = LPR / 2; o > 0; o >>= 1) {
+            sum += __shfl_xor_sync(0xffffffffu, sum, o);
+            ssq += __shfl_xor_sync(0xffffffffu, ssq, o);
+        }
+        // mu = RNE(sum / C): float estimate of the floor quotient + exact integer fix-up (|sum| < 2^26: estimate within 2)
+        int32_t qd = (int32_t)floorf((float)sum * inv_c), rem = sum - qd * C;
+#pragma unroll
+        for (int t = 0; t < 3; ++t) {
+            if (rem < 0) { qd -= 1; rem += C; }
+            if (rem >= C) { qd += 1; rem -= C; }
+        }
         if (2 * rem > C || (2 * rem == C && (qd & 1))) qd += 1;
         const int32_t mu = qd;
-        long long Vs = 0;
-#pragma unroll
-        for (int j = 0; j < NV; ++j) {
-            const bool okv = FULL || (sub + LPR * j) < nvec;
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const int32_t d = okv ? y[j][u] - mu : 0;
-                y[j][u] = d;
-                Vs = mad_wide_s32(d, d, Vs);
-            }
-        }
-#pragma unroll
-        for (int o = LPR / 2; o > 0; o >>= 1) Vs += __shfl_xor_sync(0xffffffffu, Vs, o);
+        const long long Vs = ssq - (long long)mu * (2LL * (long long)sum - (long long)C * (long long)mu);
         const unsigned long long k = ln_isqrt10((unsigned long long)Vs);
         const int32_t F = (int32_t)(k <= 0xffffffffULL ? (2147483647u / (uint32_t)k) : 0u);   // floor((2^31-1)/k), <= 2^31/64
         uint2* dst = reinterpret_cast<uint2*>(out + (row_ok ? row : rbase) * (int64_t)C);
@@ -186,21 +260,26 @@ layernorm_i16_i8_kernel(const int16_t* __restrict__ x, int64_t rows, int C, cons
         for (int j = 0; j < NV; ++j) {
             const int vi = sub + LPR * j;
             if ((FULL || vi < nvec) && row_ok) {
-                int32_t r[8];
+                const uint32_t tw[4] = {w[j].x, w[j].y, w[j].z, w[j].w};
+                int32_t r[8], z[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int32_t y = dp2a_lo_ss(tw[u >> 1], (u & 1) ? 0x0100u : 0x0001u, -mu);   // x - mu, |.| <= 65535
+                    z[u] = (int32_t)(mul_wide_s32(y, F) >> 1);                             // floor(y * F / 2), |.| <= 2^30
+                    asm("" : "+r"(z[u]));                                                  // a plain 32-bit value from here on
+                }
                 if (fast) {
 #pragma unroll
                     for (int u = 0; u < 8; ++u) {
                         const int4 pw = *reinterpret_cast<const int4*>(&s_c[u * nvec + vi]);   // one 16-byte load: {m, sh, c}
                         const long long pc = (long long)(((unsigned long long)(uint32_t)pw.w << 32) | (uint32_t)pw.z);
-                        int32_t z0 = (int32_t)(mul_wide_s32(y[j][u], F) >> 1);         // floor(y*F/2), |.| <= 2^30
-                        asm("" : "+r"(z0));                                            // a plain 32-bit value from here on
-                        r[u] = (int32_t)(((long long)z0 * (long long)pw.x + pc) >> 32) >> pw.y;   // IMAD.HI with 64-bit addend
+                        r[u] = (int32_t)(((long long)z[u] * (long long)pw.x + pc) >> 32) >> pw.y;   // IMAD.HI with 64-bit addend
                     }
                 } else {
 #pragma unroll
                     for (int u = 0; u < 8; ++u) {
                         const LnCol p = s_c[u * nvec + vi];
-                        long long o = (mul_wide_s32(y[j][u], F) >> 1) + (long long)s_b[u * nvec + vi];
+                        long long o = (long long)z[u] + (long long)s_b[u * nvec + vi];
                         o = o > 2147483647LL ? 2147483647LL : (o < -2147483648LL ? -2147483648LL : o);
                         r[u] = requant32_general((int32_t)o, p.m, p.sh + 32);
                     }
@@ -211,6 +290,14 @@ layernorm_i16_i8_kernel(const int16_t* __restrict__ x, int64_t rows, int C, cons
                 asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, %3;" : "=r"(lo) : "r"(r[7]), "r"(r[6]), "r"(0));
                 asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, %3;" : "=r"(w1) : "r"(r[5]), "r"(r[4]), "r"(lo));
                 dst[vi] = make_uint2(w0, w1);
+            }
+        }
+        if (rnext < rows) {
+            if constexpr (PRE) {
+#pragma unroll
+                for (int j = 0; j < NV; ++j) w[j] = wn[j];
+            } else {
+                load_row(rnext, w);
             }
         }
     }
@@ -337,9 +424,14 @@ int ivit_shiftgelu_lut(ivit_ctx* ctx, const int8_t* q, int64_t rows, int cols, c
     IVIT_REQUIRE(cols % 16 == 0 && cols <= 16 * 32 * 8, "ivit_shiftgelu_lut: cols must be a multiple of 16, <= 4096");
     IVIT_REQUIRE(((uintptr_t)q % 16) == 0 && ((uintptr_t)out % 16) == 0 && ((uintptr_t)lut % 8) == 0,
                  "ivit_shiftgelu_lut: q/out must be 16-byte aligned");
-    const int grid = (int)((rows + 7) / 8 < (int64_t)ctx->num_sms * 8 ? (rows + 7) / 8 : (int64_t)ctx->num_sms * 8);
     const int nv = (cols / 16 + 31) / 32;
-#define GL(MAXV) gelu_lut_apply_kernel<MAXV><<<grid, 256, 0, st(stream)>>>(q, rows, cols, lut, out)
+    // persistent grid: exactly the blocks that are resident at once (a partial second wave would run alone at the end)
+#define GL(MAXV) do {                                                                                                    \
+        static int bps = 0;                                                                                              \
+        if (!bps) IVIT_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, gelu_lut_apply_kernel<MAXV>, 256, 0)); \
+        const int64_t want = (rows + 7) / 8, cap = (int64_t)ctx->num_sms * (bps > 0 ? bps : 1);                          \
+        gelu_lut_apply_kernel<MAXV><<<(int)(want < cap ? want : cap), 256, 0, st(stream)>>>(q, rows, cols, lut, out);     \
+    } while (0)
     if (nv <= 2) GL(2); else if (nv <= 4) GL(4); else if (nv <= 6) GL(6); else GL(8);
 #undef GL
     IVIT_LAUNCH_OK("gelu_lut_apply_kernel");
@@ -384,13 +476,15 @@ int ivit_layernorm_i16_i8(ivit_ctx* ctx, const int16_t* x, int64_t rows, int C, 
     const int lpr = 16;
     const int rpb = 8 * (32 / lpr);                              // rows per 256-thread block and pass
     const int64_t want = (rows + rpb - 1) / rpb;
-    const int grid = (int)(want < (int64_t)ctx->num_sms * 4 ? want : (int64_t)ctx->num_sms * 4);
+    // persistent grid: two resident 256-thread blocks per SM (126 registers with the prefetched second register set)
+    const int grid = (int)(want < (int64_t)ctx->num_sms * 2 ? want : (int64_t)ctx->num_sms * 2);
     const int nv = (nvec + lpr - 1) / lpr;
     const bool full = (nv * lpr == nvec);
-#define LNF(NV, LPR) do { if (full) layernorm_i16_i8_kernel<NV, LPR, true><<<grid, 256, 0, st(stream)>>>(x, rows, C, bias_int, me, out); \
-                          else layernorm_i16_i8_kernel<NV, LPR, false><<<grid, 256, 0, st(stream)>>>(x, rows, C, bias_int, me, out); } while (0)
+#define LNK(NV, LPR, FULLV) layernorm_i16_i8_kernel<NV, LPR, FULLV, 2, true><<<grid, 256, 0, st(stream)>>>(x, rows, C, bias_int, me, out)
+#define LNF(NV, LPR) do { if (full) LNK(NV, LPR, true); else LNK(NV, LPR, false); } while (0)
     switch (nv) { case 1: LNF(1, 16); break; case 2: LNF(2, 16); break; case 3: LNF(3, 16); break; case 4: LNF(4, 16); break;
                   case 5: LNF(5, 16); break; case 6: LNF(6, 16); break; case 7: LNF(7, 16); break; default: LNF(8, 16); break; }
+#undef LNK
 #undef LNF
     IVIT_LAUNCH_OK("layernorm_i16_i8_kernel");
     return IVIT_OK;
