@@ -102,11 +102,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     uint32_t* sRedSum = reinterpret_cast<uint32_t*>(smem + ATC_SRED);            // [2][128]
     uint8_t* sRedMax = smem + ATC_SRED + 1024;                                   // [2][128]
     const uint32_t bar = base + ATC_BAR;
-    const uint32_t q_full = bar, k_full = bar + 8, s_full = bar + 16, p_ready = bar + 24, o_full = bar + 32, o_done = bar + 40;
-    volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + ATC_BAR + 48);
+    const uint32_t q_full = bar, k_full = bar + 8, s_full = bar + 16, p_ready = bar + 24, o_full = bar + 32, o_done = bar + 40, v_full = bar + 48;
+    volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + ATC_BAR + 56);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int b = blockIdx.x / p.H, h = blockIdx.x % p.H;
+    const int total = p.n_seq * p.H;                 // (image, head) work items; this CTA takes blockIdx.x, + gridDim.x, ...
     const int n_tok = p.n_tok;
     const int HD = p.H * 64;
     const int n_mt = (n_tok + 127) >> 7;
@@ -120,6 +120,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
         ptx::mbar_init(p_ready, 8);
         ptx::mbar_init(o_full, 1);
         ptx::mbar_init(o_done, 8);
+        ptx::mbar_init(v_full, 1);
         ptx::fence_barrier_init();
     }
     if (warp == 0) {
@@ -136,12 +137,14 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     const uint32_t idesc_s = ptx::umma_idesc_i8(128, 16 * NS16, 1, 1);
     const uint32_t idesc_pv = ptx::umma_idesc_i8(128, 64, 0, 1) | (1u << 16);   // A = unsigned byte planes of P; B (V) N-major
     const int nk32 = (n_tok + 31) >> 5;
-    if (tid == ATC_CTRL) {
-        ptx::mbar_arrive_expect_tx(k_full, 2 * 224 * 64);                       // K and V tiles (same box, keys >= n_tok read as zeros)
+    if (tid == ATC_CTRL && (int)blockIdx.x < total) {
+        const int b = (int)blockIdx.x / p.H, h = (int)blockIdx.x % p.H;
+        ptx::mbar_arrive_expect_tx(k_full, 224 * 64);                           // K tile (keys >= n_tok read as zeros)
         ptx::tma_load_3d(sK, &tmap_k, k_full, HD + h * 64, 0, b);
-        ptx::tma_load_3d(sVt, &tmap_k, k_full, 2 * HD + h * 64, 0, b);
         ptx::mbar_arrive_expect_tx(q_full, 128 * 64);
         ptx::tma_load_3d(sQ, &tmap_q, q_full, h * 64, 0, b);
+        ptx::mbar_arrive_expect_tx(v_full, 224 * 64);                           // V tile (same box)
+        ptx::tma_load_3d(sVt, &tmap_k, v_full, 2 * HD + h * 64, 0, b);
     }
     {
         // ================= softmax warps =================
@@ -169,12 +172,22 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
         const int npad = (half == (NCH1 > 0 ? 1 : 0)) ? npad_all : 0;   // ... which belongs to the upper half (if it has chunks)
         const uint32_t t_row = tmem_base + ((uint32_t)(lg * 32) << 16);
 
-        for (int mt = 0; mt < n_mt; ++mt) {
+        // Persistent CTA: the (image, head) items of this CTA are processed back to back.  The operands of the next
+        // item are requested as soon as their buffers are free -- Q and K right after the last score MMA of this item,
+        // V after its last P V MMA -- so that only the first item of a CTA waits for a memory round trip, and the
+        // barrier / TMEM / table set-up is paid once per CTA.  g counts m-tiles (barrier phases), it counts items.
+        uint32_t g = 0, it = 0;
+        for (int work = (int)blockIdx.x; work < total; work += (int)gridDim.x, ++it) {
+        const int b = work / p.H, h = work % p.H;
+        const int nwork = work + (int)gridDim.x;
+        const bool has_next = nwork < total;
+        const int nb = nwork / p.H, nh = nwork % p.H;
+        for (int mt = 0; mt < n_mt; ++mt, ++g) {
             const int row = mt * 128 + trow;
             if (tid == ATC_CTRL) {
-                if (mt > 0) mbar_wait_sleep(o_done, (uint32_t)((mt - 1) & 1), p.sleep_ns);   // TMEM columns are free again
-                mbar_wait_sleep(q_full, (uint32_t)(mt & 1), p.sleep_ns);
-                if (mt == 0) mbar_wait_sleep(k_full, 0, p.sleep_ns);
+                if (g > 0) mbar_wait_sleep(o_done, (g - 1u) & 1u, p.sleep_ns);   // TMEM columns are free again
+                mbar_wait_sleep(q_full, g & 1u, p.sleep_ns);
+                if (mt == 0) mbar_wait_sleep(k_full, it & 1u, p.sleep_ns);
                 ptx::tc_fence_after();
                 const uint64_t dq = umma_desc_k_sw64(sQ), dk = umma_desc_k_sw64(sK);
 #pragma unroll
@@ -183,17 +196,24 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
                 ptx::mma_commit(s_full);
             }
             __syncwarp();
-            mbar_wait_sleep(s_full, (uint32_t)(mt & 1), p.sleep_ns);
+            mbar_wait_sleep(s_full, g & 1u, p.sleep_ns);
             ptx::tc_fence_after();
-            if (tid == ATC_CTRL && mt + 1 < n_mt) {                 // the score MMAs have consumed the Q tile: fetch the next one now
-                ptx::mbar_arrive_expect_tx(q_full, 128 * 64);
-                ptx::tma_load_3d(sQ, &tmap_q, q_full, h * 64, (mt + 1) * 128, b);
+            if (tid == ATC_CTRL) {                                  // the score MMAs have consumed the Q tile: fetch the next one now
+                if (mt + 1 < n_mt) {
+                    ptx::mbar_arrive_expect_tx(q_full, 128 * 64);
+                    ptx::tma_load_3d(sQ, &tmap_q, q_full, h * 64, (mt + 1) * 128, b);
+                } else if (has_next) {                              // ... and, after the item's last score MMA, its K tile too
+                    ptx::mbar_arrive_expect_tx(q_full, 128 * 64);
+                    ptx::tma_load_3d(sQ, &tmap_q, q_full, nh * 64, 0, nb);
+                    ptx::mbar_arrive_expect_tx(k_full, 224 * 64);
+                    ptx::tma_load_3d(sK, &tmap_k, k_full, HD + nh * 64, 0, nb);
+                }
             }
             // my 32 rows of this m-tile lie past the sequence (upper lane groups of the last m-tile): nothing to compute, the
             // MMA reads whatever is in their P rows and nobody stores the result (both warps of a lane group agree)
             const bool act = (mt * 128 + lg * 32) < n_tok;
             if (act) {
-            // ---- pass 1: scores -> requant -> saturate to int8 -> stored as q + 128 (unsigned), four per register ----
+            // ---- pass 1: scores -> requant -> saturate to int8, four per register (signed bytes) ----
             uint32_t sc[NCH0 * 4];
 #pragma unroll
             for (int c = 0; c < NCH0; ++c) {
@@ -210,38 +230,47 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
                         uint32_t hi2, pk;
                         asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, %3;" : "=r"(hi2) : "r"(v[3]), "r"(v[2]), "r"(0));
                         asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, %3;" : "=r"(pk) : "r"(v[1]), "r"(v[0]), "r"(hi2));
-                        sc[4 * c + w] = pk ^ 0x80808080u;
+                        sc[4 * c + w] = pk;
                     }
                 } else {
 #pragma unroll
-                    for (int w = 0; w < 4; ++w) sc[4 * c + w] = 0u;
+                    for (int w = 0; w < 4; ++w) sc[4 * c + w] = 0x80808080u;
                 }
             }
-            // padding columns (all in the last chunk): forced to the smallest value so that they never raise the max;
-            // their exponentials are taken out of the sum below; their probabilities meet zero V rows
+            // padding columns (all in the last chunk): forced to the smallest value (-128) so that they never raise the
+            // max; their exponentials are taken out of the sum below; their probabilities meet zero V rows
             if (npad > 0) {
                 constexpr int CL = (NCH1 > 0 ? NCH1 : NCH0) - 1;                         // my last chunk (static index)
 #pragma unroll
                 for (int w = 0; w < 4; ++w) {
                     const int valid = 16 - npad_all - 4 * w;                             // columns of this word that exist
                     const uint32_t keep = valid >= 4 ? 0xffffffffu : (valid <= 0 ? 0u : (0xffffffffu >> (8 * (4 - valid))));
-                    sc[4 * CL + w] &= keep;
+                    sc[4 * CL + w] = (sc[4 * CL + w] & keep) | (0x80808080u & ~keep);
                 }
             }
-            uint32_t mxw = 0u;
+            // row max of my columns with the native 16x2 SIMD max: a signed 16-bit compare is decided by its high byte, so
+            // max.s16x2 over the words covers bytes 3 and 1, over the words shifted left by 8 bytes 2 and 0 (the byte-wise
+            // __vmaxu4 is emulated: seven dependent instructions per word)
+            uint32_t mo = 0x80008000u, me2 = 0x80008000u;
 #pragma unroll
-            for (int i = 0; i < NCH0 * 4; ++i) mxw = __vmaxu4(mxw, sc[i]);
-            mxw = __vmaxu4(mxw, mxw >> 16);
-            uint32_t mxu = max(mxw & 0xffu, (mxw >> 8) & 0xffu);                        // row max of q + 128 over my columns
+            for (int i = 0; i < NCH0 * 4; ++i) {
+                mo = __vmaxs2(mo, sc[i]);
+                me2 = __vmaxs2(me2, sc[i] << 8);
+            }
+            const int32_t mxs = max(max((int32_t)mo >> 24, (int32_t)(mo << 16) >> 24), max((int32_t)me2 >> 24, (int32_t)(me2 << 16) >> 24));
+            uint32_t mxu = (uint32_t)(mxs + 128);                                       // row max of q + 128 over my columns
             sRedMax[half * 128 + trow] = (uint8_t)mxu;
             asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
             mxu = max(mxu, (uint32_t)sRedMax[(half ^ 1) * 128 + trow]);
-            // ---- pass 2: exponentials E(max - q) = sE[mxu - u], row sum (E < 2^23, <= 112 terms per thread: 32-bit) ----
-            const uint32_t pEb = ptx::smem_u32(sE) + (uint32_t)(4 * ATC_LUTC) * mxu + 4u * ((uint32_t)lane & (ATC_LUTC - 1));
+            // ---- pass 2: exponentials E(max - q) = sE[max - q], row sum (E < 2^23, <= 112 terms per thread: 32-bit) ----
+            // lookup address = table + 32 * (max - q) + 4 * copy: ONE dot-product instruction per element (IDP.4A on the
+            // FMA pipe; the selector holds -32 in byte i) instead of a byte extract plus a multiply-add
+            const int32_t pEq = (int32_t)(ptx::smem_u32(sE) + (uint32_t)(4 * ATC_LUTC) * (mxu - 128u) + 4u * ((uint32_t)lane & (ATC_LUTC - 1)));
             auto lut = [&](uint32_t u, int i) -> uint32_t {
-                const uint32_t byte = __byte_perm(u, 0u, 0x4440 + i);
+                int32_t addr;
+                asm("dp4a.s32.s32 %0, %1, %2, %3;" : "=r"(addr) : "r"(u), "r"((uint32_t)(0x100 - 4 * ATC_LUTC) << (8 * i)), "r"(pEq));
                 uint32_t v;
-                asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(pEb - (uint32_t)(4 * ATC_LUTC) * byte));   // read-only table: free to schedule
+                asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));   // read-only table: free to schedule
                 return v;
             };
             uint32_t sum = 0;
@@ -255,7 +284,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
                     }
                 }
             }
-            sum -= (uint32_t)npad * lut(0u, 0);                                          // padding columns carry u = 0
+            sum -= (uint32_t)npad * lut(0x80808080u, 0);                                 // padding columns carry q = -128
             sRedSum[half * 128 + trow] = sum;
             asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
             unsigned long long S = (unsigned long long)sum + sRedSum[(half ^ 1) * 128 + trow];
@@ -271,10 +300,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
 #pragma unroll
                     for (int w = 0; w < 4; ++w) {
                         const uint32_t u = sc[4 * c + w];
-                        const uint32_t P0 = __umulhi(lut(u, 0), Fs), P1 = __umulhi(lut(u, 1), Fs);
-                        const uint32_t P2 = __umulhi(lut(u, 2), Fs), P3 = __umulhi(lut(u, 3), Fs);
-                        lo[w] = __byte_perm(__byte_perm(P0, P1, 0x0040), __byte_perm(P2, P3, 0x0040), 0x5410);
-                        hi[w] = __byte_perm(__byte_perm(P0, P1, 0x0051), __byte_perm(P2, P3, 0x0051), 0x5410);
+                        // P < 2^16: two of them share a word through one multiply-add (FMA pipe), then one byte
+                        // permute per plane
+                        const uint32_t P01 = __umulhi(lut(u, 1), Fs) * 65536u + __umulhi(lut(u, 0), Fs);
+                        const uint32_t P23 = __umulhi(lut(u, 3), Fs) * 65536u + __umulhi(lut(u, 2), Fs);
+                        lo[w] = __byte_perm(P01, P23, 0x6420);
+                        hi[w] = __byte_perm(P01, P23, 0x7531);
                     }
                     const int key0 = c_begin + 16 * c;                          // 16 keys = one 16-byte chunk of my row
                     const uint32_t off = (uint32_t)((key0 >> 7) * 16384) + (uint32_t)trow * 128u +
@@ -290,7 +321,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
             if (lane == 0) ptx::mbar_arrive(p_ready);
             if (tid == ATC_CTRL) {
                 // probabilities are in shared memory; every S column has been read
-                mbar_wait_sleep(p_ready, (uint32_t)(mt & 1), p.sleep_ns);
+                mbar_wait_sleep(p_ready, g & 1u, p.sleep_ns);
+                if (mt == 0) mbar_wait_sleep(v_full, it & 1u, p.sleep_ns);
                 ptx::tc_fence_after();
 #pragma unroll 1
                 for (int plane = 0; plane < 2; ++plane) {                       // 0: high bytes -> cols [0,64), 1: low -> [64,128)
@@ -305,8 +337,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
             }
             __syncwarp();
             // ---- output rows: (O_hi << 8) + O_lo -> attn.qact2 -> int8 ----
-            mbar_wait_sleep(o_full, (uint32_t)(mt & 1), p.sleep_ns);
+            mbar_wait_sleep(o_full, g & 1u, p.sleep_ns);
             ptx::tc_fence_after();
+            if (tid == ATC_CTRL && mt + 1 == n_mt && has_next) {    // the item's last P V MMA has read V: next item's V
+                ptx::mbar_arrive_expect_tx(v_full, 224 * 64);
+                ptx::tma_load_3d(sVt, &tmap_k, v_full, 2 * HD + nh * 64, 0, nb);
+            }
             uint4* dst = reinterpret_cast<uint4*>(out + ((long long)b * n_tok + row) * (long long)HD + h * 64 + 32 * half);
             if (!act) {
                 __syncwarp();
@@ -339,6 +375,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
                 }
                 if (row < n_tok) dst[q] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
             }
+        }
         }
     }
     ptx::tc_fence_before();
@@ -387,7 +424,8 @@ int launch_attention_tc(ivit_ctx* ctx, const int8_t* qkv, const ivit_attn_params
     if (rc) return rc;
     rc = make_tmap_qkv(ctx, &tk, qkv, ap->n_seq, ap->n_tok, ld, 224);
     if (rc) return rc;
-    const int grid = ap->n_seq * ap->n_heads;
+    const int items = ap->n_seq * ap->n_heads;
+    const int grid = items < 2 * ctx->num_sms ? items : 2 * ctx->num_sms;       // persistent: two resident CTAs per SM
 #define ATC_CASE(N)                                                                                                   \
     case N: {                                                                                                         \
         static bool attr_set = false;                                                                                 \
