@@ -47,10 +47,15 @@ struct ScalarRq {
     long long half;
     int kind;                         // 0 general, 1 unified form
     int tie;                          // unified form needs the tie-to-even correction
+    // fixed-shift form for 16 <= e <= 47 (|z| < 2^15):  q = hi32((z << 16) * m + 2^(e+15)) >> (e - 16).  The operand
+    // shifted left by 16 is what a packed pair of int16 gives for free (high half: mask, low half: one shift).
+    int32_t rs16;
+    long long half16;
 };
 static ScalarRq make_scalar_rq(ivit_dyadic_t d) {
     ScalarRq r;
-    r.m = d.m; r.e = d.e; r.ls = 0; r.rs = 0; r.himask = 0; r.half = 0; r.kind = 0; r.tie = 0;
+    r.m = d.m; r.e = d.e; r.ls = 0; r.rs = 0; r.himask = 0; r.half = 0; r.kind = 0; r.tie = 0; r.rs16 = 0; r.half16 = 0;
+    if (d.e >= 16 && d.e <= 47) { r.rs16 = d.e - 16; r.half16 = 1LL << (d.e + 15); }
     if (d.m != 0 && d.e >= 16 && d.e <= 62) {
         r.kind = 1;
         if (d.e < 32) { r.ls = 32 - d.e; r.rs = 0; r.half = 1LL << 31; }
@@ -90,6 +95,7 @@ struct GemmArgs {
     int acc_bits;                     // |acc + bias| < 2^acc_bits (tie analysis of the per-column requant)
     int scalar_mode;                  // 1: rq2/rqr unified form, no ties; 2: unified with tie correction; 0: general;
                                       // 3: mode 1 with both stages present and a wrap-free 32-bit sum (straight-line)
+                                      // 4: mode 3 with both exponents <= 47 (fixed-shift form on packed int16 pairs)
     const float* scale;
     void* out;
     long long out_ld;
@@ -264,7 +270,22 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&r)[CW], const ui
     auto resid = [&](int j) -> int32_t {
         return (j & 1) ? ((int32_t)rr[j >> 1] >> 16) : (int32_t)(int16_t)(rr[j >> 1] & 0xffff);
     };
-    if (args.scalar_mode == 3) {
+    if (args.scalar_mode == 4) {
+        // scalar_mode 3 with both exponents <= 47: the 16-bit clamp of the first stage is the saturating pack of two
+        // results into one word, and both that word and the packed residual word yield their operands already shifted
+        // left by 16 with one instruction each (mask / shift) -- 11 instead of 14 instructions per element.
+#pragma unroll
+        for (int j = 0; j < CW; j += 2) {
+            const uint32_t d = pack_sat_s16x2(q[j], q[j + 1]);
+            const uint32_t w = rr[j >> 1];
+            const int32_t zl = (int32_t)(d << 16), zh = (int32_t)(d & 0xffff0000u);
+            const int32_t rl = (int32_t)(w << 16), rh = (int32_t)(w & 0xffff0000u);
+            q[j] = ((int32_t)(((long long)zl * (long long)args.rq2.m + args.rq2.half16) >> 32) >> args.rq2.rs16) +
+                   ((int32_t)(((long long)rl * (long long)args.rqr.m + args.rqr.half16) >> 32) >> args.rqr.rs16);
+            q[j + 1] = ((int32_t)(((long long)zh * (long long)args.rq2.m + args.rq2.half16) >> 32) >> args.rq2.rs16) +
+                       ((int32_t)(((long long)rh * (long long)args.rqr.m + args.rqr.half16) >> 32) >> args.rqr.rs16);
+        }
+    } else if (args.scalar_mode == 3) {
         // the residual-block epilogue of the models (attn.proj / mlp.fc2): two-stage + residual, both scalar dyadics in
         // unified form without reachable ties, and |each term| < 2^30 so that the 32-bit sum cannot wrap (host-checked).
         // One straight-line block per chunk: no per-element conditions, the compiler interleaves the 16 chains.
@@ -901,6 +922,8 @@ extern "C" int ivit_gemm_i8(ivit_ctx* ctx, const int8_t* A, int64_t lda, const i
         ga.scalar_mode = !uni ? 0 : (tie ? 2 : 1);
         // |RNE(z*m/2^e)| <= 2^15 * 2^31 / 2^e + 1 < 2^30 for e >= 18: the sum of the two terms fits 32 bits
         if (ga.scalar_mode == 1 && use2 && user && ga.rq2.e >= 18 && ga.rqr.e >= 18) ga.scalar_mode = 3;
+        static const char* sm_env = getenv("IVIT_GEMM_SM4");
+        if (ga.scalar_mode == 3 && ga.rq2.e <= 47 && ga.rqr.e <= 47 && !(sm_env && atoi(sm_env) == 0)) ga.scalar_mode = 4;
     }
     ga.scale = epi->scale; ga.out = out; ga.out_ld = epi->out_ld;
     ga.res_async = (epi->residual && ((uintptr_t)epi->residual % 16) == 0 && epi->res_ld % 8 == 0) ? 1 : 0;

@@ -300,6 +300,29 @@ def test_gemm_requant_i16(K, M, N, K_, variant):
     assert_equal(got, want, "gemm rq16 %s acc_bits %dx%dx%d" % (variant, M, N, K_))
 
 
+@pytest.mark.parametrize("e2,e1", [(18, 47), (24, 31), (31, 32), (32, 18), (40, 40), (47, 24), (48, 33), (33, 55)])
+def test_gemm_two_stage_exponent_sweep(K, e2, e1):
+    """Residual-block epilogue (attn.proj / mlp.fc2: two-stage requant + int16 residual) over the exponent range of
+    the scalar dyadics: e <= 47 takes the fixed-shift form on packed int16 pairs, larger e the unified form; the first
+    stage saturates at +-32768 on part of the tile and the residual includes the int16 extremes."""
+    M, N, K_ = 700, 512, 256
+    rng = np.random.default_rng(1000 * e2 + e1)
+    a, w, b = gemm_inputs(rng, M, N, K_)
+    m, e = rand_me(rng, N, 33, 38, neg_every=7)
+    e[: N // 4] = 32                                      # large first-stage results: the 16-bit clamp is active
+    acc = ref_acc(a, w, b)
+    res = rng.integers(-32768, 32768, (M, N)).astype(np.int16)
+    res[0, :8] = [-32768, 32767, -32768, 32767, 0, 1, -1, 12345]
+    m2 = np.array([rng.integers(2 ** 30, 2 ** 31) | 1], np.int64)       # odd multipliers: no reachable ties
+    m1 = np.array([-(rng.integers(2 ** 30, 2 ** 31) | 1)], np.int64)
+    q1 = O.requant(acc, m, e, 16)
+    assert (np.abs(q1) >= 32767).any()
+    want = O.requant(q1, m2, np.array([e2]), 16, res, m1, np.array([e1]))
+    got = K.gemm_i8(dev(a), dev(w), bias=dev(b), mode="requant", me=me_dev(K, m, e), bits=16, residual=dev(res),
+                    res_me=(int(m1[0]), e1), two_stage=True, me2=(int(m2[0]), e2))
+    assert_equal(got, want, "gemm two-stage e2=%d e1=%d" % (e2, e1))
+
+
 def test_gemm_strided_a_and_out(K):
     # A as a column slice of a wider buffer (lda > K), out into a wider buffer
     rng = np.random.default_rng(77)
