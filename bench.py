@@ -54,41 +54,55 @@ def gemm_shapes(meta, B):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    """nvidia-smi clocks / throttle reasons while the GPU is under the benchmark's load (B200_PROFILING.md): one
+    streaming `nvidia-smi -lms 50` process, read by a thread, from the warm-up to the end of the timed regions."""
 
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index: int):
-        self.index, self.samples, self._stop = index, [], threading.Event()
+        self.index, self.samples, self.proc = index, [], None
         self.thread = threading.Thread(target=self._run, daemon=True)
 
     def _run(self):
-        while not self._stop.is_set():
-            try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.samples.append([x.strip() for x in out.split(",")])
-            except Exception:
-                pass
-            self._stop.wait(0.2)
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                line = line.strip()
+                if line:
+                    self.samples.append([x.strip() for x in line.split(",")])
+        except Exception:
+            pass
 
     def __enter__(self):
         self.thread.start()
         return self
 
     def __exit__(self, *a):
-        self._stop.set()
+        try:
+            if self.proc is not None:
+                self.proc.terminate()                      # the exact process started above
+        except Exception:
+            pass
         self.thread.join(timeout=3)
 
     def summary(self):
         sm = [float(s[0]) for s in self.samples if s and s[0].replace(".", "").isdigit()]
         mx = [float(s[1]) for s in self.samples if len(s) > 1 and s[1].replace(".", "").isdigit()]
+        pw = [float(s[2]) for s in self.samples if len(s) > 2 and s[2].replace(".", "").isdigit()]
+        # "under load": samples whose power draw is above the midpoint between idle and the maximum seen
+        if pw and len(pw) == len(sm) and max(pw) > 1.3 * min(pw):
+            thr = 0.5 * (max(pw) + min(pw))
+            load = [c for c, w in zip(sm, pw) if w >= thr] or sm
+        else:
+            load = sm
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = sorted({names[i] for s in self.samples if len(s) >= 7 for i in range(4) if s[3 + i].lower().startswith("active")})
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(self.samples)}
+        return {"sm_mhz": float(np.median(load)) if load else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(self.samples), "samples_under_load": len(load),
+                "power_w_max": max(pw) if pw else None}
 
 
 def measured_peaks():
@@ -261,14 +275,14 @@ def run_ours(args, rank, world, local_rank):
         out_host.copy_(logits, non_blocking=True)
         state["i"] += 1
 
-    for _ in range(max(args.warmup, 3)):
-        step_resident()
-    with ClockSampler(local_rank) as clk:
+    with ClockSampler(local_rank) as clk:                  # sampled from the warm-up to the end of both timed regions
+        for _ in range(max(args.warmup, 3)):
+            step_resident()
         total_ms = timed(step_resident, args.steps)
+        for _ in range(2):
+            step_e2e()
+        e2e_ms = timed(step_e2e, args.steps)
     clocks = clk.summary()
-    for _ in range(2):
-        step_e2e()
-    e2e_ms = timed(step_e2e, args.steps)
 
     ms_step = total_ms / args.steps
     value = world * B / (ms_step * 1e-3)
@@ -276,7 +290,23 @@ def run_ours(args, rank, world, local_rank):
     if rank != 0:
         return
     peaks, peak_src = measured_peaks()
-    gem = time_gemms(eng, B)
+    # dominant kernel: every tcgen05 GEMM launch of the step timed in place (CUDA events on the launching stream around
+    # each launch of eager forwards), grouped by shape; the isolated L2-warm timing of time_gemms() is kept beside it
+    per_launch = eng.time_gemms(x, forwards=3)
+    groups = {}
+    for name, M_, N_, K_, ms in per_launch:
+        key = "head" if name == "head" else name.split(".")[-1] if name.startswith("blocks.") else "patch_embed"
+        g_ = groups.setdefault(key, {"name": key, "M": M_, "N": N_, "K": K_, "launches": 0, "ms": 0.0})
+        g_["launches"] += 1
+        g_["ms"] += ms
+    gem = []
+    for g_ in groups.values():
+        g_["ms"] /= g_["launches"]
+        g_["tops"] = 2.0 * g_["M"] * g_["N"] * g_["K"] / (g_["ms"] * 1e-3) / 1e12
+        gem.append(g_)
+    iso = {g_["name"]: g_["ms"] for g_ in time_gemms(eng, B)}
+    for g_ in gem:
+        g_["ms_isolated_l2_warm"] = iso.get(g_["name"])
     ops = sum(2.0 * g_["M"] * g_["N"] * g_["K"] * g_["launches"] for g_ in gem)
     gms = sum(g_["ms"] * g_["launches"] for g_ in gem)
     achieved = ops / (gms * 1e-3) / 1e12
@@ -309,6 +339,7 @@ def run_ours(args, rank, world, local_rank):
                        "int_ops_per_image": int_ops_per_image(eng.meta)},
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                          "traffic": ncu_traffic("gemm_i8_tcgen05_kernel")[0], "traffic_source": ncu_traffic("gemm_i8_tcgen05_kernel")[1],
+                         "timing": "CUDA events around each GEMM launch inside eager forwards (operands as produced by the preceding kernels)",
                          "algorithmic_bytes_per_launch": sum((g_["M"] * g_["K"] + g_["N"] * g_["K"] + g_["M"] * g_["N"] * (1 if g_["name"] in ("qkv", "fc1") else 4))
                                                              * g_["launches"] for g_ in gem) / sum(g_["launches"] for g_ in gem), "kernel": "gemm_i8_tcgen05_kernel (all %d GEMM launches of the step)" % sum(g_["launches"] for g_ in gem),
                          "peak_source": "2 x bf16_tflops_sustained of MEASURED_PEAKS.json (%s); int8 tensor rate = 2 x bf16" % peak_src,

@@ -214,13 +214,16 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
             const bool act = (mt * 128 + lg * 32) < n_tok;
             if (act) {
             // ---- pass 1: scores -> requant -> saturate to int8, four per register (signed bytes) ----
+            // (the TMEM load of chunk c+1 is in flight while chunk c is requantised)
             uint32_t sc[NCH0 * 4];
+            uint32_t rbuf[2][16];
+            ptx::tmem_ld_32x32b_x16(t_row + (uint32_t)c_begin, rbuf[0]);
 #pragma unroll
             for (int c = 0; c < NCH0; ++c) {
                 if (c < nch) {
-                    uint32_t r[16];
-                    ptx::tmem_ld_32x32b_x16(t_row + (uint32_t)(c_begin + 16 * c), r);
+                    uint32_t (&r)[16] = rbuf[c & 1];
                     ptx::tmem_ld_wait();
+                    if (c + 1 < nch) ptx::tmem_ld_32x32b_x16(t_row + (uint32_t)(c_begin + 16 * (c + 1)), rbuf[(c + 1) & 1]);
 #pragma unroll
                     for (int w = 0; w < 4; ++w) {
                         int32_t v[4];

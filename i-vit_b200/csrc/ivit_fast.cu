@@ -333,6 +333,44 @@ __global__ void quantize_patchify_kernel(const float4* __restrict__ img, const f
     }
 }
 
+// 16 x 16 patches (DeiT/ViT): one thread per (image, channel, row pair, patch column) = 2 x 16 pixels.  The two pixel
+// rows of a patch are adjacent in the unfolded row ((c*16 + y%16)*16 + x%16), so the thread reads 2 x 64 contiguous
+// bytes and writes ONE aligned 32-byte sector; consecutive lanes take consecutive patch columns of the same image
+// rows, i.e. a warp reads whole image rows (the 4-pixel form wrote 4-byte pieces, half-empty sectors: 78 us -> 2.5 TB/s).
+__global__ void __launch_bounds__(256)
+quantize_patchify16_kernel(const float4* __restrict__ img, const float* __restrict__ scale, int B, int Cin, int H, int W,
+                           int8_t* __restrict__ out) {
+    const float inv = __fdiv_rn(1.0f, scale[0]);
+    const int Wp = W >> 4, Hp = H >> 4, H2 = H >> 1, W4 = W >> 2, K = Cin * 256;
+    const int64_t n = (int64_t)B * Cin * H2 * Wp;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int px = (int)(i % Wp);
+        int64_t r = i / Wp;
+        const int y = 2 * (int)(r % H2); r /= H2;
+        const int c = (int)(r % Cin);
+        const int64_t b = r / Cin;
+        const float4* src = img + ((b * Cin + c) * H + y) * (int64_t)W4 + px * 4;
+        float4 v[8];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { v[j] = __ldg(src + j); v[4 + j] = __ldg(src + W4 + j); }
+        uint32_t o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int32_t q0 = __float2int_rn(fminf(fmaxf(__fmul_rn(inv, v[j].x), -128.f), 127.f));
+            const int32_t q1 = __float2int_rn(fminf(fmaxf(__fmul_rn(inv, v[j].y), -128.f), 127.f));
+            const int32_t q2 = __float2int_rn(fminf(fmaxf(__fmul_rn(inv, v[j].z), -128.f), 127.f));
+            const int32_t q3 = __float2int_rn(fminf(fmaxf(__fmul_rn(inv, v[j].w), -128.f), 127.f));
+            uint32_t hi;
+            asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, %3;" : "=r"(hi) : "r"(q3), "r"(q2), "r"(0));
+            asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, %3;" : "=r"(o[j]) : "r"(q1), "r"(q0), "r"(hi));
+        }
+        const int64_t row = (b * Hp + (y >> 4)) * Wp + px;
+        uint4* dst = reinterpret_cast<uint4*>(out + row * (int64_t)K + (c * 16 + (y & 15)) * 16);
+        dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
+        dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
+    }
+}
+
 // ------------------------------------------------------------------------------------
 // Stem: cls-token concatenation + position-embedding residual QuantAct (vit_quant.py:259-265), 8 channels per
 // thread, scalar dyadics analysed on the host (same unified form as the GEMM epilogue's second stage).
@@ -443,6 +481,14 @@ int ivit_quantize_patchify(ivit_ctx* ctx, const float* img, const float* scale, 
     IVIT_REQUIRE(ctx && img && scale && out && B > 0 && Cin > 0 && p > 0, "ivit_quantize_patchify: bad arguments");
     IVIT_REQUIRE(H % p == 0 && W % p == 0 && p % 4 == 0 && W % 4 == 0, "ivit_quantize_patchify: H, W multiples of the patch size, patch % 4 == 0");
     IVIT_REQUIRE(((uintptr_t)img % 16) == 0 && ((uintptr_t)out % 4) == 0, "ivit_quantize_patchify: img must be 16-byte aligned");
+    if (p == 16 && ((uintptr_t)out % 16) == 0) {
+        const int64_t n = (int64_t)B * Cin * (H / 2) * (W / 16);
+        const int64_t blocks = (n + 255) / 256;
+        const int grid = (int)(blocks < (int64_t)ctx->num_sms * 8 ? blocks : (int64_t)ctx->num_sms * 8);
+        quantize_patchify16_kernel<<<grid, 256, 0, st(stream)>>>((const float4*)img, scale, B, Cin, H, W, out);
+        IVIT_LAUNCH_OK("quantize_patchify16_kernel");
+        return IVIT_OK;
+    }
     const int64_t n4 = (int64_t)B * Cin * H * (W / 4);
     const int64_t blocks = (n4 + 255) / 256;
     const int grid = (int)(blocks < (int64_t)ctx->num_sms * 16 ? blocks : (int64_t)ctx->num_sms * 16);

@@ -57,6 +57,7 @@ class Engine:
                 bound = int(v.shape[1]) * 128 * 128 + int(np.abs(pack.arrays[name + ".bias_integer"].astype(np.int64)).max()) + 1
                 self.acc_bits[name] = min(31, int(bound).bit_length())
         self._plans = {}
+        self._gemm_events = None
         self.launches_per_forward = 0
 
     # ------------------------------------------------------------------ parameter transport
@@ -96,8 +97,16 @@ class Engine:
             kw = {}
             if stage2 is not None:                                   # per-channel QuantAct, then residual QuantAct
                 kw = dict(two_stage=True, me2=s[stage2 + ".me"], residual=residual, res_me=s[stage2 + ".me_res"])
+            ev = self._gemm_events
+            if ev is not None:                                       # bench.py: CUDA events around every GEMM of an eager forward
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
             K.gemm_i8(a, t[name + ".weight_integer"], bias=t[name + ".bias_integer"], mode="requant",
                       me=t[me_key + ".me"], bits=bits, out=out, acc_bits=self.acc_bits[name], **kw)
+            if ev is not None:
+                e1.record()
+                w = t[name + ".weight_integer"]
+                ev.append((name, a.shape[0], w.shape[0], w.shape[1], e0, e1))
 
         # input quantisation (vit_quant.py:257) -> patch unfold -> patch-embedding GEMM (+patch_embed.qact, 16 bit)
         if taps is None and m["patch"] % 4 == 0:
@@ -183,6 +192,27 @@ class Engine:
         return plan["buf"]["logits"]
 
     __call__ = forward
+
+    @torch.no_grad()
+    def time_gemms(self, images: torch.Tensor, forwards: int = 3):
+        """Eager (un-graphed) forwards with a CUDA event pair around every tcgen05 GEMM launch of the step, on the
+        launching stream: the kernels see the operands exactly as in the real forward (produced by the preceding
+        kernel, residuals several kernels old).  Returns [(name, M, N, K, ms)] averaged over `forwards` runs."""
+        B = images.shape[0]
+        b = self._plan(B)["buf"]
+        b["img"].copy_(images)
+        self._run(b, B)                                   # warm-up
+        acc = {}
+        for _ in range(forwards):
+            self._gemm_events = []
+            self._run(b, B)
+            torch.cuda.synchronize(self.device)
+            for name, M, N, Kd, e0, e1 in self._gemm_events:
+                a = acc.setdefault(name, [M, N, Kd, 0.0, 0])
+                a[3] += e0.elapsed_time(e1)
+                a[4] += 1
+            self._gemm_events = None
+        return [(k, v[0], v[1], v[2], v[3] / v[4]) for k, v in acc.items()]
 
     @torch.no_grad()
     def forward_taps(self, images: torch.Tensor) -> dict:
