@@ -100,7 +100,8 @@ struct GemmArgs {
     void* out;
     long long out_ld;
     int res_async;                    // residual rows are 16-byte aligned: prefetched into the staging tile with cp.async
-    int debug;                        // IVIT_GEMM_DEBUG diagnostics (wrong results): 1 epilogue does no work, 2 producer loads nothing
+    int debug;                        // IVIT_GEMM_DEBUG diagnostics (wrong results): 1 epilogue does no work, 2 producer loads nothing,
+                                      // 4 residual reads as zero (no global loads), 8 no TMA store of the output
 };
 
 struct alignas(16) ColParam {         // per output column, staged in shared memory per tile
@@ -136,7 +137,7 @@ template <int CW>
 __device__ __forceinline__ void load_residual(const GemmArgs& args, int row, bool row_ok, int ncol0, uint32_t (&rr)[CW / 2]) {
 #pragma unroll
     for (int j = 0; j < CW / 2; ++j) rr[j] = 0u;
-    if (!args.residual || !row_ok || ncol0 >= args.N) return;
+    if (!args.residual || !row_ok || ncol0 >= args.N || (args.debug & 4)) return;   // debug & 4: diagnostics, residual reads as zero
     const int16_t* res = reinterpret_cast<const int16_t*>(args.residual) + (long long)row * args.res_ld + ncol0;
     if (ncol0 + CW <= args.N && ((reinterpret_cast<uintptr_t>(res) & 15) == 0)) {
 #pragma unroll
@@ -698,7 +699,7 @@ gemm_i8_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
                 // (32-row boxes; coalesced, asynchronous, clips the M / N tails).  Each warp stores and later waits
                 // for its own rows only, one tile later: no CTA-wide synchronisation around the store.
                 if (NBOX_W == 0) asm volatile("bar.sync %0, 64;" ::"r"(box_bar) : "memory");
-                if (lane == 0 && box_leader) {
+                if (lane == 0 && box_leader && !(args.debug & 8)) {      // debug & 8: diagnostics, nothing is stored
                     const int r0 = m0 + lane_group * 32;
                     constexpr int NB = NBOX_W > 0 ? NBOX_W : 1;
 #pragma unroll

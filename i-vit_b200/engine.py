@@ -84,8 +84,9 @@ class Engine:
             logits=e(B, m["num_classes"], dtype=torch.float32))
 
     # ------------------------------------------------------------------ the launch sequence
-    def _run(self, b, B: int, taps: dict = None):
+    def _run(self, b, B: int, taps: dict = None, img: torch.Tensor = None):
         m, t, s = self.meta, self.t, self.s
+        img = b["img"] if img is None else img
         C, N, H, D = m["embed_dim"], m["n_tok"], m["num_heads"], m["head_dim"]
         n = 0
 
@@ -110,9 +111,9 @@ class Engine:
 
         # input quantisation (vit_quant.py:257) -> patch unfold -> patch-embedding GEMM (+patch_embed.qact, 16 bit)
         if taps is None and m["patch"] % 4 == 0:
-            K.quantize_patchify(b["img"], t["qact_input.scale"], m["patch"], out=b["patches"]); n += 1   # one fused pass
+            K.quantize_patchify(img, t["qact_input.scale"], m["patch"], out=b["patches"]); n += 1   # one fused pass
         else:
-            _quantize_into(b["img"], t["qact_input.scale"], b["img_q"]); n += 1
+            _quantize_into(img, t["qact_input.scale"], b["img_q"]); n += 1
             tap("qact_input", b["img_q"])
             K.call("ivit_patchify_i8", K.context(self.device), K.ptr(b["img_q"]), B, m["in_chans"], m["img_size"],
                    m["img_size"], m["patch"], K.ptr(b["patches"])); n += 1
@@ -157,22 +158,25 @@ class Engine:
         return b["logits"]
 
     # ------------------------------------------------------------------ public API
+    def _capture(self, b, B: int, img: torch.Tensor = None):
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(side):
+            self._run(b, B, img=img)                 # eager warm-up: sets func attributes, builds nothing lazily later
+        torch.cuda.current_stream(self.device).wait_stream(side)
+        torch.cuda.synchronize(self.device)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self._run(b, B, img=img)
+        return g
+
     def _plan(self, B: int):
         plan = self._plans.get(B)
         if plan is None:
             b = self._buffers(B)
-            plan = {"buf": b, "graph": None}
+            plan = {"buf": b, "graph": None, "bound": {}, "seen": {}}
             if self.use_cuda_graph:
-                side = torch.cuda.Stream(device=self.device)
-                side.wait_stream(torch.cuda.current_stream(self.device))
-                with torch.cuda.stream(side):
-                    self._run(b, B)                  # eager warm-up: sets func attributes, builds nothing lazily later
-                torch.cuda.current_stream(self.device).wait_stream(side)
-                torch.cuda.synchronize(self.device)
-                g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g):
-                    self._run(b, B)
-                plan["graph"] = g
+                plan["graph"] = self._capture(b, B)
             self._plans[B] = plan
         return plan
 
@@ -184,11 +188,25 @@ class Engine:
             raise RuntimeError("Engine.forward: images on %s, engine on %s" % (images.device, self.device))
         B = images.shape[0]
         plan = self._plan(B)
-        plan["buf"]["img"].copy_(images, non_blocking=True)
-        if plan["graph"] is not None:
-            plan["graph"].replay()
-        else:
+        if plan["graph"] is None:
+            plan["buf"]["img"].copy_(images, non_blocking=True)
             self._run(plan["buf"], B)
+            return plan["buf"]["logits"]
+        # A caller that feeds the same (contiguous fp32) buffer again gets a graph bound to that address: the 2 x 154 MB
+        # device-to-device copy into the engine's own input buffer disappears (staging buffers of a serving loop,
+        # bench.py).  First and second sight of an address still go through the copy; at most 4 addresses are bound.
+        key = images.data_ptr()
+        ok = images.dtype == torch.float32 and images.is_contiguous() and images.shape == plan["buf"]["img"].shape
+        g = plan["bound"].get(key) if ok else None
+        if g is None and ok:
+            plan["seen"][key] = plan["seen"].get(key, 0) + 1
+            if plan["seen"][key] >= 2 and len(plan["bound"]) < 4:
+                g = plan["bound"][key] = self._capture(plan["buf"], B, img=images)
+        if g is not None:
+            g.replay()
+        else:
+            plan["buf"]["img"].copy_(images, non_blocking=True)
+            plan["graph"].replay()
         return plan["buf"]["logits"]
 
     __call__ = forward
