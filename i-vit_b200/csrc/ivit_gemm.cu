@@ -346,15 +346,16 @@ __device__ __forceinline__ void tmem_ld_chunk(uint32_t taddr, uint32_t (&r)[CW])
 
 // OUT_ES: bytes per output element staged through shared memory for the TMA store (0: direct global stores)
 // PAIR: the CTA holds only its half of the W tile (the other half lives in the peer CTA of the pair)
-template <int BN, int STAGES, int OUT_ES, bool PAIR>
+template <int BN, int STAGES, int OUT_ES, bool PAIR, bool RES = false>
 struct GemmSmem {
     static constexpr int A_BYTES = GEMM_BM * GEMM_BK;
     static constexpr int B_BYTES = (PAIR ? BN / 2 : BN) * GEMM_BK;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int OUT_BYTES = GEMM_BM * BN * OUT_ES;                     // [BN*OUT_ES/128 boxes][128 rows][128 B], 128B-swizzled
+    static constexpr int RES_BYTES = RES ? GEMM_BM * BN * 2 : 0;                // int16 residual tile, same box layout (output mode 3)
     static constexpr int PARAM_BYTES = 2 * BN * ((int)sizeof(ColParam) + 4);   // ColParam[2][BN] + int32 bias[2][BN]
-    static constexpr int BAR_BYTES = 256;
-    static constexpr int TOTAL = STAGES * STAGE_BYTES + OUT_BYTES + PARAM_BYTES + BAR_BYTES + 1024;  // +1024 alignment slack
+    static constexpr int BAR_BYTES = 512;                                       // pipeline barriers [0, 256), residual barriers [256, 512)
+    static constexpr int TOTAL = STAGES * STAGE_BYTES + OUT_BYTES + RES_BYTES + PARAM_BYTES + BAR_BYTES + 1024;  // +1024 alignment slack
 };
 
 // PAIR = true: CTA-pair kernel (tcgen05 cta_group::2).  The two CTAs of a 2-CTA cluster (the two SMs of a TPC) work on
@@ -365,14 +366,20 @@ struct GemmSmem {
 // epilogue LDS/STS ~ 93 % of peak wavefronts, profiles/ncu_full_r1g), which is what bounds it, not the tensor pipe.
 // OM (output mode): 0 direct global stores from registers; 1 output staged in shared memory and written by TMA;
 //                   2 direct stores, the staging tile instead holds the int16 residual, prefetched per tile by cp.async
+//                   3 as 1, and the int16 residual tile arrives by TMA in its own shared-memory tile (32-row x 128-byte
+//                     boxes, one pair per epilogue warp, refilled for the next tile as soon as a box has been consumed).
+//                     Row-per-thread global loads of the residual touch 32 different lines per instruction: reading the
+//                     residual as zeros (IVIT_GEMM_DEBUG=4) took 18 of proj's 70 us away, a deeper register prefetch none.
 template <int BN, int STAGES, int MODE, int OM, bool PAIR>
 __global__ void __launch_bounds__(gemm_threads(MODE), 1)
 gemm_i8_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                       const __grid_constant__ CUtensorMap tmap_out, const GemmArgs args) {
-    constexpr bool TS = (OM == 1), RSM = (OM == 2);
+                       const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_res,
+                       const GemmArgs args) {
+    constexpr bool TS = (OM == 1 || OM == 3), RSM = (OM == 2), RTMA = (OM == 3);
     static_assert(!RSM || MODE == GM_RQ_I16, "residual staging belongs to the 16-bit epilogue");
+    static_assert(!RTMA || (MODE == GM_RQ_I16 && BN == 256), "TMA residual: 16-bit epilogue, 256-wide tiles");
     constexpr int OUT_ES = (OM == 0) ? 0 : (MODE == GM_RQ_I8 ? 1 : 2);
-    using S = GemmSmem<BN, STAGES, OUT_ES, PAIR>;
+    using S = GemmSmem<BN, STAGES, OUT_ES, PAIR, RTMA>;
     constexpr uint32_t TMEM_COLS = 2 * BN;            // double-buffered accumulator (256 or 512)
     constexpr int WPG = gemm_wpg(MODE);
     constexpr int EPI_WARPS = 4 * WPG;
@@ -382,9 +389,11 @@ gemm_i8_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
 
     const uint32_t stage_base = smem_base;
     const uint32_t out_base = smem_base + STAGES * S::STAGE_BYTES;             // 1024-aligned (stage sizes are)
-    ColParam* col_params = reinterpret_cast<ColParam*>(smem + STAGES * S::STAGE_BYTES + S::OUT_BYTES);
+    const uint32_t res_base = out_base + S::OUT_BYTES;                         // 1024-aligned (OUT_BYTES is a multiple)
+    ColParam* col_params = reinterpret_cast<ColParam*>(smem + STAGES * S::STAGE_BYTES + S::OUT_BYTES + S::RES_BYTES);
     int32_t* col_bias = reinterpret_cast<int32_t*>(col_params + 2 * BN);
-    const uint32_t bar_base = smem_base + STAGES * S::STAGE_BYTES + S::OUT_BYTES + S::PARAM_BYTES;
+    const uint32_t bar_base = smem_base + STAGES * S::STAGE_BYTES + S::OUT_BYTES + S::RES_BYTES + S::PARAM_BYTES;
+    auto res_bar = [&](int ew, int h) { return bar_base + 256u + 8u * (uint32_t)(ew * 2 + h); };   // residual box h of epilogue warp ew landed
     // barrier layout (8 B each): full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], pfull[2], sfull[2], then tmem ptr + flags
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
     auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
@@ -392,7 +401,7 @@ gemm_i8_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
     auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + 2 + s); };
     auto pfull_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + 4 + s); };     // column constants staged (aux -> epilogue)
     auto sfull_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + 6 + s); };     // epilogue warps done with a constants buffer (-> aux)
-    volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + STAGES * S::STAGE_BYTES + S::OUT_BYTES + S::PARAM_BYTES + 8 * (2 * STAGES + 8));
+    volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + STAGES * S::STAGE_BYTES + S::OUT_BYTES + S::RES_BYTES + S::PARAM_BYTES + 8 * (2 * STAGES + 8));
     int* fast_flag = reinterpret_cast<int*>(const_cast<uint32_t*>(tmem_ptr_smem) + 2);   // [2] one per accumulator stage
 
     const int warp = threadIdx.x >> 5;
@@ -425,6 +434,9 @@ gemm_i8_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
             ptx::mbar_init(pfull_bar(s), 1);
             ptx::mbar_init(sfull_bar(s), EPI_WARPS);
         }
+        if (RTMA)
+            for (int i = 0; i < 2 * EPI_WARPS; ++i) ptx::mbar_init(res_bar(i >> 1, i & 1), 1);
+        if (RTMA) ptx::prefetch_tensormap(&tmap_res);
         ptx::fence_barrier_init();
     }
     if (warp == 1) {
@@ -590,6 +602,16 @@ gemm_i8_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
         const int col_part = ew >> 2;                 // which 1/WPG of the tile's columns
         constexpr int CW = (MODE == GM_RQ_I16) ? 16 : 32;
         const uint32_t tempty_leader = PAIR ? ptx::mapa(tempty_bar(0), 0) : 0u;   // the leader's MMA warp owns both accumulators
+        // output mode 3: residual box h (64 columns) of this warp's 32 rows for `tile`, by TMA into the residual tile
+        auto issue_res = [&](int tile, int h) {
+            if constexpr (RTMA) {
+                const int bx = col_part * 2 + h;
+                const uint32_t dst = res_base + (uint32_t)(bx * GEMM_BM * 128 + lane_group * 32 * 128);
+                ptx::mbar_arrive_expect_tx(res_bar(ew, h), 32 * 128);
+                ptx::tma_load_2d(dst, &tmap_res, res_bar(ew, h), (tile_n0(tile) + bx * 64) * 2, tile_m0(tile) + lane_group * 32);
+            }
+        };
+        if (RTMA && lane == 0 && tile_first < num_tiles) { issue_res(tile_first, 0); issue_res(tile_first, 1); }
         int it = 0;
         for (int tile = tile_first; tile < num_tiles; tile += tile_step, ++it) {
             const int as = it & 1;
@@ -623,9 +645,21 @@ gemm_i8_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
             // each), into my own rows of the staging tile: one memory round trip per tile, overlapped with the wait for
             // the accumulator, instead of one exposed round trip per 16-column chunk.  The rows are private to this
             // thread (it consumed the previous tile's copy itself), so no synchronisation is involved.
-            constexpr bool res_smem = RSM;
+            constexpr bool res_smem = RSM || RTMA;
+            const uint32_t rsm_base = RTMA ? res_base : out_base;
+            const uint32_t res_parity = (uint32_t)(it & 1);
+            const int next_tile = tile + tile_step;
+            // RTMA: box h must have landed before its first read; once its last chunk has been consumed the next tile's
+            // box is requested into the same place (every lane's reads are complete: their values have been used)
+            auto res_wait = [&](int h) { if constexpr (RTMA) ptx::mbar_wait(res_bar(ew, h), res_parity); };
+            auto res_refill = [&](int h) {
+                if constexpr (RTMA) {
+                    __syncwarp();
+                    if (lane == 0 && next_tile < num_tiles) { ptx::fence_proxy_async(); issue_res(next_tile, h); }
+                }
+            };
             uint32_t ra[CW], rb[CW], resa[CW / 2], resb[CW / 2];
-            if (res_smem) {
+            if (RSM) {
                 const int16_t* rsrc = reinterpret_cast<const int16_t*>(args.residual) + (long long)(row_ok ? row : 0) * args.res_ld + n0;
 #pragma unroll
                 for (int j = 0; j < CPART / 8; ++j) {
@@ -634,7 +668,7 @@ gemm_i8_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
                     cp_async_16(swz_addr(out_base, trow, c * 2), ok ? (const void*)(rsrc + c) : args.residual, ok ? 16 : 0);
                 }
                 cp_async_commit();
-            } else if (MODE == GM_RQ_I16 && c_begin < c_end) {
+            } else if (!RTMA && MODE == GM_RQ_I16 && c_begin < c_end) {
                 load_residual<CW>(args, row, row_ok, n0 + c_begin, resa);
             }
 
@@ -648,21 +682,27 @@ gemm_i8_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
                 tmem_ld_chunk<CW>(t_row + (uint32_t)c_begin, ra);
                 ptx::tmem_ld_wait();
             }
-            if (res_smem) {
+            if (RSM) {
                 cp_async_wait_all();                                     // my own copies: no barrier needed to read them back
                 if (work) load_residual_smem<CW>(out_base, trow, c_begin, resa);
             } else if (TS) {
                 wait_staging_free();
+            }
+            if (RTMA) {
+                res_wait(0);
+                if (work) load_residual_smem<CW>(rsm_base, trow, c_begin, resa);
             }
             if (work) {
 #pragma unroll 1
                 for (int c0 = c_begin; c0 < c_end; c0 += 2 * CW) {
                     const bool has1 = (c0 + CW) < c_end;
                     const bool has2 = (c0 + 2 * CW) < c_end;
+                    // output mode 3 (full tiles only): chunks 0-3 of my column part lie in residual box 0, 4-7 in box 1
+                    const int k = (c0 - c_begin) / CW;                   // even chunk index of this pair
                     if (has1) {
                         tmem_ld_chunk<CW>(t_row + (uint32_t)(c0 + CW), rb);
                         if (MODE == GM_RQ_I16) {
-                            if (res_smem) load_residual_smem<CW>(out_base, trow, c0 + CW, resb);
+                            if (res_smem) load_residual_smem<CW>(rsm_base, trow, c0 + CW, resb);
                             else load_residual<CW>(args, row, row_ok, n0 + c0 + CW, resb);
                         }
                     }
@@ -673,7 +713,8 @@ gemm_i8_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
                         if (has2) {
                             tmem_ld_chunk<CW>(t_row + (uint32_t)(c0 + 2 * CW), ra);
                             if (MODE == GM_RQ_I16) {
-                                if (res_smem) load_residual_smem<CW>(out_base, trow, c0 + 2 * CW, resa);
+                                if (RTMA && k + 2 == 4) res_wait(1);      // the next pair starts box 1
+                                if (res_smem) load_residual_smem<CW>(rsm_base, trow, c0 + 2 * CW, resa);
                                 else load_residual<CW>(args, row, row_ok, n0 + c0 + 2 * CW, resa);
                             }
                         }
@@ -681,7 +722,13 @@ gemm_i8_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
                                                      out_base, lane_group * 32 + lane, c0 + CW);
                         ptx::tmem_ld_wait();
                     }
+                    if (RTMA && (k == 2 || k == 6)) res_refill(k == 2 ? 0 : 1);   // chunks 3 / 7 done: box consumed
                 }
+            } else if (RTMA) {
+                // diagnostics path (no epilogue work): keep the residual pipeline's phases in step
+                res_wait(1);
+                res_refill(0);
+                res_refill(1);
             }
             // release the accumulator back to the MMA warp and the constants buffer to the auxiliary warp
             ptx::tc_fence_before();
@@ -814,10 +861,11 @@ int make_tmap_2d_u8(ivit_ctx* ctx, CUtensorMap* tm, const void* base, uint64_t i
 
 template <int BN, int STAGES, int MODE, int OM, bool PAIR>
 static int launch_gemm(ivit_ctx* ctx, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const GemmArgs& ga,
-                       cudaStream_t s) {
+                       cudaStream_t s, const CUtensorMap* tres = nullptr) {
     constexpr int OUT_ES = (OM == 0) ? 0 : (MODE == GM_RQ_I8 ? 1 : 2);
     constexpr int CS = PAIR ? 2 : 1;
-    using S = GemmSmem<BN, STAGES, OUT_ES, PAIR>;
+    using S = GemmSmem<BN, STAGES, OUT_ES, PAIR, OM == 3>;
+    const CUtensorMap& tr = tres ? *tres : ta;
     static_assert(S::TOTAL <= 227 * 1024, "shared memory budget");
     auto kern = gemm_i8_tcgen05_kernel<BN, STAGES, MODE, OM, PAIR>;
     static bool attr_set = false;                     // per instantiation
@@ -845,7 +893,7 @@ static int launch_gemm(ivit_ctx* ctx, const CUtensorMap& ta, const CUtensorMap& 
     const int cap = (CS > 1) ? max_clusters : ctx->num_sms;
     const int nclusters = ctiles < cap ? ctiles : cap;
     cfg.gridDim = dim3(nclusters * CS);
-    IVIT_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, ta, tb, to, ga));
+    IVIT_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, ta, tb, to, tr, ga));
     IVIT_LAUNCH_OK("gemm_i8_tcgen05_kernel");
     return IVIT_OK;
 }
@@ -885,6 +933,20 @@ static int dispatch_bn(ivit_ctx* ctx, const int8_t* A, int64_t lda, const int8_t
             // byte-typed view of the output: inner dim = N*ES bytes, box = 128 bytes x 32 rows (one epilogue warp), 128B swizzle
             rc = make_tmap_2d_u8(ctx, &to, ga.out, (uint64_t)ga.N * ES, (uint64_t)ga.M, (uint64_t)ga.out_ld * ES, 128, GEMM_BM / 4);
             if (rc) return rc;
+            if constexpr (MODE == GM_RQ_I16) {
+                // residual tile by TMA (output mode 3): pairs, full 256-wide tiles, 16-byte aligned residual rows.  The extra
+                // 64 KB tile leaves two operand stages, enough for the K <= 1024 shapes whose epilogue sets the time
+                // (attn.proj); IVIT_GEMM_RTMA=0 disables, =2 takes it for every K.
+                static const char* rt_env = getenv("IVIT_GEMM_RTMA");
+                const int rt = rt_env ? atoi(rt_env) : 1;
+                if (pair && rt && ga.residual && ga.N % 256 == 0 && ((uintptr_t)ga.residual % 16) == 0 && (ga.res_ld * 2) % 16 == 0 &&
+                    (ga.K <= 1024 || rt == 2)) {
+                    CUtensorMap tr;
+                    rc = make_tmap_2d_u8(ctx, &tr, ga.residual, (uint64_t)ga.N * 2, (uint64_t)ga.M, (uint64_t)ga.res_ld * 2, 128, GEMM_BM / 4);
+                    if (rc) return rc;
+                    return launch_gemm<256, 2, MODE, 3, true>(ctx, ta, tb, to, ga, s, &tr);
+                }
+            }
             if (pair) return launch_gemm<256, (ES == 1 ? 5 : 4), MODE, 1, true>(ctx, ta, tb, to, ga, s);
             if (wide) return launch_gemm<256, 3, MODE, 1, false>(ctx, ta, tb, to, ga, s);
             return launch_gemm<128, 5, MODE, 1, false>(ctx, ta, tb, to, ga, s);
