@@ -14,7 +14,8 @@ import torch  # noqa: E402
 import ivit_b200.kernels as K  # noqa: E402
 
 SHAPES = [("qkv", 50432, 2304, 768, 8, False), ("fc1", 50432, 3072, 768, 8, False),
-          ("proj", 50432, 768, 768, 16, True), ("fc2", 50432, 768, 3072, 16, True)]
+          ("proj", 50432, 768, 768, 16, True), ("fc2", 50432, 768, 3072, 16, True),
+          ("patch", 50176, 768, 768, 16, False)]          # patch embedding: plain 16-bit requant, no residual
 
 
 def main():
@@ -26,7 +27,7 @@ def main():
         w = torch.randint(-128, 128, (N, Kd), dtype=torch.int8, device=dev)
         bias = torch.randint(-2 ** 15, 2 ** 15, (N,), dtype=torch.int32, device=dev)
         m = rng.integers(2 ** 30, 2 ** 31 - 1, N) | 1
-        e = rng.integers(44, 48, N)
+        e = rng.integers(44, 48, N) if bits == 8 or res else rng.integers(33, 36, N)
         me = K.dyadic_table(m, e, dev)
         out = torch.empty((M, N), dtype=torch.int8 if bits == 8 else torch.int16, device=dev)
         kw = {}
