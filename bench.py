@@ -250,30 +250,39 @@ def run_ours(args, rank, world, local_rank):
     # i+1 runs on a copy stream while step i computes (two device staging buffers); every step still pays
     # its own H2D and D2H inside the timed region.
     copy_stream = torch.cuda.Stream(device=dev)
-    stage = [torch.empty_like(x), torch.empty_like(x)]
-    ready = [torch.cuda.Event(), torch.cuda.Event()]
-    consumed = [torch.cuda.Event(), torch.cuda.Event()]
-    state = {"i": 0, "primed": False}
 
-    def issue_h2d(slot):
-        with torch.cuda.stream(copy_stream):
-            copy_stream.wait_event(consumed[slot])
-            stage[slot].copy_(host, non_blocking=True)
-            ready[slot].record(copy_stream)
+    def make_e2e(host_t):
+        """Pipelined end-to-end step over `host_t` (pinned): H2D of step i+1 on the copy stream during step i."""
+        stage = [torch.empty(host_t.shape, dtype=host_t.dtype, device=dev) for _ in range(2)]
+        ready = [torch.cuda.Event(), torch.cuda.Event()]
+        consumed = [torch.cuda.Event(), torch.cuda.Event()]
+        state = {"i": 0, "primed": False}
 
-    def step_e2e():
-        main = torch.cuda.current_stream(dev)
-        slot = state["i"] & 1
-        if not state["primed"]:
-            consumed[0].record(main); consumed[1].record(main)
-            issue_h2d(slot)
-            state["primed"] = True
-        issue_h2d(slot ^ 1)                                 # prefetch the next step's images
-        main.wait_event(ready[slot])
-        logits = eng(stage[slot])
-        consumed[slot].record(main)
-        out_host.copy_(logits, non_blocking=True)
-        state["i"] += 1
+        def issue_h2d(slot):
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(consumed[slot])
+                stage[slot].copy_(host_t, non_blocking=True)
+                ready[slot].record(copy_stream)
+
+        def step():
+            main = torch.cuda.current_stream(dev)
+            slot = state["i"] & 1
+            if not state["primed"]:
+                consumed[0].record(main); consumed[1].record(main)
+                issue_h2d(slot)
+                state["primed"] = True
+            issue_h2d(slot ^ 1)                             # prefetch the next step's images
+            main.wait_event(ready[slot])
+            logits = eng(stage[slot])
+            consumed[slot].record(main)
+            out_host.copy_(logits, non_blocking=True)
+            state["i"] += 1
+        return step
+
+    step_e2e = make_e2e(host)
+    # the same images as decoded uint8 pixels (the engine applies ToTensor + Normalize on the device): 4x fewer H2D bytes
+    host_u8 = torch.randint(0, 256, host.shape, generator=g, dtype=torch.uint8).pin_memory()
+    step_e2e_u8 = make_e2e(host_u8)
 
     with ClockSampler(local_rank) as clk:                  # sampled from the warm-up to the end of both timed regions
         for _ in range(max(args.warmup, 3)):
@@ -282,6 +291,9 @@ def run_ours(args, rank, world, local_rank):
         for _ in range(max(args.warmup, 6)):               # both staging buffers seen often enough to be graph-bound
             step_e2e()
         e2e_ms = timed(step_e2e, args.steps)
+        for _ in range(3):
+            step_e2e_u8()
+        e2e_u8_ms = timed(step_e2e_u8, args.steps)
     clocks = clk.summary()
 
     ms_step = total_ms / args.steps
@@ -347,7 +359,10 @@ def run_ours(args, rank, world, local_rank):
                          "whole_step_int_tops": int_ops_per_image(eng.meta) * B / (ms_step * 1e-3) / 1e12},
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_val, "unit": "images/s", "h2d_bytes_per_step": int(host.numel() * 4) * world,
-                    "d2h_bytes_per_step": int(out_host.numel() * 4) * world, "ms_per_step": e2e_ms / args.steps},
+                    "d2h_bytes_per_step": int(out_host.numel() * 4) * world, "ms_per_step": e2e_ms / args.steps,
+                    "uint8_input": {"value": world * B / (e2e_u8_ms / args.steps * 1e-3), "unit": "images/s",
+                                    "h2d_bytes_per_step": int(host_u8.numel()) * world, "ms_per_step": e2e_u8_ms / args.steps,
+                                    "note": "decoded uint8 pixels in, ToTensor + Normalize fused into the stem kernel"}},
             "gpu_launches": (eng.launches_per_forward - 1) * args.steps,
             "clocks": clocks}
     print(json.dumps(line), flush=True)

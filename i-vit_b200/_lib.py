@@ -65,6 +65,7 @@ SIGNATURES = {
     "ivit_shiftgelu_lut": [_vp, _vp, _i64, _int, _vp, _vp, _vp],
     "ivit_layernorm_i16_i8": [_vp, _vp, _i64, _int, _vp, _vp, _vp, _vp],
     "ivit_quantize_patchify": [_vp, _vp, _vp, _int, _int, _int, _int, _int, _vp, _vp],
+    "ivit_quantize_patchify_u8": [_vp, _vp, _vp, _vp, _vp, _int, _int, _int, _int, _int, _vp, _vp],
     "ivit_embed_tokens_fast": [_vp, _vp, _vp, _vp, _int, _int, _int, Dyadic, Dyadic, _vp, _vp],
 }
 EXPORTS = ["ivit_version", "ivit_last_error", "ivit_create", "ivit_destroy", "ivit_num_sms"] + sorted(SIGNATURES)

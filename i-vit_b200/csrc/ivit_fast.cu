@@ -371,6 +371,48 @@ quantize_patchify16_kernel(const float4* __restrict__ img, const float* __restri
     }
 }
 
+// uint8 input: the whole fp32 chain of the reference's eval transform + input QuantAct depends only on (channel, byte):
+//   t = u / 255 (ToTensor); x = (t - mean[c]) / std[c] (Normalize, utils/data_utils.py:90-91); q = clamp8(RNE(x * (1/s)))
+// -> a Cin x 256 table built per launch by the first threads of each block (same IEEE operations as torch: div, sub, div,
+// mul, round-half-even), applied as a byte lookup.  One thread per (image, channel, row pair, patch column) as above.
+__global__ void __launch_bounds__(256)
+quantize_patchify16_u8_kernel(const uint8_t* __restrict__ img, const float* __restrict__ mean, const float* __restrict__ stdv,
+                              const float* __restrict__ scale, int B, int Cin, int H, int W, int8_t* __restrict__ out) {
+    __shared__ __align__(16) int8_t s_tab[4][256];
+    {
+        const float inv = __fdiv_rn(1.0f, scale[0]);
+        for (int i = threadIdx.x; i < Cin * 256; i += blockDim.x) {
+            const int c = i >> 8, u = i & 255;
+            const float t = __fdiv_rn((float)u, 255.0f);
+            const float x = __fdiv_rn(__fsub_rn(t, mean[c]), stdv[c]);
+            s_tab[c][u] = (int8_t)fminf(fmaxf(rintf(__fmul_rn(inv, x)), -128.f), 127.f);
+        }
+    }
+    __syncthreads();
+    const int Wp = W >> 4, Hp = H >> 4, H2 = H >> 1, K = Cin * 256;
+    const int64_t n = (int64_t)B * Cin * H2 * Wp;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int px = (int)(i % Wp);
+        int64_t r = i / Wp;
+        const int y = 2 * (int)(r % H2); r /= H2;
+        const int c = (int)(r % Cin);
+        const int64_t b = r / Cin;
+        const uint8_t* src = img + ((b * Cin + c) * H + y) * (int64_t)W + px * 16;
+        const uint4 v0 = __ldg(reinterpret_cast<const uint4*>(src)), v1 = __ldg(reinterpret_cast<const uint4*>(src + W));
+        const uint32_t in[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+        const int8_t* tab = s_tab[c];
+        uint32_t o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            o[j] = (uint32_t)(uint8_t)tab[in[j] & 0xff] | ((uint32_t)(uint8_t)tab[(in[j] >> 8) & 0xff] << 8) |
+                   ((uint32_t)(uint8_t)tab[(in[j] >> 16) & 0xff] << 16) | ((uint32_t)(uint8_t)tab[in[j] >> 24] << 24);
+        const int64_t row = (b * Hp + (y >> 4)) * Wp + px;
+        uint4* dst = reinterpret_cast<uint4*>(out + row * (int64_t)K + (c * 16 + (y & 15)) * 16);
+        dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
+        dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
+    }
+}
+
 // ------------------------------------------------------------------------------------
 // Stem: cls-token concatenation + position-embedding residual QuantAct (vit_quant.py:259-265), 8 channels per
 // thread, scalar dyadics analysed on the host (same unified form as the GEMM epilogue's second stage).
@@ -494,6 +536,20 @@ int ivit_quantize_patchify(ivit_ctx* ctx, const float* img, const float* scale, 
     const int grid = (int)(blocks < (int64_t)ctx->num_sms * 16 ? blocks : (int64_t)ctx->num_sms * 16);
     quantize_patchify_kernel<<<grid, 256, 0, st(stream)>>>((const float4*)img, scale, B, Cin, H, W, p, out);
     IVIT_LAUNCH_OK("quantize_patchify_kernel");
+    return IVIT_OK;
+}
+
+int ivit_quantize_patchify_u8(ivit_ctx* ctx, const uint8_t* img, const float* mean, const float* stdv, const float* scale,
+                              int B, int Cin, int H, int W, int p, int8_t* out, ivit_stream stream) {
+    IVIT_REQUIRE(ctx && img && mean && stdv && scale && out && B > 0, "ivit_quantize_patchify_u8: bad arguments");
+    IVIT_REQUIRE(p == 16 && Cin >= 1 && Cin <= 4, "ivit_quantize_patchify_u8: patch 16, at most 4 channels");
+    IVIT_REQUIRE(H % 16 == 0 && W % 16 == 0, "ivit_quantize_patchify_u8: H, W multiples of the patch size");
+    IVIT_REQUIRE(((uintptr_t)img % 16) == 0 && ((uintptr_t)out % 16) == 0, "ivit_quantize_patchify_u8: 16-byte alignment");
+    const int64_t n = (int64_t)B * Cin * (H / 2) * (W / 16);
+    const int64_t blocks = (n + 255) / 256;
+    const int grid = (int)(blocks < (int64_t)ctx->num_sms * 8 ? blocks : (int64_t)ctx->num_sms * 8);
+    quantize_patchify16_u8_kernel<<<grid, 256, 0, st(stream)>>>(img, mean, stdv, scale, B, Cin, H, W, out);
+    IVIT_LAUNCH_OK("quantize_patchify16_u8_kernel");
     return IVIT_OK;
 }
 

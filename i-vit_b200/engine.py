@@ -57,6 +57,9 @@ class Engine:
                 bound = int(v.shape[1]) * 128 * 128 + int(np.abs(pack.arrays[name + ".bias_integer"].astype(np.int64)).max()) + 1
                 self.acc_bits[name] = min(31, int(bound).bit_length())
         self._plans = {}
+        # eval transform of the reference (utils/data_utils.py:91, timm's IMAGENET_DEFAULT_MEAN / STD) for uint8 inputs
+        self._norm = (torch.tensor([0.485, 0.456, 0.406], dtype=torch.float32, device=self.device),
+                      torch.tensor([0.229, 0.224, 0.225], dtype=torch.float32, device=self.device))
         self._gemm_events = None
         self.launches_per_forward = 0
 
@@ -75,6 +78,7 @@ class Engine:
         return dict(
             img=e(B, m["in_chans"], m["img_size"], m["img_size"], dtype=torch.float32),
             img_q=e(B, m["in_chans"], m["img_size"], m["img_size"], dtype=torch.int8),
+            img_u8=e(B, m["in_chans"], m["img_size"], m["img_size"], dtype=torch.uint8),
             patches=e(B * (N - 1), m["in_chans"] * m["patch"] ** 2, dtype=torch.int8),
             pe16=e(B * (N - 1), C, dtype=torch.int16),
             xa=e(M, C, dtype=torch.int16), xb=e(M, C, dtype=torch.int16),
@@ -87,6 +91,7 @@ class Engine:
     def _run(self, b, B: int, taps: dict = None, img: torch.Tensor = None):
         m, t, s = self.meta, self.t, self.s
         img = b["img"] if img is None else img
+        u8 = img.dtype == torch.uint8                      # raw decoded image: ToTensor + Normalize fused into the stem kernel
         C, N, H, D = m["embed_dim"], m["n_tok"], m["num_heads"], m["head_dim"]
         n = 0
 
@@ -110,7 +115,9 @@ class Engine:
                 ev.append((name, a.shape[0], w.shape[0], w.shape[1], e0, e1))
 
         # input quantisation (vit_quant.py:257) -> patch unfold -> patch-embedding GEMM (+patch_embed.qact, 16 bit)
-        if taps is None and m["patch"] % 4 == 0:
+        if u8:
+            K.quantize_patchify_u8(img, self._norm[0], self._norm[1], t["qact_input.scale"], m["patch"], out=b["patches"]); n += 1
+        elif taps is None and m["patch"] % 4 == 0:
             K.quantize_patchify(img, t["qact_input.scale"], m["patch"], out=b["patches"]); n += 1   # one fused pass
         else:
             _quantize_into(img, t["qact_input.scale"], b["img_q"]); n += 1
@@ -174,7 +181,7 @@ class Engine:
         plan = self._plans.get(B)
         if plan is None:
             b = self._buffers(B)
-            plan = {"buf": b, "graph": None, "bound": {}, "seen": {}}
+            plan = {"buf": b, "graph": None, "graph_u8": None, "bound": {}, "seen": {}}
             if self.use_cuda_graph:
                 plan["graph"] = self._capture(b, B)
             self._plans[B] = plan
@@ -182,12 +189,26 @@ class Engine:
 
     @torch.no_grad()
     def forward(self, images: torch.Tensor) -> torch.Tensor:
-        """images: fp32 [B, 3, H, W] on this engine's device -> fp32 logits [B, classes]
+        """images: fp32 [B, 3, H, W] (already normalised, as the reference's models take them) or uint8 [B, 3, H, W]
+        (decoded pixels: ToTensor + Normalize of the reference's eval transform are applied on the device, bit-identical
+        to torchvision's fp32 arithmetic) on this engine's device -> fp32 logits [B, classes]
         (a view of an internal buffer, valid until the next call with the same batch size)."""
         if images.device != self.device and not (images.is_cuda and self.device.index is None):
             raise RuntimeError("Engine.forward: images on %s, engine on %s" % (images.device, self.device))
         B = images.shape[0]
         plan = self._plan(B)
+        if images.dtype == torch.uint8:
+            # decoded uint8 NCHW images: the reference's ToTensor + Normalize run inside the stem kernel (patch 16 models)
+            if self.meta["patch"] != 16 or self.meta["in_chans"] > 4:
+                raise NotImplementedError("uint8 input path: 16 x 16 patches, at most 4 channels")
+            plan["buf"]["img_u8"].copy_(images, non_blocking=True)
+            if plan["graph"] is None:
+                self._run(plan["buf"], B, img=plan["buf"]["img_u8"])
+            else:
+                if plan["graph_u8"] is None:
+                    plan["graph_u8"] = self._capture(plan["buf"], B, img=plan["buf"]["img_u8"])
+                plan["graph_u8"].replay()
+            return plan["buf"]["logits"]
         if plan["graph"] is None:
             plan["buf"]["img"].copy_(images, non_blocking=True)
             self._run(plan["buf"], B)

@@ -256,6 +256,17 @@ def quantize_patchify(img: torch.Tensor, scale: torch.Tensor, patch: int, out: t
     return out
 
 
+def quantize_patchify_u8(img: torch.Tensor, mean: torch.Tensor, std: torch.Tensor, scale: torch.Tensor, patch: int,
+                         out: torch.Tensor = None):
+    """uint8 NCHW image -> int8 patch rows: ToTensor + Normalize (utils/data_utils.py:90-91) + input QuantAct + unfold."""
+    assert img.dtype == torch.uint8 and img.dim() == 4 and img.is_contiguous()
+    B, Cin, H, W = img.shape
+    if out is None:
+        out = torch.empty((B * (H // patch) * (W // patch), Cin * patch * patch), dtype=torch.int8, device=img.device)
+    call("ivit_quantize_patchify_u8", context(img.device), ptr(img), ptr(mean), ptr(std), ptr(scale), B, Cin, H, W, patch, ptr(out))
+    return out
+
+
 def embed_tokens_fast(pe16, cls32, pos16, B: int, n_tok: int, C: int, me, me_res, out=None):
     if out is None:
         out = torch.empty((B * n_tok, C), dtype=torch.int16, device=pe16.device)

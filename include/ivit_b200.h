@@ -242,6 +242,16 @@ IVIT_API int ivit_layernorm_i16_i8(ivit_ctx*, const int16_t* x, int64_t rows, in
 IVIT_API int ivit_quantize_patchify(ivit_ctx*, const float* img, const float* scale, int B, int Cin, int H,
                                     int W, int p, int8_t* out, ivit_stream stream);
 
+/* uint8 NCHW image -> int8 GEMM rows in one pass: ToTensor (u / 255), Normalize ((t - mean[c]) / std[c]) -- the
+ * reference's eval transform, utils/data_utils.py:90-91 -- then the input QuantAct and the 16 x 16 patch unfold of
+ * ivit_quantize_patchify.  Every step is the same correctly-rounded fp32 operation torch performs, so the result equals
+ * the reference's pipeline on the decoded uint8 image bit for bit; it is evaluated once per (channel, byte value) into a
+ * 768-entry table on the device and applied by lookup.  mean/std: device fp32 [Cin]; patch 16; Cin <= 4.
+ * Moves 4x fewer bytes host -> device than the fp32 entry point. */
+IVIT_API int ivit_quantize_patchify_u8(ivit_ctx*, const uint8_t* img, const float* mean, const float* std,
+                                       const float* scale, int B, int Cin, int H, int W, int p, int8_t* out,
+                                       ivit_stream stream);
+
 /* Vectorised form of ivit_embed_tokens (bits 16, C % 8 == 0, dyadic exponents in [16, 62]). */
 IVIT_API int ivit_embed_tokens_fast(ivit_ctx*, const int16_t* pe, const int32_t* cls, const int16_t* pos,
                                     int B, int n_tok, int C, ivit_dyadic_t me, ivit_dyadic_t me_res,

@@ -438,6 +438,24 @@ def test_quantize_patchify_fused(K):
         assert np.array_equal(got, want), (B, Cin, H, W, p)
 
 
+def test_quantize_patchify_u8_matches_reference_transform(K):
+    """uint8 pixels -> ToTensor -> Normalize (utils/data_utils.py:90-91) -> input QuantAct -> unfold, against the same
+    chain evaluated by torch in fp32 on the CPU (every step is a single correctly-rounded fp32 operation)."""
+    import torch
+    rng = np.random.default_rng(31)
+    mean = torch.tensor([0.485, 0.456, 0.406]); std = torch.tensor([0.229, 0.224, 0.225])
+    for (B, H, W) in [(2, 32, 48), (1, 224, 224)]:
+        u = rng.integers(0, 256, (B, 3, H, W)).astype(np.uint8)
+        u[0, :, 0, :16] = np.arange(16, dtype=np.uint8) * 17           # includes 0 and 255
+        s = np.float32(0.02071)
+        t = torch.from_numpy(u).to(torch.float32).div(255)             # ToTensor
+        x = t.sub(mean[None, :, None, None]).div(std[None, :, None, None])   # Normalize
+        q = O.quantize_f32(x.numpy(), s, 8).astype(np.int8)
+        want = q.reshape(B, 3, H // 16, 16, W // 16, 16).transpose(0, 2, 4, 1, 3, 5).reshape(-1, 3 * 256)
+        got = K.quantize_patchify_u8(dev(u), mean.cuda(), std.cuda(), dev(np.array([s])), 16).cpu().numpy()
+        assert np.array_equal(got, want), (B, H, W)
+
+
 def test_embed_tokens_fast_matches_general(K):
     rng = np.random.default_rng(22)
     B, N, C = 3, 17, 64

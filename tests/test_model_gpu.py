@@ -83,6 +83,38 @@ def test_cuda_graph_replay_and_batch_sizes(tiny):
     assert eng.launches_per_forward == 3 + 8 * 12 + 3        # fused stem: quantize+patchify, patch GEMM, embed
 
 
+def test_graph_bound_to_a_stable_input_buffer(tiny):
+    """Feeding the same device buffer repeatedly binds a graph to its address (no copy into the engine's own input
+    buffer); new contents of that buffer, and other buffers in between, must still give their own logits."""
+    from ivit_b200.synth import synth_images
+    eng = tiny["eng"]
+    xa, xb = synth_images(3, seed=41), synth_images(3, seed=42)
+    wa, wb = OM.deit_forward(tiny["pack"], xa.numpy()), OM.deit_forward(tiny["pack"], xb.numpy())
+    buf = xa.cuda()
+    for _ in range(4):                                       # copy path, then bound graph
+        assert np.array_equal(eng(buf).cpu().numpy(), wa)
+    buf.copy_(xb.cuda())                                     # same address, new images
+    assert np.array_equal(eng(buf).cpu().numpy(), wb)
+    other = xa.cuda()                                        # a different address: copy path again
+    assert np.array_equal(eng(other).cpu().numpy(), wa)
+    assert np.array_equal(eng(buf).cpu().numpy(), wb)
+
+
+def test_uint8_input_path_matches_oracle(tiny):
+    """Decoded uint8 pixels in: ToTensor + Normalize (utils/data_utils.py:90-91) happen inside the stem kernel; the logits
+    must equal the oracle's on the images torch normalises in fp32 on the CPU."""
+    eng = tiny["eng"]
+    rng = np.random.default_rng(43)
+    u = torch.from_numpy(rng.integers(0, 256, (3, 3, 224, 224)).astype(np.uint8))
+    mean = torch.tensor([0.485, 0.456, 0.406])[None, :, None, None]
+    std = torch.tensor([0.229, 0.224, 0.225])[None, :, None, None]
+    x = u.to(torch.float32).div(255).sub(mean).div(std)
+    want = OM.deit_forward(tiny["pack"], x.numpy())
+    for _ in range(2):                                       # eager capture, then replay
+        assert np.array_equal(eng(u.cuda()).cpu().numpy(), want)
+    assert np.array_equal(eng(x.cuda()).cpu().numpy(), want)  # the fp32 entry still agrees
+
+
 def test_operator_level_path_matches_engine(tiny):
     """The drop-in operator classes (fp32 carrier in / out, one kernel per reference operator)
     give bit-identical logits to the fused engine."""
