@@ -4,21 +4,27 @@
 //   S = Q K^T  -> qact_attn1 (dyadic requant to int8) -> Shiftmax (IntSoftmax) -> P V -> attn.qact2
 //   reference call order: vit_quant.py:59-83; Shiftmax: quant_modules.py:469-497
 //
-// One CTA per (image, head), two CTAs per SM, 288 threads:
-//   warp 0      TMEM allocator; one thread drives TMA (Q m-tile, K: 64-byte rows, 64B swizzle) and the MMAs:
+// Persistent CTAs, two per SM, 4 * NP warps each (NP = 2 column parts per TMEM lane group by default); a CTA walks
+// the (image, head) items blockIdx.x, + gridDim.x, ...:
+//   control     one elected thread (lane 0 of the first warp of the last column part) drives TMA (Q m-tile, K, V:
+//               64-byte rows, 64B swizzle; next item's operands requested as soon as their buffers are free) and the MMAs:
 //               S[128 x NS] = Q K^T as 2 x tcgen05.mma.kind::i8 (K = 32 each) into TMEM columns [0, NS),
 //               later O_hi / O_lo [128 x 64] = P_hi V / P_lo V (u8 x s8, one MMA per 32 keys and byte plane)
 //               into TMEM columns [0, 64) / [64, 128) -- the S columns are dead by then.
-//   warps 1-8   "softmax" warps, two per TMEM lane group (each owns half of the columns of its 32 rows).  One
+//   all warps   "softmax" warps, NP per TMEM lane group (each owns a share of the columns of its 32 rows).  One
 //               thread = one query row: tcgen05.ld hands it its scores, so row max and row sum are thread-local
-//               (one shared-memory exchange with the partner thread of the other column half, no shuffles):
-//                 pass 1  scores -> requant -> int8, four per register (<= 28 registers), running packed max
-//                 pass 2  exponent LUT over max - q (257 entries, exact: the domain is int8 - int8), row sum, F
+//               (one shared-memory exchange with the partner threads of the other column parts, no shuffles):
+//                 pass 1  scores -> requant -> int8, four per register (<= 28 registers), row max (16x2 SIMD max)
+//                 pass 2  exponent LUT over max - q (256 entries, exact: the domain is int8 - int8; the lookup address
+//                         is one IDP.4A), row sum, F
 //                 pass 3  P = (E * F) >> 16, split into a high and a low byte plane, written to shared memory
 //                         in the K-major 128B-swizzled layout the MMA reads as its A operand
-//               then the output rows: (O_hi << 8) + O_lo -> requant -> int8 -> 32 bytes per thread to global.
-//   V is transposed once per head by the softmax warps into a K-major tile (keys contiguous); keys >= n_tok are
-//   zero there, so the probabilities of padding columns never need masking in the second product.
+//               then the output rows: (O_hi << 8) + O_lo -> requant -> int8 -> global.
+//   V is used as loaded (N-major B operand); keys >= n_tok are zero rows (TMA out-of-bounds fill), so the
+//   probabilities of padding columns never need masking in the second product.
+//   NP = 3 (IVIT_ATTN_PARTS=3: 12 warps per CTA at 80 registers, exponentials looked up again in pass 3) is kept as a
+//   measured alternative: 205 us against 153 us for NP = 2 at the DeiT-B bs=256 shape (the table lookups, not the
+//   warp count, limit the softmax phases).
 //
 // The mma.sync kernel in ivit_attn.cu stays as the general path (Swin bias / mask, 8-bit P, head_dim 32, slow-form
 // requants); this one is selected by the host when its preconditions hold, and computes bit-identical results.
@@ -42,10 +48,11 @@ struct AttnTcArgs {
     int sleep_ns;                 // back-off between mbarrier polls (IVIT_ATTN_SLEEP, default 0: plain polling)
 };
 
-constexpr int ATC_THREADS = 256;
-constexpr int ATC_CTRL = 128;         // control thread: lane 0 of warp 4 -- the upper column half has one chunk less, so this warp
-                                      // reaches the hand-over points first and the MMAs go out as soon as the last warp arrives
-constexpr int ATC_MAXCH = 7;          // 16-column chunks per column half (n_tok <= 224)
+// NP column parts per TMEM lane group: 4*NP warps per CTA.  NP = 2: 8 warps, 128 registers, the exponentials stay in
+// registers between passes 2 and 3.  NP = 3: 12 warps at <= 80 registers (24 warps per SM), shorter per-thread row
+// segments, exponentials looked up again in pass 3.  The control thread is lane 0 of the first warp of the LAST part
+// (it has the fewest chunks, so it reaches the hand-over points first).
+constexpr int ATC_MAXCH = 7;          // 16-column chunks per column part (n_tok <= 224)
 constexpr int ATC_SQ = 0;             // 128 rows x 64 B
 constexpr int ATC_SK = 8192;          // 224 rows x 64 B
 constexpr int ATC_SVT = 22528;        // V as loaded: 224 keys x 64 B (N-major B operand of the second product), 16 KB reserved
@@ -53,8 +60,9 @@ constexpr int ATC_SP = 38912;         // [plane 2][k-block 2][128 rows x 128 B]
 constexpr int ATC_LUTC = 8;           // copies of the exponent table (lane & 7 picks one): 2.1 instead of 3.5 bank conflicts per lookup
 constexpr int ATC_SE = 104448;        // [256][ATC_LUTC] int32
 constexpr int ATC_BAR = ATC_SE + 256 * ATC_LUTC * 4;   // 6 mbarriers + tmem pointer
-constexpr int ATC_SRED = ATC_BAR + 64;         // sum[2][128] uint32, max[2][128] uint8
-constexpr int ATC_SMEM = ATC_SRED + 1024 + 256 + 1024;  // + alignment slack; two CTAs per SM need <= 115200
+constexpr int ATC_SRED = ATC_SVT + 224 * 64;   // sum[3][128] uint32, max[3][128] uint8: the 2 KB the V tile leaves of its 16 KB
+constexpr int ATC_SMEM = ATC_BAR + 64 + 1024;  // + alignment slack; two CTAs per SM need <= 115200
+static_assert(ATC_SRED + 3 * 128 * 4 + 3 * 128 <= ATC_SP, "reduction scratch fits behind the V tile");
 static_assert(ATC_SMEM <= 115200, "two CTAs per SM");
 
 __device__ __forceinline__ uint64_t umma_desc_k_sw64(uint32_t smem_addr) {
@@ -90,8 +98,8 @@ __device__ __forceinline__ void mbar_wait_sleep(uint32_t bar, uint32_t parity, i
 }
 
 // NS16 = ceil(n_tok / 16): number of 16-column score chunks (compile-time so that the packed scores stay in registers)
-template <int NS16>
-__global__ void __launch_bounds__(ATC_THREADS, 2)
+template <int NS16, int NP>
+__global__ void __launch_bounds__(128 * NP, 2)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                     const int8_t* __restrict__ qkv, const AttnTcArgs p, int8_t* __restrict__ out) {
     extern __shared__ uint8_t atc_smem_raw[];
@@ -99,8 +107,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     uint8_t* smem = atc_smem_raw + (base - ptx::smem_u32(atc_smem_raw));
     const uint32_t sQ = base + ATC_SQ, sK = base + ATC_SK, sVt = base + ATC_SVT, sP = base + ATC_SP;
     int32_t* sE = reinterpret_cast<int32_t*>(smem + ATC_SE);
-    uint32_t* sRedSum = reinterpret_cast<uint32_t*>(smem + ATC_SRED);            // [2][128]
-    uint8_t* sRedMax = smem + ATC_SRED + 1024;                                   // [2][128]
+    uint32_t* sRedSum = reinterpret_cast<uint32_t*>(smem + ATC_SRED);            // [NP][128]
+    uint8_t* sRedMax = smem + ATC_SRED + 3 * 128 * 4;                            // [NP][128]
     const uint32_t bar = base + ATC_BAR;
     const uint32_t q_full = bar, k_full = bar + 8, s_full = bar + 16, p_ready = bar + 24, o_full = bar + 32, o_done = bar + 40, v_full = bar + 48;
     volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + ATC_BAR + 56);
@@ -117,9 +125,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
         ptx::mbar_init(q_full, 1);
         ptx::mbar_init(k_full, 1);
         ptx::mbar_init(s_full, 1);
-        ptx::mbar_init(p_ready, 8);
+        ptx::mbar_init(p_ready, 4 * NP);
         ptx::mbar_init(o_full, 1);
-        ptx::mbar_init(o_done, 8);
+        ptx::mbar_init(o_done, 4 * NP);
         ptx::mbar_init(v_full, 1);
         ptx::fence_barrier_init();
     }
@@ -137,6 +145,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     const uint32_t idesc_s = ptx::umma_idesc_i8(128, 16 * NS16, 1, 1);
     const uint32_t idesc_pv = ptx::umma_idesc_i8(128, 64, 0, 1) | (1u << 16);   // A = unsigned byte planes of P; B (V) N-major
     const int nk32 = (n_tok + 31) >> 5;
+    constexpr int ATC_CTRL = 128 * (NP - 1);
     if (tid == ATC_CTRL && (int)blockIdx.x < total) {
         const int b = (int)blockIdx.x / p.H, h = (int)blockIdx.x % p.H;
         ptx::mbar_arrive_expect_tx(k_full, 224 * 64);                           // K tile (keys >= n_tok read as zeros)
@@ -148,28 +157,30 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     }
     {
         // ================= softmax warps =================
-        const int sw = warp;                           // 0..7
         const int lg = warp & 3;                       // TMEM lanes [32*lg, +32)
-        const int half = sw >> 2;                      // column half
-        const int st = sw * 32 + lane;                 // 0..255
+        const int part = warp >> 2;                    // column part
+        const int st = tid;
         const int trow = lg * 32 + lane;               // row inside the m-tile
-        const int pair_bar = 1 + lg;                   // named barrier of the two warps sharing my rows
+        const int pair_bar = 1 + lg;                   // named barrier of the NP warps sharing my rows
 
         // ---- exponent LUT: sE[k][copy] = int_exp_shift(-k), k = max - q in [0, 255] ----
-        {
+        if (st < 256) {
             const int32_t e = (int32_t)shiftexp(-st, p.x0, p.inv_x0, p.n);
 #pragma unroll
             for (int j = 0; j < ATC_LUTC; ++j) sE[st * ATC_LUTC + j] = e;
         }
         __syncthreads();                                 // LUT visible to all warps
 
-        constexpr int NCH0 = (NS16 + 1) / 2, NCH1 = NS16 / 2;    // 16-column chunks of the lower / upper column half
-        constexpr int NS = 16 * NS16, H0 = 16 * NCH0;
+        // 16-column chunks per part: the first REM parts take one more than the others
+        constexpr int BASE = NS16 / NP, REM = NS16 % NP;
+        constexpr int NCH0 = BASE + (REM > 0 ? 1 : 0);            // most chunks any part has (compile-time bound of the loops)
+        constexpr int LASTP = BASE > 0 ? NP - 1 : REM - 1;        // the part that owns the last chunk (and with it the padding)
+        constexpr int NS = 16 * NS16;
         static_assert(NCH0 <= ATC_MAXCH, "n_tok <= 224");
-        const int c_begin = half ? H0 : 0;
-        const int nch = half ? NCH1 : NCH0;
+        const int nch = BASE + (part < REM ? 1 : 0);
+        const int c_begin = 16 * (part * BASE + (part < REM ? part : REM));
         const int npad_all = NS - n_tok;                          // 0..15 padding columns, all in the last chunk
-        const int npad = (half == (NCH1 > 0 ? 1 : 0)) ? npad_all : 0;   // ... which belongs to the upper half (if it has chunks)
+        const int npad = (part == LASTP) ? npad_all : 0;
         const uint32_t t_row = tmem_base + ((uint32_t)(lg * 32) << 16);
 
         // Persistent CTA: the (image, head) items of this CTA are processed back to back.  The operands of the next
@@ -243,7 +254,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
             // padding columns (all in the last chunk): forced to the smallest value (-128) so that they never raise the
             // max; their exponentials are taken out of the sum below; their probabilities meet zero V rows
             if (npad > 0) {
-                constexpr int CL = (NCH1 > 0 ? NCH1 : NCH0) - 1;                         // my last chunk (static index)
+                constexpr int CL = (BASE > 0 ? BASE : 1) - 1;                            // my last chunk (static index)
 #pragma unroll
                 for (int w = 0; w < 4; ++w) {
                     const int valid = 16 - npad_all - 4 * w;                             // columns of this word that exist
@@ -262,9 +273,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
             }
             const int32_t mxs = max(max((int32_t)mo >> 24, (int32_t)(mo << 16) >> 24), max((int32_t)me2 >> 24, (int32_t)(me2 << 16) >> 24));
             uint32_t mxu = (uint32_t)(mxs + 128);                                       // row max of q + 128 over my columns
-            sRedMax[half * 128 + trow] = (uint8_t)mxu;
-            asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
-            mxu = max(mxu, (uint32_t)sRedMax[(half ^ 1) * 128 + trow]);
+            sRedMax[part * 128 + trow] = (uint8_t)mxu;
+            asm volatile("bar.sync %0, %1;" ::"r"(pair_bar), "n"(32 * NP) : "memory");
+#pragma unroll
+            for (int pp = 0; pp < NP; ++pp) mxu = max(mxu, (uint32_t)sRedMax[pp * 128 + trow]);
             // ---- pass 2: exponentials E(max - q) = sE[max - q], row sum (E < 2^23, <= 112 terms per thread: 32-bit) ----
             // lookup address = table + 32 * (max - q) + 4 * copy: ONE dot-product instruction per element (IDP.4A on the
             // FMA pipe; the selector holds -32 in byte i) instead of a byte extract plus a multiply-add
@@ -275,6 +287,20 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
                 uint32_t v;
                 asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));   // read-only table: free to schedule
                 return v;
+            };
+            // pass 3 needs the same exponentials again.  NP == 2: the identical (pure) asm lets the compiler keep the values
+            // of pass 2 in registers (128-register budget).  NP == 3: a textually different asm, so that they are looked up
+            // again instead of occupying ~80 registers across the hand-over (80-register budget).
+            auto lut3 = [&](uint32_t u, int i) -> uint32_t {
+                if constexpr (NP == 2) {
+                    return lut(u, i);
+                } else {
+                    int32_t addr;
+                    asm("dp4a.s32.s32 %0, %1, %2, %3; // pass 3" : "=r"(addr) : "r"(u), "r"((uint32_t)(0x100 - 4 * ATC_LUTC) << (8 * i)), "r"(pEq));
+                    uint32_t v;
+                    asm("ld.shared.u32 %0, [%1]; // pass 3" : "=r"(v) : "r"(addr));
+                    return v;
+                }
             };
             uint32_t sum = 0;
 #pragma unroll
@@ -288,9 +314,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
                 }
             }
             sum -= (uint32_t)npad * lut(0x80808080u, 0);                                 // padding columns carry q = -128
-            sRedSum[half * 128 + trow] = sum;
-            asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
-            unsigned long long S = (unsigned long long)sum + sRedSum[(half ^ 1) * 128 + trow];
+            sRedSum[part * 128 + trow] = sum;
+            asm volatile("bar.sync %0, %1;" ::"r"(pair_bar), "n"(32 * NP) : "memory");
+            unsigned long long S = 0;
+#pragma unroll
+            for (int pp = 0; pp < NP; ++pp) S += sRedSum[pp * 128 + trow];
             const uint32_t S32 = S > 2147483647ULL ? 2147483647u : (uint32_t)S;   // clamp_max_(2**31-1)
             const uint32_t F = 2147483647u / (S32 ? S32 : 1u);                    // <= 65535 (host-checked: E(0) >= 2^15)
             const uint32_t Fs = F << 16;                                          // P = (E*F) >> 16 == umulhi(E, F << 16)
@@ -305,8 +333,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
                         const uint32_t u = sc[4 * c + w];
                         // P < 2^16: two of them share a word through one multiply-add (FMA pipe), then one byte
                         // permute per plane
-                        const uint32_t P01 = __umulhi(lut(u, 1), Fs) * 65536u + __umulhi(lut(u, 0), Fs);
-                        const uint32_t P23 = __umulhi(lut(u, 3), Fs) * 65536u + __umulhi(lut(u, 2), Fs);
+                        const uint32_t P01 = __umulhi(lut3(u, 1), Fs) * 65536u + __umulhi(lut3(u, 0), Fs);
+                        const uint32_t P23 = __umulhi(lut3(u, 3), Fs) * 65536u + __umulhi(lut3(u, 2), Fs);
                         lo[w] = __byte_perm(P01, P23, 0x6420);
                         hi[w] = __byte_perm(P01, P23, 0x7531);
                     }
@@ -346,37 +374,51 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
                 ptx::mbar_arrive_expect_tx(v_full, 224 * 64);
                 ptx::tma_load_3d(sVt, &tmap_k, v_full, 2 * HD + nh * 64, 0, nb);
             }
-            uint4* dst = reinterpret_cast<uint4*>(out + ((long long)b * n_tok + row) * (long long)HD + h * 64 + 32 * half);
+            // my share of the 64 output channels: NP == 2: 32 + 32 (two 16-channel steps); NP == 3: 24 + 24 + 16 (8-channel steps)
+            constexpr int OSTEP = (NP == 2) ? 16 : 8;
+            const int ch0 = (NP == 2) ? 32 * part : 24 * part;
+            const int nstep = (NP == 2) ? 2 : (part < 2 ? 3 : 2);
+            int8_t* dst = out + ((long long)b * n_tok + row) * (long long)HD + h * 64 + ch0;
             if (!act) {
                 __syncwarp();
                 if (lane == 0) ptx::mbar_arrive(o_done);
                 continue;
             }
 #pragma unroll
-            for (int q = 0; q < 2; ++q) {                                      // 16 of my 32 output channels at a time
-                uint32_t oh[16], ol[16];
-                ptx::tmem_ld_32x32b_x16(t_row + (uint32_t)(32 * half + 16 * q), oh);
-                ptx::tmem_ld_32x32b_x16(t_row + (uint32_t)(64 + 32 * half + 16 * q), ol);
-                ptx::tmem_ld_wait();
-                if (q == 1) {                                                  // last TMEM read of this m-tile
-                    ptx::tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) ptx::mbar_arrive(o_done);
-                }
-                uint32_t ow[4];
-#pragma unroll
-                for (int w = 0; w < 4; ++w) {
-                    int32_t o[4];
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const int32_t z = ((int32_t)oh[4 * w + e] << 8) + (int32_t)ol[4 * w + e];
-                        o[e] = (int32_t)(((long long)z * (long long)p.m_o + p.half_o) >> 32) >> p.sh_o;
+            for (int q = 0; q < ((NP == 2) ? 2 : 3); ++q) {
+                if (q < nstep) {
+                    uint32_t oh[OSTEP], ol[OSTEP];
+                    if constexpr (OSTEP == 16) {
+                        ptx::tmem_ld_32x32b_x16(t_row + (uint32_t)(ch0 + 16 * q), oh);
+                        ptx::tmem_ld_32x32b_x16(t_row + (uint32_t)(64 + ch0 + 16 * q), ol);
+                    } else {
+                        ptx::tmem_ld_32x32b_x8(t_row + (uint32_t)(ch0 + 8 * q), oh);
+                        ptx::tmem_ld_32x32b_x8(t_row + (uint32_t)(64 + ch0 + 8 * q), ol);
                     }
-                    uint32_t hi2;
-                    asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, %3;" : "=r"(hi2) : "r"(o[3]), "r"(o[2]), "r"(0));
-                    asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, %3;" : "=r"(ow[w]) : "r"(o[1]), "r"(o[0]), "r"(hi2));
+                    ptx::tmem_ld_wait();
+                    if (q == nstep - 1) {                                      // last TMEM read of this m-tile
+                        ptx::tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) ptx::mbar_arrive(o_done);
+                    }
+                    uint32_t ow[OSTEP / 4];
+#pragma unroll
+                    for (int w = 0; w < OSTEP / 4; ++w) {
+                        int32_t o[4];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const int32_t z = ((int32_t)oh[4 * w + e] << 8) + (int32_t)ol[4 * w + e];
+                            o[e] = (int32_t)(((long long)z * (long long)p.m_o + p.half_o) >> 32) >> p.sh_o;
+                        }
+                        uint32_t hi2;
+                        asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, %3;" : "=r"(hi2) : "r"(o[3]), "r"(o[2]), "r"(0));
+                        asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, %3;" : "=r"(ow[w]) : "r"(o[1]), "r"(o[0]), "r"(hi2));
+                    }
+                    if (row < n_tok) {
+                        if constexpr (OSTEP == 16) reinterpret_cast<uint4*>(dst)[q] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+                        else reinterpret_cast<uint2*>(dst)[q] = make_uint2(ow[0], ow[1]);
+                    }
                 }
-                if (row < n_tok) dst[q] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
             }
         }
         }
@@ -427,17 +469,22 @@ int launch_attention_tc(ivit_ctx* ctx, const int8_t* qkv, const ivit_attn_params
     if (rc) return rc;
     rc = make_tmap_qkv(ctx, &tk, qkv, ap->n_seq, ap->n_tok, ld, 224);
     if (rc) return rc;
+    static const char* parts_env = getenv("IVIT_ATTN_PARTS");
+    const int parts = (parts_env && atoi(parts_env) == 3) ? 3 : 2;
     const int items = ap->n_seq * ap->n_heads;
     const int grid = items < 2 * ctx->num_sms ? items : 2 * ctx->num_sms;       // persistent: two resident CTAs per SM
 #define ATC_CASE(N)                                                                                                   \
     case N: {                                                                                                         \
         static bool attr_set = false;                                                                                 \
         if (!attr_set) {                                                                                              \
-            IVIT_CUDA_OK(cudaFuncSetAttribute(attention_tc_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATC_SMEM)); \
-            IVIT_CUDA_OK(cudaFuncSetAttribute(attention_tc_kernel<N>, cudaFuncAttributePreferredSharedMemoryCarveout, 100)); \
+            IVIT_CUDA_OK(cudaFuncSetAttribute(attention_tc_kernel<N, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATC_SMEM)); \
+            IVIT_CUDA_OK(cudaFuncSetAttribute(attention_tc_kernel<N, 2>, cudaFuncAttributePreferredSharedMemoryCarveout, 100)); \
+            IVIT_CUDA_OK(cudaFuncSetAttribute(attention_tc_kernel<N, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATC_SMEM)); \
+            IVIT_CUDA_OK(cudaFuncSetAttribute(attention_tc_kernel<N, 3>, cudaFuncAttributePreferredSharedMemoryCarveout, 100)); \
             attr_set = true;                                                                                          \
         }                                                                                                             \
-        attention_tc_kernel<N><<<grid, ATC_THREADS, ATC_SMEM, s>>>(tq, tk, qkv, a, out);                              \
+        if (parts == 3) attention_tc_kernel<N, 3><<<grid, 384, ATC_SMEM, s>>>(tq, tk, qkv, a, out);                   \
+        else attention_tc_kernel<N, 2><<<grid, 256, ATC_SMEM, s>>>(tq, tk, qkv, a, out);                              \
     } break;
     switch (a.ns >> 4) {
         ATC_CASE(1) ATC_CASE(2) ATC_CASE(3) ATC_CASE(4) ATC_CASE(5) ATC_CASE(6) ATC_CASE(7)
