@@ -58,8 +58,65 @@ def quantize_f32(x: torch.Tensor, scale: torch.Tensor, bits: int, per_row: bool 
     return out
 
 
+# ---------------------------------------------------------------------------------------------------------------
+# Integer shadows of carriers.  The operator API passes fp32/fp64 "integer x scale" carriers between modules
+# (quant_modules.py: every forward returns x_int * scaling_factor and the next one divides it out again).  Every
+# carrier this package creates from an integer tensor remembers that tensor: a consumer that is handed the carrier --
+# or ANY VIEW of it (reshape / permute / transpose / slicing share the storage, so the same sizes, strides and offset
+# address the same elements of the integer tensor) -- together with the same scale tensor gets the integers back
+# without the divide-and-round pass (29 % of an operator-level DeiT forward).  A shadow is valid only while the carrier
+# base tensor object is alive and unmodified (weak reference + version counter) and for the scale it was made with
+# (the scale tensor is kept alive, so its address cannot be reused); copies (cat, contiguous() of a permuted view,
+# arithmetic on the carrier) have no shadow and take the conversion kernel.  IVIT_SHADOW=0 disables the mechanism.
+# ---------------------------------------------------------------------------------------------------------------
+import os as _os
+import weakref as _weakref
+
+_SHADOW = {}
+_SHADOW_ON = _os.environ.get("IVIT_SHADOW", "1") != "0"
+_WIDER = {torch.int8: (torch.int8, torch.int16, torch.int32), torch.int16: (torch.int16, torch.int32),
+          torch.int32: (torch.int32,)}
+
+
+def _shadow_register(carrier: torch.Tensor, q: torch.Tensor, s: torch.Tensor):
+    if not _SHADOW_ON or carrier._base is not None or q.shape != carrier.shape or not q.is_contiguous():
+        return
+    key = id(carrier)
+    _SHADOW[key] = (_weakref.ref(carrier, lambda _r, k=key: _SHADOW.pop(k, None)), carrier._version, q, s, s._version)
+
+
+def _shadow_lookup(x: torch.Tensor, s: torch.Tensor):
+    """The integer tensor behind carrier `x` (a view with x's sizes / strides) if x is a registered carrier, or a view
+    of one, and `s` is the scale it was made with; else None."""
+    if not _SHADOW_ON:
+        return None
+    base = x._base if x._base is not None else x
+    e = _SHADOW.get(id(base))
+    if e is None:
+        return None
+    ref, ver, q, s0, sver = e
+    if ref() is not base or base._version != ver or s0._version != sver or x.dtype != base.dtype:
+        return None
+    if s.data_ptr() != s0.data_ptr() or s.numel() != s0.numel() or s.dtype != s0.dtype:
+        return None
+    if x is base:
+        return q
+    return q.as_strided(x.size(), x.stride(), x.storage_offset())
+
+
+def carrier_to_int_any(x: torch.Tensor, s: torch.Tensor):
+    """Integers of carrier x in whatever integer type they were produced in (shadow hit: no conversion pass), else int32."""
+    qv = _shadow_lookup(x, s)
+    if qv is not None:
+        return qv.contiguous()
+    return carrier_to_int(x, s, torch.int32)
+
+
 def carrier_to_int(x: torch.Tensor, s: torch.Tensor, out_dtype=torch.int32):
     """z = RNE(x / s[c]); x is an fp32 (or fp64, see int_to_carrier) carrier."""
+    qv = _shadow_lookup(x, s)
+    if qv is not None and out_dtype in _WIDER.get(qv.dtype, ()):
+        return qv.contiguous() if qv.dtype == out_dtype else qv.to(out_dtype)
     x = x.contiguous()
     if x.dtype not in (torch.float32, torch.float64):
         x = x.float()
@@ -74,11 +131,13 @@ def carrier_to_int(x: torch.Tensor, s: torch.Tensor, out_dtype=torch.int32):
 def int_to_carrier(q: torch.Tensor, s: torch.Tensor, out_dtype=torch.float32):
     """x = q * s[c].  out_dtype float64 keeps integers beyond 2^24 exact (IntLayerNorm outputs)."""
     q = q.contiguous()
+    s_arg = s                                              # the caller's scale tensor: identity of the shadow
     s = s.reshape(-1).contiguous().float()
     cols = q.shape[-1]
     out = torch.empty(q.shape, dtype=out_dtype, device=q.device)
     call("ivit_int_to_carrier", context(q.device), ptr(q), TORCH2IVIT[q.dtype], q.numel() // cols, cols,
          ptr(s), s.numel(), TORCH2IVIT[out_dtype], ptr(out))
+    _shadow_register(out, q, s_arg)
     return out
 
 

@@ -100,13 +100,13 @@ class fixedpoint_mul:
             raise NotImplementedError("per-channel scales on 4-D activations (dim 1) are not used by the models")
         if s_in.numel() not in (1, pre_act.shape[-1]):
             raise ValueError("scaling factor has %d entries for last dim %d" % (s_in.numel(), pre_act.shape[-1]))
-        z = K.carrier_to_int(pre_act, s_in, torch.int32)
+        z = K.carrier_to_int_any(pre_act, s_in)              # integer shadow of the carrier when there is one
         me = K.dyadic_device(s_in, z_scaling_factor)
         w = me1 = None
         if identity is not None:
             s_id = identity_scaling_factor.reshape(-1)
             if identity.numel() > pre_act.numel() or pre_act.numel() % identity.numel() != 0:
                 raise ValueError("identity shape %s does not broadcast to %s" % (tuple(identity.shape), tuple(pre_act.shape)))
-            w = K.carrier_to_int(identity, s_id, torch.int32)
+            w = K.carrier_to_int_any(identity, s_id)
             me1 = K.dyadic_device(s_id, z_scaling_factor)
         return K.requant(z, me, int(bit_num), w, me1)
