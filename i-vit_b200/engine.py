@@ -285,3 +285,28 @@ def _gelu_into(q, x0, me, out):
     cols = q.shape[-1]
     K.call("ivit_shiftgelu", K.context(q.device), K.ptr(q), K.TORCH2IVIT[q.dtype], q.numel() // cols, cols,
            int(x0), 23, K.ptr(me), 8, K.TORCH2IVIT[out.dtype], K.ptr(out))
+
+
+def accelerate(model: torch.nn.Module, device="cuda"):
+    """One-line adoption for code written against the reference's API: ``model = ivit_b200.engine.accelerate(model)``.
+
+    ``model`` is a calibrated, frozen DeiT/ViT built on the reference's operator classes (the reference's own
+    ``models/vit_quant.py`` object, or this package's ``deit`` graph).  Its static integer parameters are exported once
+    (``pack.export_deit``) and ``model.forward`` is replaced by the fused engine: same logits bit for bit as the
+    operator-by-operator forward (tests/test_model_gpu.py), ~30x its throughput (fp32 carriers never touch HBM).
+    Calling ``unfreeze_model`` / changing weights afterwards requires ``accelerate`` again; the original forward is kept
+    as ``model._ivit_forward_operator_level``."""
+    from .pack import export_deit
+    for m in model.modules():
+        if type(m).__name__ == "QuantAct" and getattr(m, "running_stat", False):
+            raise RuntimeError("accelerate: the model is not frozen (QuantAct.running_stat is set); call freeze_model first")
+    eng = Engine(export_deit(model), device)
+    model._ivit_engine = eng
+    model._ivit_forward_operator_level = model.forward
+
+    def forward(x):
+        return eng(x.to(eng.device, non_blocking=True)).clone()
+
+    model.forward = forward
+    return model
+

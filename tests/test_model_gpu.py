@@ -146,6 +146,21 @@ def test_operator_level_path_matches_engine(tiny):
     assert np.array_equal(y.cpu().numpy(), tiny["logits"])
 
 
+def test_accelerate_replaces_the_forward_with_the_engine(tiny):
+    """engine.accelerate(model): same logits as the operator-by-operator forward of the same model object."""
+    import copy
+    from ivit_b200.engine import accelerate
+    model = copy.deepcopy(tiny["model"]).cuda()
+    x = tiny["x"].cuda()
+    with torch.no_grad():
+        slow = model(x)
+        accelerate(model)
+        fast = model(x)
+    assert hasattr(model, "_ivit_engine")
+    assert np.array_equal(fast.cpu().numpy(), tiny["logits"])
+    assert float((slow.float() - fast).abs().max()) <= 2e-6 * float(fast.abs().max())   # head carrier: fp32 product of the same integers
+
+
 def test_operator_level_calibration_pass_runs(tiny):
     """One unfrozen forward (running_stat=True, quant_modules.py:170-189) through the operator
     classes on the GPU sets every executed QuantAct's range."""
