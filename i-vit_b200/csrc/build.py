@@ -25,15 +25,17 @@ def stale() -> bool:
     return any(os.path.getmtime(os.path.join(HERE, f)) > t for f in SRCS + HDRS + ["build.py"])
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
+def build(force: bool = False, verbose: bool = False, diag: bool = False) -> str:
+    """diag: compile the GEMM's IVIT_GEMM_DEBUG diagnostics in (tools/gemm_bench.py experiments; slower production path)."""
     if not (force or stale()):
         return OUT
+    flags = FLAGS + (["-DIVIT_GEMM_DIAG"] if diag else [])
     objs = []
     procs = []
     for s in SRCS:
         o = os.path.join(HERE, s.replace(".cu", ".o"))
         objs.append(o)
-        procs.append((s, subprocess.Popen([NVCC, *FLAGS, "-c", os.path.join(HERE, s), "-o", o],
+        procs.append((s, subprocess.Popen([NVCC, *flags, "-c", os.path.join(HERE, s), "-o", o],
                                           stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     log = []
     bad = False
@@ -53,4 +55,4 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build(force="--force" in sys.argv or "--diag" in sys.argv, verbose="-v" in sys.argv, diag="--diag" in sys.argv))

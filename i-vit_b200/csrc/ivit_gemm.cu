@@ -83,6 +83,15 @@ __device__ __forceinline__ int32_t add_sat_s32(int32_t a, int32_t b) {
     return r;
 }
 
+// The IVIT_GEMM_DEBUG diagnostics (skip epilogue work / operand loads / residual loads / output stores) are compiled in only
+// with -DIVIT_GEMM_DIAG (python i-vit_b200/csrc/build.py --diag): even never-taken branches in the chunk loop cost the
+// production kernel several per cent (register allocation / code layout).
+#ifdef IVIT_GEMM_DIAG
+#define IVIT_DBG(args, bit) ((args).debug & (bit))
+#else
+#define IVIT_DBG(args, bit) 0
+#endif
+
 struct GemmArgs {
     int M, N, K;
     int mode_bits;                    // clamp bits for requant modes
@@ -137,7 +146,7 @@ template <int CW>
 __device__ __forceinline__ void load_residual(const GemmArgs& args, int row, bool row_ok, int ncol0, uint32_t (&rr)[CW / 2]) {
 #pragma unroll
     for (int j = 0; j < CW / 2; ++j) rr[j] = 0u;
-    if (!args.residual || !row_ok || ncol0 >= args.N || (args.debug & 4)) return;   // debug & 4: diagnostics, residual reads as zero
+    if (!args.residual || !row_ok || ncol0 >= args.N || (IVIT_DBG(args, 4))) return;   // debug & 4: diagnostics, residual reads as zero
     const int16_t* res = reinterpret_cast<const int16_t*>(args.residual) + (long long)row * args.res_ld + ncol0;
     if (ncol0 + CW <= args.N && ((reinterpret_cast<uintptr_t>(res) & 15) == 0)) {
 #pragma unroll
@@ -466,7 +475,7 @@ gemm_i8_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
                     ptx::mbar_wait(empty_bar(stage), phase ^ 1u);    // the MMAs that read this stage have retired
                     const uint32_t a_dst = stage_base + stage * S::STAGE_BYTES;
                     const uint32_t b_dst = a_dst + S::A_BYTES;
-                    if (args.debug & 2) {                            // diagnostics: mainloop without operand traffic
+                    if (IVIT_DBG(args, 2)) {                            // diagnostics: mainloop without operand traffic
                         if (ry == 0) ptx::mbar_arrive(full_bar(stage));
                     } else if (PAIR) {
                         // the leader's barrier collects the bytes of both CTAs' loads
@@ -677,7 +686,7 @@ gemm_i8_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
             ptx::mbar_wait(tfull_bar(as), aphase);
             ptx::tc_fence_after();
 
-            const bool work = (c_begin < c_end) && !(args.debug & 1);    // debug & 1: diagnostics, epilogue does nothing
+            const bool work = (c_begin < c_end) && !IVIT_DBG(args, 1);    // debug & 1: diagnostics, epilogue does nothing
             if (work) {
                 tmem_ld_chunk<CW>(t_row + (uint32_t)c_begin, ra);
                 ptx::tmem_ld_wait();
@@ -746,7 +755,7 @@ gemm_i8_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
                 // (32-row boxes; coalesced, asynchronous, clips the M / N tails).  Each warp stores and later waits
                 // for its own rows only, one tile later: no CTA-wide synchronisation around the store.
                 if (NBOX_W == 0) asm volatile("bar.sync %0, 64;" ::"r"(box_bar) : "memory");
-                if (lane == 0 && box_leader && !(args.debug & 8)) {      // debug & 8: diagnostics, nothing is stored
+                if (lane == 0 && box_leader && !IVIT_DBG(args, 8)) {      // debug & 8: diagnostics, nothing is stored
                     const int r0 = m0 + lane_group * 32;
                     constexpr int NB = NBOX_W > 0 ? NBOX_W : 1;
 #pragma unroll
