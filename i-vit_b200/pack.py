@@ -197,6 +197,91 @@ def export_deit(model) -> Pack:
     return Pack(meta, A)
 
 
+def export_swin(model) -> Pack:
+    """Walk a calibrated + frozen Swin (``SwinTransformer`` of swin.py or of the reference's swin_quant.py) in forward
+    order (swin_quant.py:539-564, 251-301, 121-169, 328-349; layers_quant.py:144-153, 184-196) and emit the static
+    integer parameters.  Per block: the gathered relative-position bias (int8 [heads, N, N], swin_quant.py:142-147) and,
+    for shifted blocks, the window mask as 0/1 flags (int8 [windows, N, N], :223-247)."""
+    A = {}
+    pe = model.patch_embed
+    P = int(pe.patch_size[0])
+    img = int(pe.img_size[0])
+    C0 = int(model.embed_dim)
+    if model.absolute_pos_embed is not None:
+        raise NotImplementedError("export_swin: absolute position embedding (ape=True) is not used by the model zoo")
+    layers = list(model.layers)
+    meta = dict(arch="swin", embed_dim=C0, patch=P, img_size=img, in_chans=int(pe.proj.in_channels),
+                num_classes=int(model.head.out_features), grid=int(pe.grid_size[0]),
+                depths=[len(l.blocks) for l in layers], num_heads=[int(l.blocks[0].attn.num_heads) for l in layers],
+                window=[int(l.blocks[0].window_size) for l in layers],
+                shift=[[int(b.shift_size) for b in l.blocks] for l in layers],
+                mlp_hidden=[int(l.blocks[0].mlp.fc1.out_features) for l in layers],
+                softmax_bits=int(layers[0].blocks[0].attn.log_int_softmax.output_bit))
+
+    s_img = _act_scale(model.qact_input)                                   # swin_quant.py:540
+    A["qact_input.scale"] = s_img.numpy().astype(np.float32)
+    s_conv = _linear(A, "patch_embed.proj", pe.proj, s_img)                # layers_quant.py:190
+    s = _qact(A, "patch_embed.qact_before_norm", pe.qact_before_norm, s_conv)   # :193
+    s_ln = _layernorm(A, "patch_embed.norm", pe.norm, C0)                  # :194
+    s_pe = _qact(A, "patch_embed.qact", pe.qact, s_ln)                     # :195 (16 bit)
+    s_x = _qact(A, "qact1", model.qact1, s_pe)                             # swin_quant.py:546
+
+    for li, layer in enumerate(layers):
+        for bi, blk in enumerate(layer.blocks):
+            p = "layers.%d.blocks.%d." % (li, bi)
+            C = int(blk.dim)
+            s_ln = _layernorm(A, p + "norm1", blk.norm1, C)                # :256
+            s = _qact(A, p + "qact1", blk.qact1, s_ln)                     # :257
+            at = blk.attn
+            s_qkv_acc = _linear(A, p + "attn.qkv", at.qkv, s)              # :128
+            s_1 = _qact(A, p + "attn.qact1", at.qact1, s_qkv_acc)          # :129
+            s_scores = (s_1 * s_1) * at.scale                              # :135-138
+            s_a = _qact(A, p + "attn.qact_attn1", at.qact_attn1, s_scores)  # :140
+            s_t = _act_scale(at.qact_table)                                # :142-143 (input quantisation of the table)
+            A[p + "attn.qact_table.scale"] = s_t.numpy().astype(np.float32)
+            table = at.relative_position_bias_table.detach().cpu().float()
+            tq = _quantize(table, s_t, at.qact_table.activation_bit).to(torch.int8)
+            A[p + "attn.qact_table.table_integer"] = tq.numpy()
+            N = int(at.window_size[0] * at.window_size[1])
+            idx = at.relative_position_index.detach().cpu().reshape(-1).long()
+            A[p + "attn.bias_integer"] = tq[idx].view(N, N, -1).permute(2, 0, 1).contiguous().numpy()   # :144-147
+            s_2 = _qact(A, p + "attn.qact2", at.qact2, s_a, s_t)           # :149 (bias as the identity branch)
+            if blk.attn_mask is not None:
+                A[p + "attn_mask"] = (blk.attn_mask.detach().cpu() != 0).to(torch.int8).numpy()   # :223-247, -100 where set
+            _x0(A, p + "attn.log_int_softmax.x0", s_2)                     # :156
+            s_p = torch.tensor([1 / 2 ** (at.log_int_softmax.output_bit - 1)], dtype=torch.float32)
+            s_pv = s_p * s_1                                               # :161-162
+            s = _qact(A, p + "attn.qact3", at.qact3, s_pv)                 # :164
+            s_proj = _linear(A, p + "attn.proj", at.proj, s)               # :166
+            s_a4 = _qact(A, p + "attn.qact4", at.qact4, s_proj)            # :167 (16 bit)
+            s_x2 = _qact(A, p + "qact2", blk.qact2, s_a4, s_x)             # :293 residual
+            s_ln = _layernorm(A, p + "norm2", blk.norm2, C)                # :295
+            s = _qact(A, p + "qact3", blk.qact3, s_ln)                     # :296
+            mlp = blk.mlp
+            s_fc1 = _linear(A, p + "mlp.fc1", mlp.fc1, s)                  # layers_quant.py:145
+            s_g = _qact(A, p + "mlp.qact_gelu", mlp.qact_gelu, s_fc1)      # :146
+            _x0(A, p + "mlp.act.x0", s_g * 1.702)                          # quant_modules.py:427, 414
+            s_go = s_g * torch.tensor([1 / 2 ** (mlp.act.output_bit - 1)], dtype=torch.float32)
+            s = _qact(A, p + "mlp.qact1", mlp.qact1, s_go)                 # layers_quant.py:148
+            s_fc2 = _linear(A, p + "mlp.fc2", mlp.fc2, s)                  # :150
+            s_m2 = _qact(A, p + "mlp.qact2", mlp.qact2, s_fc2)             # :151 (16 bit)
+            s_x = _qact(A, p + "qact4", blk.qact4, s_m2, s_x2)             # swin_quant.py:299 residual
+        if layer.downsample is not None:
+            d = "layers.%d.downsample." % li
+            ds = layer.downsample
+            s_ln = _layernorm(A, d + "norm", ds.norm, 4 * int(ds.dim))     # :344
+            s = _qact(A, d + "qact1", ds.qact1, s_ln)                      # :345
+            s_red = _linear(A, d + "reduction", ds.reduction, s)           # :346 (no bias)
+            s_x = _qact(A, d + "qact2", ds.qact2, s_red)                   # :347
+
+    Cf = int(model.num_features)
+    s_ln = _layernorm(A, "norm", model.norm, Cf)                           # :552
+    s = _qact(A, "qact2", model.qact2, s_ln)                               # :553
+    s = _qact(A, "qact3", model.qact3, s)                                  # :555 (on the token average)
+    _linear(A, "head", model.head, s)                                      # :562
+    return Pack(meta, A)
+
+
 def check_supported(pack: Pack):
     """Domain checks of the fused kernels, raised at freeze time rather than deep inside a launch."""
     for k, v in pack.arrays.items():

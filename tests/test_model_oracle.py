@@ -93,3 +93,64 @@ def test_pack_from_reference_model_is_identical(tiny):
     assert pref.meta == pack.meta
     for k in pack.arrays:
         assert np.array_equal(pref[k], pack[k]), k
+
+
+# ------------------------------------------------------------------------------------------------ Swin
+@pytest.fixture(scope="module")
+def swin():
+    from ivit_b200.calib import build_synthetic
+    from ivit_b200.pack import export_swin
+    from ivit_b200.synth import synth_images
+    model = build_synthetic("swin_tiny_patch4_window7_224")
+    pack = export_swin(model)
+    gold = np.load(os.path.join(GOLDEN, "swin_tiny_b1.npz"))
+    x = synth_images(int(gold["batch"]), seed=int(gold["seed_images"])).numpy()
+    return model, pack, gold, x
+
+
+def test_swin_oracle_reproduces_reference_at_every_boundary(swin):
+    """Swin-tiny (BASELINE.json config 4): frozen pack + oracle forward -- windows, cyclic shift + mask, relative-position
+    bias as a QuantAct identity, patch merging, token average -- against the digests of the reference's own run with
+    exact-carrier hooks at all 298 operator boundaries (tests/golden/swin_tiny_b1.npz)."""
+    model, pack, gold, x = swin
+    cap = {}
+    logits = OM.swin_forward(pack, x, cap)
+    want = dict(zip(gold["names"].tolist(), gold["digests"].tolist()))
+    for name, arr in cap.items():
+        assert name in want, "oracle boundary %s is not a reference module" % name
+        assert digest(arr) == want[name], "first divergence from the reference at %s" % name
+    assert set(want) <= set(cap), "boundaries not restated by the oracle: %s" % sorted(set(want) - set(cap))[:5]
+    assert len(cap) >= 298
+    err = np.abs(logits.astype(np.float64) - gold["logits"].astype(np.float64)).max()
+    assert err <= 2e-6 * np.abs(gold["logits"]).max()
+    for key in gold.files:
+        if key.startswith("full/"):
+            assert np.array_equal(cap[key[5:]].reshape(gold[key].shape), gold[key])
+    # shifted blocks really exercised the mask path
+    assert any(k.endswith("attn_mask") for k in pack.arrays)
+
+
+def test_swin_pack_roundtrip_and_reference_model(swin, tmp_path):
+    from ivit_b200.pack import Pack, export_swin
+    _, pack, _, _ = swin
+    f = str(tmp_path / "s.npz")
+    pack.save(f)
+    p2 = Pack.load(f)
+    assert p2.meta == pack.meta and all(np.array_equal(p2[k], pack[k]) for k in pack.arrays)
+    sys.path.insert(0, GOLDEN)
+    import refload
+    if not refload.have_reference():
+        pytest.skip("reference checkout not present (GPU box)")
+    from ivit_b200.calib import apply_calibration, load_calibration
+    from ivit_b200.synth import synth_parameters
+    m = refload.load()
+    with torch.no_grad():
+        ref = m.swin_tiny_patch4_window7_224(pretrained=False).eval()
+        cal = load_calibration("swin_tiny_patch4_window7_224")
+        assert synth_parameters(ref, 0) == cal["weights_sha256"]
+        apply_calibration(ref, cal["ranges"])
+        pref = export_swin(ref)                      # the exporter reads the REFERENCE's model object
+    assert pref.meta == pack.meta
+    for k in pack.arrays:
+        assert np.array_equal(pref[k], pack[k]), k
+
