@@ -388,6 +388,47 @@ def test_attention(K, n_seq, n_tok, H, D, p_bits):
     assert_equal(got, want, "attention n_tok=%d H=%d D=%d P%d" % (n_tok, H, D, p_bits))
 
 
+@pytest.mark.parametrize("n_win,H,with_mask", [(4, 3, True), (1, 6, False), (16, 2, True)])
+def test_attention_swin_bias_and_mask(K, n_win, H, with_mask):
+    """Window attention of Swin in the fused kernel (swin_quant.py:135-164): scores -> qact_attn1 -> qact2 with the
+    relative-position bias as identity -> shifted-window mask -> 8-bit Shiftmax -> P V -> qact3, 49 tokens, head_dim 32."""
+    n_tok, D = 49, 32
+    n_seq = 2 * n_win
+    rng = np.random.default_rng(100 * n_win + H)
+    qkv = rng.integers(-128, 128, (n_seq * n_tok, 3 * H * D)).astype(np.int8)
+    bias = rng.integers(-128, 128, (H, n_tok, n_tok)).astype(np.int8)
+    s_a, s_b, s_2 = np.float32(0.05), np.float32(0.004), np.float32(0.043)
+    acc_scale = np.float32(127 * s_a / (D * 127 * 30))
+    m_s, e_s = K.dyadic_host(np.array([acc_scale], np.float32), s_a)
+    m_2, e_2 = K.dyadic_host(np.array([s_a], np.float32), s_2)
+    m_b, e_b = K.dyadic_host(np.array([s_b], np.float32), s_2)
+    x0 = O.x0_of(s_2)
+    m_o, e_o = K.dyadic_host(np.array([2.0 ** -7 * 0.02], np.float32), np.float32(0.02 * 0.9))
+    mask01 = np.zeros((n_win, n_tok, n_tok), np.int64)
+    if with_mask:
+        grp = rng.integers(0, 3, (n_win, n_tok))
+        mask01 = (grp[:, :, None] != grp[:, None, :]).astype(np.int64)      # block structure as in swin_quant.py:223-247
+        mask01[0] = 0                                                       # the first window is never masked
+    add = int(np.rint(np.float64(-100.0) / np.float64(s_2)))               # integer addend of a masked entry (App. A.5)
+    Cc = H * D
+    want = np.zeros((n_seq * n_tok, Cc), np.int64)
+    for b in range(n_seq):
+        blk = qkv[b * n_tok:(b + 1) * n_tok].astype(np.int64)
+        for h in range(H):
+            q, k, v = blk[:, h * D:(h + 1) * D], blk[:, Cc + h * D:Cc + (h + 1) * D], blk[:, 2 * Cc + h * D:2 * Cc + (h + 1) * D]
+            s = O.requant(q @ k.T, [m_s[0]], [e_s[0]], 8)
+            s = O.requant(s, [m_2[0]], [e_2[0]], 8, bias[h].astype(np.int64), [m_b[0]], [e_b[0]])
+            s = s + add * mask01[b % n_win]
+            pr = O.shiftmax(s, x0, 8)
+            want[b * n_tok:(b + 1) * n_tok, h * D:(h + 1) * D] = O.requant(pr @ v, [m_o[0]], [e_o[0]], 8)
+    mask_dev = dev((add * mask01).astype(np.int32)) if with_mask else None
+    got = K.attention_i8(dev(qkv), n_seq, n_tok, H, D, (int(m_s[0]), int(e_s[0])), x0, (int(m_o[0]), int(e_o[0])), p_bits=8,
+                         relbias=dev(bias), me_s2=(int(m_2[0]), int(e_2[0])), me_b=(int(m_b[0]), int(e_b[0])),
+                         mask=mask_dev, n_win=n_win if with_mask else 0)
+    assert np.abs(want).max() > 8, "test should produce non-trivial outputs"
+    assert_equal(got, want, "swin attention n_win=%d H=%d mask=%s" % (n_win, H, with_mask))
+
+
 # ------------------------------------------------------------------------------- hot-path specialisations
 @pytest.mark.parametrize("cols,s", [(768, 0.03), (3072, 0.045), (1536, 0.0734), (384, 0.012), (4096, 0.02), (48, 0.05)])
 def test_shiftgelu_lut_matches_general_and_oracle(K, cols, s):
