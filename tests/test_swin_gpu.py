@@ -50,3 +50,36 @@ def test_swin_tiny_operator_level_matches_reference_digests():
     err = np.abs(y.cpu().numpy().astype(np.float64) - gold["logits"].astype(np.float64)).max()
     assert err <= 2e-6 * np.abs(gold["logits"]).max()
     assert (y.cpu().numpy().argmax(1) == gold["logits"].argmax(1)).all()
+
+
+def test_swin_fused_engine_matches_oracle_at_every_fused_boundary():
+    """SwinEngine (integer tensors end to end, fused window attention with bias + mask, patch merging, token average)
+    against the CPU oracle -- itself pinned to the reference's digests at all 298 boundaries -- at every boundary the
+    engine materialises, for the golden batch and for a batch of 3 (graph replay included)."""
+    import oracle.model as OM
+    from ivit_b200.calib import build_synthetic
+    from ivit_b200.pack import export_swin
+    from ivit_b200.swin_engine import SwinEngine
+    from ivit_b200.synth import synth_images
+    gold = np.load(os.path.join(GOLDEN, "swin_tiny_b1.npz"))
+    pack = export_swin(build_synthetic("swin_tiny_patch4_window7_224"))
+    eng = SwinEngine(pack, "cuda")
+    for batch, seed in [(int(gold["batch"]), int(gold["seed_images"])), (3, 19)]:
+        x = synth_images(batch, seed=seed)
+        cap = {}
+        want = OM.swin_forward(pack, x.numpy(), cap)
+        taps = eng.forward_taps(x.cuda())
+        checked = 0
+        for name in cap:                                  # oracle (forward) order: report the FIRST divergence
+            if name in taps:
+                got = taps[name].cpu().numpy().astype(np.int64).reshape(-1)
+                bad = int((got != cap[name].reshape(-1)).sum())
+                assert bad == 0, "SwinEngine diverges from the oracle at %s (%d of %d elements)" % (name, bad, got.size)
+                checked += 1
+        assert checked >= 12 * 9 + 3 * 2 + 5, checked
+        assert np.array_equal(taps["logits"].cpu().numpy(), want)
+        for _ in range(2):                                # captured graph, then replay
+            assert np.array_equal(eng(x.cuda()).cpu().numpy(), want)
+    err = np.abs(want.astype(np.float64)).max()
+    assert err > 0
+
