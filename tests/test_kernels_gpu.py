@@ -370,7 +370,10 @@ def oracle_attention(qkv, n_seq, n_tok, H, D, me_s, x0, me_o, p_bits):
 @pytest.mark.parametrize("n_seq,n_tok,H,D,p_bits", [(2, 197, 3, 64, 16), (3, 49, 3, 32, 8), (1, 197, 12, 64, 16),
                                                     (2, 64, 2, 64, 16), (2, 50, 4, 32, 16), (1, 17, 1, 64, 8),
                                                     (1, 129, 2, 64, 16), (1, 224, 1, 64, 16), (2, 5, 2, 64, 16),
-                                                    (1, 200, 2, 64, 16), (3, 128, 1, 64, 16)])
+                                                    (1, 200, 2, 64, 16), (3, 128, 1, 64, 16),
+                                                    # more (image, head) items than resident CTAs (2 x 148): the persistent
+                                                    # loop with next-item operand prefetch, one and two m-tiles per item
+                                                    (110, 64, 3, 64, 16), (42, 197, 8, 64, 16)])
 def test_attention(K, n_seq, n_tok, H, D, p_bits):
     rng = np.random.default_rng(n_tok * 31 + H)
     qkv = rng.integers(-128, 128, (n_seq * n_tok, 3 * H * D)).astype(np.int8)
