@@ -7,6 +7,8 @@
 // in place as the A operand of the second MMA (16-bit P split into an unsigned high and low
 // byte plane, two u8 x s8 MMAs, recombined (hi << 8) + lo).
 // Reference call order: vit_quant.py:59-83 (DeiT), swin_quant.py:121-164 (Swin).
+// This mma.sync kernel is the GENERAL path (Swin's relative-position-bias QuantAct and shifted-window mask, 8-bit
+// probabilities, head_dim 32, slow-form requants); the DeiT shapes take the tcgen05 kernel of ivit_attn_tc.cu.
 //
 // ivit_bmm_i32: QuantMatMul.forward's contraction (quant_modules.py:223-228) for the
 // operator-level API (raw int32 result, strided batched views, int8 or int16 A).

@@ -4,15 +4,18 @@
 //   acc[i,j] = sum_k A[i,k] * W[j,k] (+ bias[j])              QuantLinear.forward, quant_modules.py:93-97
 //   out[i,j] = clamp(RNE(acc * m[j] / 2^e[j]) ...)            QuantAct / fixedpoint_mul, quant_utils.py:192-253
 //
-// Structure (one persistent CTA per SM, 320 threads):
-//   warp 0      TMA producer: A tile [128 x 128 B] and W tile [BN x 128 B] per k-block into a
+// Structure (one persistent CTA per SM, 352 threads; for M >= 512 and 256-wide tiles the CTAs of a TPC run as a pair,
+// tcgen05 cta_group::2, on a 256 x 256 output tile -- see the kernel's comment):
+//   warp 0      TMA producer: A tile [128 x 128 B] and W tile [BN (or BN/2 in a pair) x 128 B] per k-block into a
 //               STAGES-deep shared-memory ring (128-byte swizzle), mbarrier full/empty pairs
 //   warp 1      TMEM allocator + MMA issuer: one thread issues 4 x tcgen05.mma (K = 32 each) per
 //               k-block into one of two TMEM accumulators (128 lanes x BN int32 columns each)
-//   warps 2-9   epilogue (two warps per TMEM lane group, half of the tile's columns each):
-//               tcgen05.ld 16/32 columns at a time (prefetched one chunk ahead, as is the int16 residual)
-//               -> per-channel dyadic requant (+ second stage + residual) in registers -> 16-byte stores.  Runs concurrently with the MMAs of
-//               the next tile (double-buffered accumulator).
+//   warp 2      auxiliary warp: per-column requant constants of the tile two ahead -> shared memory, requant form vote
+//   warps 3-10  epilogue (two warps per TMEM lane group, half of the tile's columns each):
+//               tcgen05.ld 16/32 columns at a time (prefetched one chunk ahead) -> per-channel dyadic requant
+//               (+ second stage + int16 residual, which arrives by TMA for the K <= 1024 shapes) in registers ->
+//               128B-swizzled staging tile -> one TMA store per warp.  Runs concurrently with the MMAs of the next
+//               tile (double-buffered accumulator); no CTA-wide barrier in the loop.
 // Both operands are K-major (row-major A [M,K], row-major W [N,K]), so no transposes anywhere.
 #include <stdio.h>
 #include <stdlib.h>
