@@ -220,6 +220,8 @@ class Engine:
         ok = images.dtype == torch.float32 and images.is_contiguous() and images.shape == plan["buf"]["img"].shape
         g = plan["bound"].get(key) if ok else None
         if g is None and ok:
+            if len(plan["seen"]) > 256:                      # a caller that feeds fresh tensors every time: forget old addresses
+                plan["seen"].clear()
             plan["seen"][key] = plan["seen"].get(key, 0) + 1
             if plan["seen"][key] >= 2 and len(plan["bound"]) < 4:
                 g = plan["bound"][key] = self._capture(plan["buf"], B, img=images)
