@@ -25,6 +25,7 @@ FACTORIES = {
     "deit_tiny_patch16_224": deit.deit_tiny_patch16_224,
     "deit_small_patch16_224": deit.deit_small_patch16_224,
     "deit_base_patch16_224": deit.deit_base_patch16_224,
+    "vit_large_patch16_224": deit.vit_large_patch16_224,
     "swin_tiny_patch4_window7_224": swin.swin_tiny_patch4_window7_224,
 }
 

@@ -10,6 +10,7 @@ carrier is not exact) and storing inputs + integer outputs:
   ops_kat.npz        per-operator known answers (every class of quantization_utils/__init__.py)
   deit_tiny_b2.npz   DeiT-tiny, batch 2: logits, sha256 of the integer tensor at every
                      operator boundary, full tensors for block 0 / tail, weight checksum
+  swin_tiny_b1.npz / vit_large_b1.npz   the same digests for Swin-tiny (298 boundaries) and ViT-large (512), batch 1
   calib_<model>.json activation ranges (min,max per QuantAct) of the calibrated synthetic
                      models; weights are regenerated from the per-name seed (synth.py)
 
@@ -270,6 +271,8 @@ if __name__ == "__main__":
     if "calib" in which:
         for f in ("deit_small_patch16_224", "deit_base_patch16_224"):
             model_golden(f, None, None, [])
+    if "large" in which:
+        model_golden("vit_large_patch16_224", "vit_large_b1", 1, ["head"])
     if "swin" in which:
         model_golden("swin_tiny_patch4_window7_224", "swin_tiny_b1", 1,
                      ["qact3", "head"])

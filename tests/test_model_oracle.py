@@ -154,3 +154,24 @@ def test_swin_pack_roundtrip_and_reference_model(swin, tmp_path):
     for k in pack.arrays:
         assert np.array_equal(pref[k], pack[k]), k
 
+
+def test_vit_large_oracle_reproduces_reference_at_every_boundary():
+    """ViT-large (24 blocks, C = 1024, 16 heads; vit_quant.py:365-381): pack + oracle forward against the digests of the
+    reference's own run at all 512 operator boundaries (tests/golden/vit_large_b1.npz)."""
+    from ivit_b200.calib import build_synthetic
+    from ivit_b200.pack import export_deit
+    from ivit_b200.synth import synth_images
+    gold = np.load(os.path.join(GOLDEN, "vit_large_b1.npz"))
+    pack = export_deit(build_synthetic("vit_large_patch16_224"))
+    assert pack.meta["depth"] == 24 and pack.meta["embed_dim"] == 1024
+    x = synth_images(int(gold["batch"]), seed=int(gold["seed_images"])).numpy()
+    cap = {}
+    logits = OM.deit_forward(pack, x, cap)
+    want = dict(zip(gold["names"].tolist(), gold["digests"].tolist()))
+    for name, arr in cap.items():
+        assert digest(arr) == want[name], "first divergence from the reference at %s" % name
+    executed = {n for n in want if "qact_softmax" not in n and n != "act_out"}
+    assert executed <= set(cap) and len(cap) >= 500
+    err = np.abs(logits.astype(np.float64) - gold["logits"].astype(np.float64)).max()
+    assert err <= 2e-6 * np.abs(gold["logits"]).max()
+
