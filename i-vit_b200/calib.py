@@ -27,6 +27,7 @@ FACTORIES = {
     "deit_base_patch16_224": deit.deit_base_patch16_224,
     "vit_large_patch16_224": deit.vit_large_patch16_224,
     "swin_tiny_patch4_window7_224": swin.swin_tiny_patch4_window7_224,
+    "swin_base_patch4_window7_224": swin.swin_base_patch4_window7_224,
 }
 
 

@@ -273,6 +273,8 @@ if __name__ == "__main__":
             model_golden(f, None, None, [])
     if "large" in which:
         model_golden("vit_large_patch16_224", "vit_large_b1", 1, ["head"])
+    if "swinb" in which:
+        model_golden("swin_base_patch4_window7_224", "swin_base_b1", 1, ["head"])
     if "swin" in which:
         model_golden("swin_tiny_patch4_window7_224", "swin_tiny_b1", 1,
                      ["qact3", "head"])

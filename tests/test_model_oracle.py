@@ -175,3 +175,23 @@ def test_vit_large_oracle_reproduces_reference_at_every_boundary():
     err = np.abs(logits.astype(np.float64) - gold["logits"].astype(np.float64)).max()
     assert err <= 2e-6 * np.abs(gold["logits"]).max()
 
+
+def test_swin_base_oracle_reproduces_reference_at_every_boundary():
+    """Swin-base (depths 2/2/18/2, heads 4/8/16/32, C = 128..1024; swin_quant.py:609-627): pack + oracle forward against
+    the digests of the reference's own run at all 574 operator boundaries (tests/golden/swin_base_b1.npz)."""
+    from ivit_b200.calib import build_synthetic
+    from ivit_b200.pack import export_swin
+    from ivit_b200.synth import synth_images
+    gold = np.load(os.path.join(GOLDEN, "swin_base_b1.npz"))
+    pack = export_swin(build_synthetic("swin_base_patch4_window7_224"))
+    assert pack.meta["depths"] == [2, 2, 18, 2] and pack.meta["num_heads"] == [4, 8, 16, 32]
+    x = synth_images(int(gold["batch"]), seed=int(gold["seed_images"])).numpy()
+    cap = {}
+    logits = OM.swin_forward(pack, x, cap)
+    want = dict(zip(gold["names"].tolist(), gold["digests"].tolist()))
+    for name, arr in cap.items():
+        assert digest(arr) == want[name], "first divergence from the reference at %s" % name
+    assert set(want) <= set(cap) and len(cap) >= 570
+    err = np.abs(logits.astype(np.float64) - gold["logits"].astype(np.float64)).max()
+    assert err <= 2e-6 * np.abs(gold["logits"]).max()
+
