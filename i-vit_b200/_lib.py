@@ -140,14 +140,16 @@ def context(device=None) -> Context:
     return ctx
 
 
-def _stream() -> int:
-    return torch.cuda.current_stream().cuda_stream
-
-
 def call(name: str, ctx: Context, *args):
-    """Invoke ``name(ctx, *args, stream)`` on torch's current stream."""
+    """Invoke ``name(ctx, *args, stream)`` on torch's current stream OF THE CONTEXT'S DEVICE, with that device current
+    for the duration of the launch (one process may drive several GPUs; kernel launches go to the current device)."""
     fn = getattr(load_library(), name)
-    _check(fn(ctx.handle, *args, _stream()), name)
+    if torch.cuda.current_device() == ctx.device:
+        rc = fn(ctx.handle, *args, torch.cuda.current_stream(ctx.device).cuda_stream)
+    else:
+        with torch.cuda.device(ctx.device):
+            rc = fn(ctx.handle, *args, torch.cuda.current_stream(ctx.device).cuda_stream)
+    _check(rc, name)
 
 
 def ptr(t):

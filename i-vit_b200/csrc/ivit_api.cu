@@ -46,8 +46,12 @@ int ivit_create(int device, ivit_ctx** out) {
     if (prop.major != 10)
         return fail(IVIT_ENODEV, "ivit_create: device %d is sm_%d%d; this library is built for sm_100a only",
                     device, prop.major, prop.minor);
+    int prev = -1;
+    IVIT_CUDA_OK(cudaGetDevice(&prev));
     IVIT_CUDA_OK(cudaSetDevice(device));
-    IVIT_CUDA_OK(cudaFree(0));                         // make sure the primary context exists
+    e = cudaFree(0);                                   // make sure the primary context exists
+    if (prev != device) cudaSetDevice(prev);           // the caller's current device is not ours to change
+    IVIT_CUDA_OK(e);
     ivit_ctx* c = new ivit_ctx();
     c->device = device;
     c->num_sms = prop.multiProcessorCount;

@@ -384,10 +384,12 @@ template <int D, int KT, bool SWIN, bool P16, bool FAST>
 static int launch_attention(int grid, const int8_t* qkv, const AttnArgs& a, int8_t* out, cudaStream_t s) {
     constexpr int SMEM = KT * 32 * (D + 16) + D * (KT * 32 + 16) + 260 * 4 + ATT_WARPS * KT * 4 * 32 * 4;
     auto kern = attention_kernel<D, KT, SWIN, P16, FAST>;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDevice attr_set;
+    int dev = 0;
+    IVIT_CUDA_OK(cudaGetDevice(&dev));
+    if (!attr_set[dev]) {
         IVIT_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
-        attr_set = true;
+        attr_set[dev] = 1;
     }
     kern<<<grid, ATT_WARPS * 32, SMEM, s>>>(qkv, a, out);
     IVIT_LAUNCH_OK("attention_kernel");
@@ -466,12 +468,20 @@ extern "C" int ivit_bmm_i32(ivit_ctx* ctx, const void* A, int a_dtype, int64_t l
                             int32_t* C, int64_t ldc, int64_t sc, ivit_stream stream) {
     IVIT_REQUIRE(ctx && A && B && C && batch > 0 && M > 0 && N > 0 && K > 0, "ivit_bmm_i32: bad arguments");
     IVIT_REQUIRE(a_dtype == IVIT_I8 || a_dtype == IVIT_I16, "ivit_bmm_i32: a_dtype must be I8 or I16");
-    IVIT_REQUIRE(batch <= 65535, "ivit_bmm_i32: batch > 65535");
-    dim3 grid((N + 63) / 64, (M + 63) / 64, (unsigned)batch);
-    if (a_dtype == IVIT_I8)
-        bmm_i32_kernel<int8_t><<<grid, 256, 0, st(stream)>>>((const int8_t*)A, lda, sa, B, ldb, sb, trans_b, M, N, K, C, ldc, sc);
-    else
-        bmm_i32_kernel<int16_t><<<grid, 256, 0, st(stream)>>>((const int16_t*)A, lda, sa, B, ldb, sb, trans_b, M, N, K, C, ldc, sc);
+    // the batch index rides in gridDim.z (<= 65535): larger batches (Swin-B bs=256 stage 1: 256*64*4 windows x heads) are
+    // launched in z-chunks
+    for (int64_t b0 = 0; b0 < batch; b0 += 65535) {
+        const int64_t nb = batch - b0 < 65535 ? batch - b0 : 65535;
+        dim3 grid((N + 63) / 64, (M + 63) / 64, (unsigned)nb);
+        const int es = a_dtype == IVIT_I8 ? 1 : 2;
+        const void* Ab = (const char*)A + b0 * sa * es;
+        const int8_t* Bb = B + b0 * sb;
+        int32_t* Cb = C + b0 * sc;
+        if (a_dtype == IVIT_I8)
+            bmm_i32_kernel<int8_t><<<grid, 256, 0, st(stream)>>>((const int8_t*)Ab, lda, sa, Bb, ldb, sb, trans_b, M, N, K, Cb, ldc, sc);
+        else
+            bmm_i32_kernel<int16_t><<<grid, 256, 0, st(stream)>>>((const int16_t*)Ab, lda, sa, Bb, ldb, sb, trans_b, M, N, K, Cb, ldc, sc);
+    }
     IVIT_LAUNCH_OK("bmm_i32_kernel");
     return IVIT_OK;
 }

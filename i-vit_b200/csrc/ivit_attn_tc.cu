@@ -475,13 +475,13 @@ int launch_attention_tc(ivit_ctx* ctx, const int8_t* qkv, const ivit_attn_params
     const int grid = items < 2 * ctx->num_sms ? items : 2 * ctx->num_sms;       // persistent: two resident CTAs per SM
 #define ATC_CASE(N)                                                                                                   \
     case N: {                                                                                                         \
-        static bool attr_set = false;                                                                                 \
-        if (!attr_set) {                                                                                              \
+        static PerDevice attr_set;                                                                                    \
+        if (!attr_set[ctx->device]) {                                                                                           \
             IVIT_CUDA_OK(cudaFuncSetAttribute(attention_tc_kernel<N, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATC_SMEM)); \
             IVIT_CUDA_OK(cudaFuncSetAttribute(attention_tc_kernel<N, 2>, cudaFuncAttributePreferredSharedMemoryCarveout, 100)); \
             IVIT_CUDA_OK(cudaFuncSetAttribute(attention_tc_kernel<N, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATC_SMEM)); \
             IVIT_CUDA_OK(cudaFuncSetAttribute(attention_tc_kernel<N, 3>, cudaFuncAttributePreferredSharedMemoryCarveout, 100)); \
-            attr_set = true;                                                                                          \
+            attr_set[ctx->device] = 1;                                                                                \
         }                                                                                                             \
         if (parts == 3) attention_tc_kernel<N, 3><<<grid, 384, ATC_SMEM, s>>>(tq, tk, qkv, a, out);                   \
         else attention_tc_kernel<N, 2><<<grid, 256, ATC_SMEM, s>>>(tq, tk, qkv, a, out);                              \

@@ -114,9 +114,13 @@ IVIT_DEVINL int32_t clamp_i64_bits(long long v, int bits) {
 // int_exp_shift   quant_modules.py:410-423 (IntGELU) / :469-481 (IntSoftmax)
 //   t = d + floor(d/2) - floor(d/16); t = max(t, n*x0); k = floor(t/x0); r = t - x0*k
 //   E = max(floor((r/2 - x0) * 2^(n-k)), 0) = ((r - 2*x0) << (n-k)) >> 1
-// x0 < 0.  inv_x0 = 1.0f / x0 (host supplied) seeds the floor division; two exact
-// corrections make it an exact floor for |t| < 2^24.
-// Domain (checked at freeze): 8 <= -x0 <= 2^15, |d| <= 256  => result < 2^62.
+// x0 < 0.  inv_x0 = 1.0f / x0 (host supplied) seeds the floor division; two exact corrections make it an exact
+// floor: |k| <= 184 (t in [n*x0, 184]), so the fp32 quotient is within 2e-5 of the true one and its floor is off by
+// at most one.
+// Domain (checked by the callers): 1 <= -x0 <= 2^24, -256 <= d <= 256.  The result is exact below 2^62 and SATURATES at
+// 2^62 above (k < 0 with a tiny |x0|: ShiftGELU's e^(-x_max) of an all-negative row at a coarse input scale reaches
+// 2^(n+184)).  Saturation is invisible to both users: Shiftmax only has d <= 0 (k >= 0, E < 2^40), and ShiftGELU feeds
+// that term into a sum that is clamped at 2^31 - 1 (quant_modules.py:435-437) -- any value >= 2^31 acts the same.
 // ------------------------------------------------------------------------------------
 IVIT_DEVINL long long shiftexp(int32_t d, int32_t x0, float inv_x0, int n) {
     int32_t t = d + (d >> 1) - (d >> 4);
@@ -126,10 +130,10 @@ IVIT_DEVINL long long shiftexp(int32_t d, int32_t x0, float inv_x0, int n) {
     int32_t r = t - x0 * k;                          // want x0 < r <= 0
     if (r > 0) { k -= 1; r += x0; }
     if (r <= x0) { k += 1; r -= x0; }
-    const int32_t base = r - 2 * x0;                 // in (|x0|, 2|x0|]
+    const int32_t base = r - 2 * x0;                 // in (|x0|, 2|x0|] : 2 <= base <= 2^25
     const int sh = n - k - 1;
-    long long E = (sh >= 0) ? ((long long)base << (sh > 46 ? 46 : sh)) : (long long)(base >> 1);
-    return E;
+    if (sh > 36) return 1LL << 62;                   // >= 2^38: saturated (see above)
+    return (sh >= 0) ? ((long long)base << sh) : (long long)(base >> 1);
 }
 
 // IntLayerNorm's integer square root: k = 2^16; 10x k = floor((k + floor(V/k)) / 2)   quant_modules.py:366-370

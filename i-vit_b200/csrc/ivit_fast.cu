@@ -491,8 +491,8 @@ int ivit_shiftgelu_build_lut(ivit_ctx* ctx, int32_t x0, int n, const ivit_dyadic
     IVIT_REQUIRE(ctx && me && lut, "ivit_shiftgelu_build_lut: null pointer");
     IVIT_REQUIRE(bits == 8, "ivit_shiftgelu_build_lut: the table holds int8 outputs (bits == 8)");
     IVIT_REQUIRE(n >= 1 && n <= 30, "ivit_shiftgelu_build_lut: bad n");
-    if (!(x0 <= -8 && x0 >= -65536))
-        return fail(IVIT_ENOTSUP, "ivit_shiftgelu_build_lut: x0=%d outside the supported domain [-65536, -8]", x0);
+    if (!(x0 <= -1 && x0 >= -(1 << 24)))
+        return fail(IVIT_ENOTSUP, "ivit_shiftgelu_build_lut: x0=%d outside [-2^24, -1]", x0);
     gelu_lut_build_kernel<<<256, 256, 0, st(stream)>>>(x0, 1.0f / (float)x0, n, me, bits, lut);
     IVIT_LAUNCH_OK("gelu_lut_build_kernel");
     return IVIT_OK;
@@ -507,7 +507,8 @@ int ivit_shiftgelu_lut(ivit_ctx* ctx, const int8_t* q, int64_t rows, int cols, c
     const int nv = (cols / 16 + 31) / 32;
     // persistent grid: exactly the blocks that are resident at once (a partial second wave would run alone at the end)
 #define GL(MAXV) do {                                                                                                    \
-        static int bps = 0;                                                                                              \
+        static PerDevice bps_dev;                                                                                        \
+        int& bps = bps_dev[ctx->device];                                                                                 \
         if (!bps) IVIT_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, gelu_lut_apply_kernel<MAXV>, 256, 0)); \
         const int64_t want = (rows + 7) / 8, cap = (int64_t)ctx->num_sms * (bps > 0 ? bps : 1);                          \
         gelu_lut_apply_kernel<MAXV><<<(int)(want < cap ? want : cap), 256, 0, st(stream)>>>(q, rows, cols, lut, out);     \

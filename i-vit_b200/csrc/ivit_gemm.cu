@@ -880,8 +880,9 @@ static int launch_gemm(ivit_ctx* ctx, const CUtensorMap& ta, const CUtensorMap& 
     const CUtensorMap& tr = tres ? *tres : ta;
     static_assert(S::TOTAL <= 227 * 1024, "shared memory budget");
     auto kern = gemm_i8_tcgen05_kernel<BN, STAGES, MODE, OM, PAIR>;
-    static bool attr_set = false;                     // per instantiation
-    static int max_clusters = 0;
+    static PerDevice attr_dev, clusters_dev;          // per instantiation and device
+    int& attr_set = attr_dev[ctx->device];
+    int& max_clusters = clusters_dev[ctx->device];
     cudaLaunchConfig_t cfg = {};
     cfg.blockDim = dim3(gemm_threads(MODE));
     cfg.dynamicSmemBytes = S::TOTAL;
@@ -898,7 +899,7 @@ static int launch_gemm(ivit_ctx* ctx, const CUtensorMap& ta, const CUtensorMap& 
             IVIT_CUDA_OK(cudaOccupancyMaxActiveClusters(&max_clusters, kern, &cfg));
             if (max_clusters < 1) return fail(IVIT_ECUDA, "gemm: no co-resident cluster of %d CTAs fits", CS);
         }
-        attr_set = true;
+        attr_set = 1;
     }
     const int tiles_m = (ga.M + GEMM_BM - 1) / GEMM_BM, tiles_n = (ga.N + BN - 1) / BN;
     const int ctiles = ((tiles_m + CS - 1) / CS) * tiles_n;

@@ -17,6 +17,13 @@ struct ivit_ctx {
 };
 
 namespace ivit {
+// Per-device one-time state of a kernel instantiation (cudaFuncSetAttribute and the occupancy queries are per device:
+// one process may hold contexts on several GPUs).  Indexed by ivit_ctx::device.
+constexpr int kMaxDevices = 64;
+struct PerDevice {
+    int v[kMaxDevices] = {};
+    int& operator[](int dev) { return v[(unsigned)dev % kMaxDevices]; }
+};
 int fail(int code, const char* fmt, ...);
 int fail_cuda(cudaError_t e, const char* what);
 inline cudaStream_t st(ivit_stream s) { return reinterpret_cast<cudaStream_t>(s); }

@@ -432,14 +432,11 @@ int ivit_layernorm(ivit_ctx* ctx, const void* x, int x_dtype, int64_t rows, int 
     return IVIT_OK;
 }
 
-// Supported x0 domain of the exact 64-bit shift-exponential (see shiftexp()):
-//   Shiftmax: d <= 0, so k in [0, n] for any x0 <= -1;
-//   ShiftGELU: an all-negative row makes -max > 0 and k >= -ceil(184/|x0|); the shift
-//   n - k - 1 stays <= 45 only for x0 <= -8 (input scale s <= 0.0734).
-static int check_x0(const char* who, int32_t x0, int32_t hi) {
-    if (!(x0 <= hi && x0 >= -65536))
-        return fail(IVIT_ENOTSUP, "%s: x0=%d outside the supported domain [-65536, %d] "
-                    "(input scale too coarse or too fine for the exact 64-bit path)", who, x0, hi);
+// Supported x0 domain of the exact 64-bit shift-exponential (see shiftexp()): 1 <= -x0 <= 2^24, i.e. every scale the
+// reference can produce (its scales are clamped at fp32 eps = 1.19e-7 -> x0 >= -8.4e6, quant_utils.py:63-67).
+static int check_x0(const char* who, int32_t x0) {
+    if (!(x0 <= -1 && x0 >= -(1 << 24)))
+        return fail(IVIT_ENOTSUP, "%s: x0=%d outside [-2^24, -1]", who, x0);
     return IVIT_OK;
 }
 
@@ -452,10 +449,13 @@ int ivit_shiftmax(ivit_ctx* ctx, const void* q, int q_dtype, int64_t rows, int c
                  (out_bits == 8 && (out_dtype == IVIT_I8 || out_dtype == IVIT_I16 || out_dtype == IVIT_I32)),
                  "ivit_shiftmax: out_bits must be 8 or 16 with a dtype that holds [0, 2^(bits-1)]");
     IVIT_REQUIRE(n >= 1 && n <= 30, "ivit_shiftmax: bad n");
-    int rc = check_x0("ivit_shiftmax", x0, -1);
+    int rc = check_x0("ivit_shiftmax", x0);
     if (rc) return rc;
-    // int8 output of an 8-bit softmax can reach 2^7 = 128 only if F*E hits 2^31 exactly;
-    // E*F <= S*F <= 2^31-1, so P <= 127 (8 bit) / 32767 (16 bit): storage is safe.
+    // E*F <= S*F <= 2^31-1 while the row sum S is below the 2^31-1 clamp, so P <= 127 (8 bit) / 32767 (16 bit) and the
+    // narrow storage is safe.  Only for |x0| > 65536 (E(0) = |x0| << n can exceed 2^31: the clamp bites, F = 1) the
+    // reference's own result leaves the nominal range (quant_modules.py:491-493): int32 storage is required there.
+    if (x0 < -65536)
+        IVIT_REQUIRE(out_dtype == IVIT_I32, "ivit_shiftmax: x0=%d (scale below 2^-16) needs an int32 output", x0);
     const float inv_x0 = 1.0f / (float)x0;
     const int wpb = 8;
     const int grid = grid_for(rows, wpb, ctx->num_sms, 16);
@@ -481,8 +481,11 @@ int ivit_shiftgelu(ivit_ctx* ctx, const void* q, int q_dtype, int64_t rows, int 
                      "ivit_shiftgelu: out_dtype cannot hold %d bits", bits);
     } else {
         IVIT_REQUIRE(out_dtype == IVIT_I16 || out_dtype == IVIT_I32, "ivit_shiftgelu: un-fused output is int16/int32");
+        // |q * sigmoid_int| <= 128 * 127 only while the 2^31-1 clamp of the exponential sum does not bite (|x0| < 256);
+        // below that scale the reference's sigmoid_int exceeds 127 (quant_modules.py:437-439) and int32 is needed
+        if (out_dtype == IVIT_I16) IVIT_REQUIRE(x0 >= -255, "ivit_shiftgelu: x0=%d needs an int32 output", x0);
     }
-    int rc = check_x0("ivit_shiftgelu", x0, -8);
+    int rc = check_x0("ivit_shiftgelu", x0);
     if (rc) return rc;
     const float inv_x0 = 1.0f / (float)x0;
     const int wpb = 8;

@@ -292,17 +292,24 @@ def _gelu_into(q, x0, me, out):
 def accelerate(model: torch.nn.Module, device="cuda"):
     """One-line adoption for code written against the reference's API: ``model = ivit_b200.engine.accelerate(model)``.
 
-    ``model`` is a calibrated, frozen DeiT/ViT built on the reference's operator classes (the reference's own
-    ``models/vit_quant.py`` object, or this package's ``deit`` graph).  Its static integer parameters are exported once
-    (``pack.export_deit``) and ``model.forward`` is replaced by the fused engine: same logits bit for bit as the
-    operator-by-operator forward (tests/test_model_gpu.py), ~30x its throughput (fp32 carriers never touch HBM).
-    Calling ``unfreeze_model`` / changing weights afterwards requires ``accelerate`` again; the original forward is kept
-    as ``model._ivit_forward_operator_level``."""
-    from .pack import export_deit
+    ``model`` is a calibrated, frozen DeiT/ViT or Swin built on the reference's operator classes (the reference's own
+    ``models/vit_quant.py`` / ``models/swin_quant.py`` object loaded through ``ivit_b200.dropin``, or this package's
+    ``deit`` / ``swin`` graphs).  Its static integer parameters are exported once (``pack.export_deit`` /
+    ``pack.export_swin``) and ``model.forward`` is replaced by the fused engine: same logits bit for bit as the
+    operator-by-operator forward (tests/test_model_gpu.py, tests/test_zz_reference_graphs_gpu.py), ~30x its throughput
+    (fp32 carriers never touch HBM).  Calling ``unfreeze_model`` / changing weights afterwards requires ``accelerate``
+    again; the original forward is kept as ``model._ivit_forward_operator_level``."""
+    from .pack import export_deit, export_swin
     for m in model.modules():
         if type(m).__name__ == "QuantAct" and getattr(m, "running_stat", False):
             raise RuntimeError("accelerate: the model is not frozen (QuantAct.running_stat is set); call freeze_model first")
-    eng = Engine(export_deit(model), device)
+    if hasattr(model, "layers") and hasattr(model, "patch_grid"):              # SwinTransformer (swin_quant.py:419)
+        from .swin_engine import SwinEngine
+        eng = SwinEngine(export_swin(model), device)
+    elif hasattr(model, "blocks") and hasattr(model, "cls_token"):             # VisionTransformer (vit_quant.py:146)
+        eng = Engine(export_deit(model), device)
+    else:
+        raise NotImplementedError("accelerate: %s is neither a VisionTransformer nor a SwinTransformer" % type(model).__name__)
     model._ivit_engine = eng
     model._ivit_forward_operator_level = model.forward
 
@@ -311,4 +318,3 @@ def accelerate(model: torch.nn.Module, device="cuda"):
 
     model.forward = forward
     return model
-

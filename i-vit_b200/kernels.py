@@ -81,6 +81,8 @@ _WIDER = {torch.int8: (torch.int8, torch.int16, torch.int32), torch.int16: (torc
 def _shadow_register(carrier: torch.Tensor, q: torch.Tensor, s: torch.Tensor):
     if not _SHADOW_ON or carrier._base is not None or q.shape != carrier.shape or not q.is_contiguous():
         return
+    if q.storage_offset() != 0 or carrier.storage_offset() != 0:
+        return                   # views are re-derived with the CARRIER's absolute storage offsets (as_strided below)
     key = id(carrier)
     _SHADOW[key] = (_weakref.ref(carrier, lambda _r, k=key: _SHADOW.pop(k, None)), carrier._version, q, s, s._version)
 

@@ -283,9 +283,11 @@ def export_swin(model) -> Pack:
 
 
 def check_supported(pack: Pack):
-    """Domain checks of the fused kernels, raised at freeze time rather than deep inside a launch."""
+    """Domain checks of the fused kernels, raised at freeze time rather than deep inside a launch.  Every scale the
+    reference can produce is inside the domain of the general kernels (x0 in [-2^24, -1]); the fused attention kernels
+    need the Shiftmax input scale >= 2^-16 (|x0| <= 65535: 8-bit scores over a range of at least 0.002)."""
     for k, v in pack.arrays.items():
         if k.endswith("int_softmax.x0") and not (-65535 <= int(v[0]) <= -1):
             raise ValueError("%s = %d outside [-65535, -1]" % (k, int(v[0])))
-        if k.endswith("act.x0") and not (-65536 <= int(v[0]) <= -8):
-            raise ValueError("%s = %d outside [-65536, -8] (GELU input scale too coarse)" % (k, int(v[0])))
+        if k.endswith("act.x0") and not (-(1 << 24) <= int(v[0]) <= -1):
+            raise ValueError("%s = %d outside [-2^24, -1]" % (k, int(v[0])))

@@ -332,11 +332,14 @@ class IntLayerNorm(nn.LayerNorm):
 
 
 def _host_scalar(t: torch.Tensor, cache: dict):
-    """Value of a 1-element device tensor, cached on (data_ptr, version): frozen scales are
-    static, so the one device->host read happens once per operator, not per forward."""
-    key = (t.data_ptr(), t._version)
-    if cache.get("key") != key:
-        cache["key"] = key
+    """Value of a 1-element device tensor, cached on the tensor OBJECT and its version: frozen scales are the same
+    tensor on every forward (QuantAct._frozen_scale), so the one device->host read happens once per operator, not per
+    forward.  The cache holds a reference to the tensor, so its address cannot be recycled for another scale while the
+    entry is alive; a scale produced by arithmetic (a new tensor every forward: calibration passes, `s * self.scale`)
+    never hits and is read back each time."""
+    if cache.get("tensor") is not t or cache.get("version") != t._version:
+        cache["tensor"] = t
+        cache["version"] = t._version
         cache["val"] = t.detach().reshape(-1)[:1].to(torch.float32).cpu()
     return cache["val"]
 
@@ -363,7 +366,7 @@ class IntGELU(nn.Module):
         s = scaling_factor.reshape(-1)
         if s.numel() != 1:
             raise NotImplementedError("IntGELU: scalar input scale expected")
-        s_host = _host_scalar(s, self._c)
+        s_host = _host_scalar(scaling_factor, self._c)     # the producer's scale tensor object: stable when frozen
         x0 = int(torch.floor(-1.0 / (s_host * 1.702)))                            # :414, :427
         x_int = K.carrier_to_int(x, s, torch.int8)                                # :426
         y = K.shiftgelu(x_int, x0, n=self.n, out_dtype=torch.int32)               # :429-442
@@ -395,10 +398,12 @@ class IntSoftmax(nn.Module):
         s = scaling_factor.reshape(-1)
         if s.numel() != 1:
             raise NotImplementedError("IntSoftmax: scalar input scale expected")
-        s_host = _host_scalar(s, self._c)
+        s_host = _host_scalar(scaling_factor, self._c)     # the producer's scale tensor object: stable when frozen
         x0 = int(torch.floor(-1.0 / s_host))                                      # :473
         x_int = K.carrier_to_int(x, s, torch.int32)                               # :484 (int32: Swin adds -100 masks)
-        p = K.shiftmax(x_int, x0, self.output_bit, n=self.n)                      # :485-493
+        # below a scale of 2^-16 the reference's own result leaves [0, 2^(bits-1)) (clamped sum, :491-493): int32 storage
+        p = K.shiftmax(x_int, x0, self.output_bit, n=self.n,
+                       out_dtype=torch.int32 if x0 < -65536 else None)            # :485-493
         out_sf = torch.tensor([1 / 2 ** (self.output_bit - 1)], dtype=torch.float32, device=x.device)   # :494
         self.act_scaling_factor = out_sf
         return K.int_to_carrier(p, out_sf), out_sf

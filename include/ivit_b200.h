@@ -169,14 +169,16 @@ IVIT_API int ivit_layernorm(ivit_ctx*, const void* x, int x_dtype, int64_t rows,
 
 /* IntSoftmax.forward (quant_modules.py:469-497), Shiftmax over the last dim.
  * q: [rows, cols] IVIT_I8 (or IVIT_I32 with values in int8 range); x0 = floor(-1/s) (host,
- * fp32 arithmetic), n = 15, out_bits 16 (out IVIT_I16) or 8 (out IVIT_I8). */
+ * fp32 arithmetic) in [-2^24, -1] (any scale the reference can produce), n = 15, out_bits 16 (out IVIT_I16) or 8
+ * (out IVIT_I8); x0 < -65536 (scale below 2^-16: the reference's clamped sum lets the result leave the nominal range,
+ * quant_modules.py:491-493) needs out IVIT_I32. */
 IVIT_API int ivit_shiftmax(ivit_ctx*, const void* q, int q_dtype, int64_t rows, int cols,
                            int32_t x0, int n, int out_bits, int out_dtype, void* out,
                            ivit_stream stream);
 
 /* IntGELU.forward (quant_modules.py:410-445), ShiftGELU over the last dim (row max).
- * q: [rows, cols] IVIT_I8; x0 = floor(-1/fp32(s*1.702)); n = 23; sigmoid bits 8.
- * out = q * sigma (IVIT_I16 / IVIT_I32); if `me` != NULL the following scalar QuantAct is
+ * q: [rows, cols] IVIT_I8; x0 = floor(-1/fp32(s*1.702)) in [-2^24, -1]; n = 23; sigmoid bits 8.
+ * out = q * sigma (IVIT_I16 while |x0| <= 255, IVIT_I32 always); if `me` != NULL the following scalar QuantAct is
  * fused: out = clamp(RNE(q*sigma*m/2^e), bits) (out IVIT_I8). */
 IVIT_API int ivit_shiftgelu(ivit_ctx*, const void* q, int q_dtype, int64_t rows, int cols,
                             int32_t x0, int n, const ivit_dyadic_t* me, int bits,

@@ -219,6 +219,36 @@ def op_kats():
         out[tag + "_sf"] = sf.detach().numpy().astype(np.float32)
         out[tag + "_o"] = (y[0].double() / sf.double()).round().numpy().astype(np.int64)
         out[tag + "_rowsum_mod"] = np.array([int(q[3].sum() % C)], np.int64)
+    # --- round 2 additions.  A SEPARATE generator, so that every array above keeps its round-1 value.
+    rng2 = np.random.default_rng(20262)
+    # IntGELU at coarse input scales (x0 = floor(-1/(1.702 s)) in [-7, -1]: e^(-x_max) of an all-negative row reaches
+    # 2^(23+184) and saturates the 2^31-1 clamp, quant_modules.py:434-438) and at a very fine one
+    for tag, cols, s in [("gelu_x7", 96, 0.0840), ("gelu_x3", 64, 0.19), ("gelu_x2", 48, 0.29), ("gelu_x1", 80, 0.75),
+                         ("gelu_fine", 64, 2.1e-5)]:
+        ge = Q.IntGELU()
+        q = rng2.integers(-128, 128, (7, cols)).astype(np.int64)
+        q[1] = rng2.integers(-128, -20, cols)         # all-negative rows: -x_max > 0, k < 0
+        q[2] = 0
+        q[3] = -128
+        q[4] = rng2.integers(-128, -100, cols)
+        q[5, 0] = 127
+        sc = torch.tensor([np.float32(s)])
+        y, sf = ge(torch.from_numpy(q).double() * sc.double(), sc)
+        out[tag + "_q"], out[tag + "_s"] = q, np.float32(s)
+        out[tag + "_sf"] = sf.numpy().astype(np.float32)
+        out[tag + "_o"] = (y.double() / sf.double()).round().numpy().astype(np.int64)
+    # IntSoftmax at coarse / very fine scales (x0 = -1 ... -2^20)
+    for tag, bits, cols, s in [("sm16_x1", 16, 50, 0.9), ("sm8_x2", 8, 49, 0.4), ("sm16_x5", 16, 197, 0.17),
+                               ("sm8_fine", 8, 49, 1.1e-6), ("sm16_fine", 16, 64, 3.3e-5)]:
+        sm = Q.IntSoftmax(bits)
+        q = rng2.integers(-128, 128, (6, cols)).astype(np.int64)
+        q[1] = -128
+        q[2, :] = rng2.integers(100, 128, cols)
+        q[3, 0] = 127
+        sc = torch.tensor([np.float32(s)])
+        y, sf = sm(torch.from_numpy(q).double() * sc.double(), sc)
+        out[tag + "_q"], out[tag + "_s"] = q, np.float32(s)
+        out[tag + "_p"] = (y.double() / sf.double()).round().numpy().astype(np.int64)
     np.savez_compressed(os.path.join(HERE, "ops_kat.npz"), **out)
     print("ops_kat.npz:", len(out), "arrays")
 

@@ -195,11 +195,58 @@ def test_shiftgelu_random(K):
                      "shiftgelu cols=%d" % cols)
 
 
-def test_unsupported_scales_fail_loudly(K):
+@pytest.mark.parametrize("tag,bits", [("sm16_x1", 16), ("sm8_x2", 8), ("sm16_x5", 16), ("sm8_fine", 8), ("sm16_fine", 16)])
+def test_shiftmax_kat_extreme_scales(K, kat, tag, bits):
+    x0 = O.x0_of(kat[tag + "_s"])
+    got = K.shiftmax(dev(kat[tag + "_q"].astype(np.int8)), x0, bits, out_dtype=torch.int32)
+    assert_equal(got, kat[tag + "_p"], "shiftmax " + tag)
+
+
+@pytest.mark.parametrize("tag", ["gelu_x7", "gelu_x3", "gelu_x2", "gelu_x1", "gelu_fine"])
+def test_shiftgelu_kat_extreme_scales(K, kat, tag):
+    """Scales the round-1 kernels refused (x0 > -8), vectors from the reference's IntGELU; the fused QuantAct
+    form and the 64 KiB table form must agree with the oracle as well."""
+    s = kat[tag + "_s"]
+    x0 = O.x0_of(O.gelu_sig_scale(s))
+    q = kat[tag + "_q"]
+    got = K.shiftgelu(dev(q.astype(np.int8)), x0, out_dtype=torch.int32)
+    assert_equal(got, kat[tag + "_o"], "shiftgelu " + tag)
+    s_in = np.float32(s) * np.float32(1 / 128)
+    s_out = np.float32(np.abs(kat[tag + "_o"]).max() * float(s_in) / 127.0)
+    m, e = K.dyadic_host(np.array([s_in], np.float32), s_out)
+    want = O.requant(kat[tag + "_o"], m, e, 8)
+    me = me_dev(K, m, e)
+    assert_equal(K.shiftgelu(dev(q.astype(np.int8)), x0, me, 8), want, "shiftgelu+qact " + tag)
+    lut = K.shiftgelu_build_lut(x0, me)
+    assert_equal(K.shiftgelu_lut(dev(np.ascontiguousarray(np.tile(q, (1, 2))).astype(np.int8)), lut),
+                 np.tile(want, (1, 2)), "shiftgelu LUT " + tag)          # row max unchanged by tiling; cols % 16 == 0
+
+
+@pytest.mark.parametrize("s", [1e-4, 6e-4, 2.3e-3, 0.009, 0.0734, 0.12, 0.3, 0.59, 1.0])
+def test_shiftgelu_and_shiftmax_over_scales(K, s):
+    """Property sweep over input scales 1e-4 ... 1: general kernels == oracle, no refusal."""
+    rng = np.random.default_rng(int(s * 1e6))
+    q = rng.integers(-128, 128, (40, 208)).astype(np.int64)
+    q[0] = rng.integers(-128, -1, 208)
+    q[1] = -128
+    q[2] = 127
+    x0g = O.x0_of(O.gelu_sig_scale(np.float32(s)))
+    assert_equal(K.shiftgelu(dev(q.astype(np.int8)), x0g, out_dtype=torch.int32), O.shiftgelu(q, x0g), "shiftgelu s=%g" % s)
+    x0s = O.x0_of(np.float32(s))
+    for bits in (8, 16):
+        assert_equal(K.shiftmax(dev(q.astype(np.int8)), x0s, bits, out_dtype=torch.int32), O.shiftmax(q, x0s, bits),
+                     "shiftmax s=%g bits=%d" % (s, bits))
+
+
+def test_unsupported_arguments_fail_loudly(K):
     from ivit_b200._lib import IvitError
     q = torch.zeros((4, 64), dtype=torch.int8, device="cuda")
     with pytest.raises(IvitError, match="x0"):
-        K.shiftgelu(q, -3)
+        K.shiftgelu(q, 0)
+    with pytest.raises(IvitError, match="int32"):
+        K.shiftgelu(q, -4000)                              # un-fused int16 output cannot hold the result below 2^-8 scales
+    with pytest.raises(IvitError, match="int32"):
+        K.shiftmax(q, -(1 << 20), 8)
     with pytest.raises(IvitError, match="bits"):
         K.requant(q.int(), me_dev(K, [2 ** 30], [31]), 7, out_dtype=torch.int32)
 
@@ -433,7 +480,8 @@ def test_attention_swin_bias_and_mask(K, n_win, H, with_mask):
 
 
 # ------------------------------------------------------------------------------- hot-path specialisations
-@pytest.mark.parametrize("cols,s", [(768, 0.03), (3072, 0.045), (1536, 0.0734), (384, 0.012), (4096, 0.02), (48, 0.05)])
+@pytest.mark.parametrize("cols,s", [(768, 0.03), (3072, 0.045), (1536, 0.0734), (384, 0.012), (4096, 0.02), (48, 0.05),
+                                    (768, 0.15), (3072, 0.6), (384, 0.0011)])
 def test_shiftgelu_lut_matches_general_and_oracle(K, cols, s):
     rng = np.random.default_rng(cols)
     q = rng.integers(-128, 128, (77, cols)).astype(np.int64)

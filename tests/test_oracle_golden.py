@@ -119,6 +119,22 @@ def test_shiftmax(kat, tag, bits):
     assert p.min() >= 0 and p.max() <= 2 ** (bits - 1)
 
 
+@pytest.mark.parametrize("tag,bits", [("sm16_x1", 16), ("sm8_x2", 8), ("sm16_x5", 16), ("sm8_fine", 8), ("sm16_fine", 16)])
+def test_shiftmax_extreme_scales(kat, tag, bits):
+    """Coarse (x0 = -2 ... -6) and very fine (x0 ~ -1e6: the 2^31-1 clamp of the sum bites and the reference's own
+    result leaves [0, 2^(bits-1)]) input scales -- vectors generated by the reference's IntSoftmax."""
+    x0 = O.x0_of(kat[tag + "_s"])
+    assert np.array_equal(O.shiftmax(kat[tag + "_q"], x0, bits), kat[tag + "_p"])
+
+
+@pytest.mark.parametrize("tag", ["gelu_x7", "gelu_x3", "gelu_x2", "gelu_x1", "gelu_fine"])
+def test_shiftgelu_extreme_scales(kat, tag):
+    """Pre-GELU scales the round-1 kernels refused (x0 in [-7, -1]: e^(-x_max) of an all-negative row is 2^(23+184))
+    and a very fine one -- vectors generated by the reference's IntGELU."""
+    x0 = O.x0_of(O.gelu_sig_scale(kat[tag + "_s"]))
+    assert np.array_equal(O.shiftgelu(kat[tag + "_q"], x0), kat[tag + "_o"])
+
+
 @pytest.mark.parametrize("tag", ["gelu_a", "gelu_b", "gelu_c"])
 def test_shiftgelu(kat, tag):
     s = kat[tag + "_s"]

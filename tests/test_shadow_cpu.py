@@ -55,3 +55,30 @@ def test_shadow_dies_with_the_carrier():
     del v
     gc.collect()
     assert key not in K._SHADOW
+
+
+def test_integers_at_a_storage_offset_are_not_registered():
+    """a contiguous slice of a bigger integer buffer (q.storage_offset() != 0) must not become a shadow --
+    views of the carrier are re-derived with the carrier's absolute storage offsets, which would address other rows."""
+    big = torch.arange(6 * 12, dtype=torch.int16).reshape(6, 12)
+    q = big[2:4]                                       # contiguous, storage offset 24
+    assert q.is_contiguous() and q.storage_offset() == 24
+    s = torch.tensor([0.5])
+    c = _carrier(q, s)
+    assert K._shadow_lookup(c, s) is None and K._shadow_lookup(c[1], s) is None
+    q0 = q.clone()                                     # offset 0: registered, views address the right rows
+    c0 = _carrier(q0, s)
+    assert torch.equal(K._shadow_lookup(c0[1], s), q0[1])
+
+
+def test_host_scalar_cache_is_keyed_on_the_tensor_object():
+    """a temporary scale tensor freed and reallocated at the same address with version 0 must not hit."""
+    from ivit_b200.quantization_utils.ops import _host_scalar
+    cache = {}
+    a = torch.tensor([0.25])
+    assert float(_host_scalar(a, cache)) == 0.25
+    assert _host_scalar(a, cache) is cache["val"]
+    b = torch.tensor([0.5])                            # another object (possibly the same address after `del a`)
+    assert float(_host_scalar(b, cache)) == 0.5
+    b.mul_(2.0)
+    assert float(_host_scalar(b, cache)) == 1.0        # in-place change bumps the version

@@ -1,0 +1,177 @@
+"""The reference's OWN model files -- models/vit_quant.py, models/swin_quant.py, models/layers_quant.py,
+models/model_utils.py, unmodified, staged under baseline/_ref by tools/fetch_ref.py -- running on the sm_100a operator
+mirror on the GPU (``ivit_b200.dropin``: the reference's ``quantization_utils`` import is the plugin boundary).
+
+Checked against digests that the reference's own quantization_utils produced in the build container
+(tests/golden/*.npz: sha256 of the integer tensor at EVERY operator boundary), then ``accelerate(ref_model)`` (fused
+engine behind the reference model object) against the CPU oracle.  This file FAILS, not skips, when the staged
+reference is missing: "runs unchanged as a drop-in" is the first sentence of the north star.
+
+(Named test_zz_* so that it runs after the kernel-level parity tests under ``pytest -x``.)
+"""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN
+
+pytestmark = pytest.mark.gpu
+
+
+def digest(a):
+    return hashlib.sha256(np.ascontiguousarray(a, dtype="<i8").tobytes()).hexdigest()
+
+
+@pytest.fixture(scope="module")
+def ref():
+    from ivit_b200.dropin import load_reference_models
+    try:
+        m = load_reference_models()
+    except FileNotFoundError as e:
+        pytest.fail("staged reference missing (run tools/fetch_ref.py / __graft_entry__.build() where /root/reference "
+                    "exists; baseline/_ref travels with the snapshot): %s" % e)
+    return m
+
+
+def _build(ref, name):
+    """Reference factory -> synthetic weights -> reference-generated calibration table -> cuda -> the reference's own
+    freeze_model (exact-type dispatch on QuantAct, model_utils.py:9)."""
+    from ivit_b200.calib import apply_calibration, load_calibration
+    from ivit_b200.synth import synth_parameters
+    cal = load_calibration(name)
+    model = getattr(ref, name)(pretrained=False).eval()
+    assert synth_parameters(model, cal["seed"]) == cal["weights_sha256"], "parameter names / shapes differ from the golden run"
+    apply_calibration(model, cal["ranges"])
+    model = model.cuda()
+    ref.unfreeze_model(model)
+    assert all(m.running_stat for m in model.modules() if type(m) is ref.QuantAct)
+    ref.freeze_model(model)
+    qa = [m for m in model.modules() if type(m) is ref.QuantAct]
+    assert len(qa) > 50 and not any(m.running_stat for m in qa)
+    return model
+
+
+def _run_with_digests(ref, model, x):
+    kinds = (ref.QuantAct, ref.QuantLinear, ref.QuantConv2d, ref.QuantMatMul, ref.IntLayerNorm, ref.IntSoftmax, ref.IntGELU)
+    got, order, hooks = {}, [], []
+
+    def mk(name):
+        def hook(mod, inp, out):
+            t, sf = out
+            got[name] = digest((t.double() / sf.double()).round().to(torch.int64).cpu().numpy())
+        return hook
+
+    for name, mod in model.named_modules():
+        if isinstance(mod, kinds):
+            hooks.append(mod.register_forward_hook(mk(name)))
+            order.append(name)
+    with torch.no_grad():
+        y = model(x)
+    for h in hooks:
+        h.remove()
+    return y, got, order
+
+
+@pytest.mark.parametrize("name,gold_file,min_checked", [
+    ("deit_tiny_patch16_224", "deit_tiny_b2.npz", 255),
+    ("swin_tiny_patch4_window7_224", "swin_tiny_b1.npz", 290),
+])
+def test_reference_graph_unchanged_on_the_mirror(ref, name, gold_file, min_checked):
+    from ivit_b200.synth import synth_images
+    import ivit_b200.quantization_utils as qu
+    assert ref.QuantAct is qu.QuantAct and ref.IntSoftmax is qu.IntSoftmax          # the classes in the reference namespace are ours
+    gold = np.load(os.path.join(GOLDEN, gold_file))
+    want = dict(zip(gold["names"].tolist(), gold["digests"].tolist()))
+    model = _build(ref, name)
+    assert type(model).__module__.startswith(ref.__name__ + "."), type(model).__module__   # built from the reference file
+    assert os.path.realpath(__import__("sys").modules[type(model).__module__].__file__).startswith(
+        os.path.realpath(os.path.dirname(ref.__file__)))
+    x = synth_images(int(gold["batch"]), seed=int(gold["seed_images"])).cuda()
+    y, got, order = _run_with_digests(ref, model, x)
+    checked = 0
+    for n in order:                                       # ~forward order: report the first divergence
+        if n in got and n in want:
+            assert got[n] == want[n], "%s on the mirror diverges from the reference's own run at %s" % (name, n)
+            checked += 1
+    assert checked >= min_checked, checked
+    yl = y.cpu().numpy().astype(np.float64)
+    err = np.abs(yl - gold["logits"].astype(np.float64)).max()
+    assert err <= 2e-6 * np.abs(gold["logits"]).max()     # head carrier: fp32 product of bit-identical integers
+    assert (yl.argmax(1) == gold["logits"].argmax(1)).all()
+
+
+@pytest.mark.parametrize("name,arch", [("deit_tiny_patch16_224", "deit"), ("swin_tiny_patch4_window7_224", "swin")])
+def test_accelerate_on_the_reference_model_object(ref, name, arch):
+    """engine.accelerate(reference model object): fused engine behind the reference's module; logits == CPU oracle."""
+    import oracle.model as OM
+    from ivit_b200.engine import accelerate
+    from ivit_b200.synth import synth_images
+    model = _build(ref, name)
+    x = synth_images(3, seed=23)
+    with torch.no_grad():
+        slow = model(x.cuda()).float().cpu().numpy()
+        accelerate(model)
+        fast = model(x.cuda()).cpu().numpy()
+    pack_meta = model._ivit_engine.meta
+    assert pack_meta["arch"] == arch
+    from ivit_b200.pack import export_deit, export_swin
+    model_cpu_pack = (export_deit if arch == "deit" else export_swin)(model.cpu())
+    want = (OM.deit_forward if arch == "deit" else OM.swin_forward)(model_cpu_pack, x.numpy())
+    assert np.array_equal(fast, want), "fused engine behind the reference model differs from the oracle"
+    assert np.abs(slow - fast).max() <= 2e-6 * np.abs(fast).max()
+
+
+def test_reference_calibration_pass_on_the_mirror_tracks_the_golden_ranges(ref):
+    """one UNFROZEN forward of the reference graph on the mirror (running min/max, quant_modules.py:170-192)
+    on the images the golden table was made with, against the ranges the reference's own quantization_utils recorded
+    (tests/golden/calib_deit_tiny_patch16_224.json).
+
+    Bitwise equality is NOT the contract here and cannot be: the golden table comes from the reference's LITERAL fp32
+    carrier run, whose IntSoftmax / IntGELU / IntLayerNorm deviate from their own integer formulas by carrier noise
+    (0.5 % / 2-4 % / ~70 % of elements off by one unit), while the mirror evaluates the formulas exactly
+    (the reference cannot run its exact-carrier form unfrozen: the fp64 carrier turns the running ranges into fp64 and
+    F.linear then rejects the dtype).  In an unfrozen pass every scale is derived from the ranges, so those one-unit
+    differences feed back into later ranges.  Stated bounds, measured on this test (max over 148 executed QuantActs):
+    the stem ranges (no integer operator upstream) are bit-identical; every other range within 2 % relative.
+    The frozen forward of the GPU-calibrated model must then classify the golden images like the reference did."""
+    from ivit_b200.calib import load_calibration
+    from ivit_b200.synth import synth_images, synth_parameters
+    name = "deit_tiny_patch16_224"
+    cal = load_calibration(name)
+    model = getattr(ref, name)(pretrained=False).eval()
+    assert synth_parameters(model, cal["seed"]) == cal["weights_sha256"]
+    model = model.cuda()
+    ref.unfreeze_model(model)
+    with torch.no_grad():
+        model(synth_images(cal["calib_batch"], cal["seed"]).cuda())
+    ref.freeze_model(model)
+    worst, executed, exact = (0.0, None), 0, 0
+    for n, mod in model.named_modules():
+        if type(mod) is ref.QuantAct and n in cal["ranges"]:
+            mn = float(torch.as_tensor(mod.min_val).float().reshape(-1)[0])
+            mx = float(torch.as_tensor(mod.max_val).float().reshape(-1)[0])
+            gmn, gmx, _ = cal["ranges"][n]
+            if gmn == 0.0 and gmx == 0.0:
+                assert mn == 0.0 and mx == 0.0, n             # never executed in the reference (qact_softmax, act_out)
+                continue
+            executed += 1
+            exact += (np.float32(mn) == np.float32(gmn) and np.float32(mx) == np.float32(gmx))
+            span = max(abs(gmn), abs(gmx))
+            rel = max(abs(mn - gmn), abs(mx - gmx)) / span
+            if rel > worst[0]:
+                worst = (rel, n)
+    print("calibration on the mirror: %d QuantActs executed, %d bit-identical to the reference's, worst relative "
+          "deviation %.3g at %s" % (executed, exact, worst[0], worst[1]))
+    assert executed > 100
+    for n in ("qact_input", "patch_embed.qact", "qact_pos"):         # upstream of every integer operator: exact
+        mod = dict(model.named_modules())[n]
+        assert np.float32(float(torch.as_tensor(mod.max_val).float().reshape(-1)[0])) == np.float32(cal["ranges"][n][1]), n
+    assert worst[0] <= 2e-2, worst
+    gold = np.load(os.path.join(GOLDEN, "deit_tiny_b2.npz"))
+    with torch.no_grad():
+        y = model(synth_images(int(gold["batch"]), seed=int(gold["seed_images"])).cuda()).float().cpu().numpy()
+    assert (y.argmax(1) == gold["logits"].argmax(1)).all()
+    assert np.abs(y - gold["logits"]).max() <= 0.1 * np.abs(gold["logits"]).max()
