@@ -446,12 +446,17 @@ extern "C" int ivit_attention_i8(ivit_ctx* ctx, const int8_t* qkv, const ivit_at
     a.sum32 = (((long long)(-ap->x0)) << ap->n) < (1LL << 23) ? 1 : 0;
     a.half_s = (ap->me_s.e >= 1 && ap->me_s.e <= 62) ? (1LL << (ap->me_s.e - 1)) : 0;
     a.half_o = (ap->me_o.e >= 1 && ap->me_o.e <= 62) ? (1LL << (ap->me_o.e - 1)) : 0;
-    // DeiT path on the tcgen05 tensor cores (ivit_attn_tc.cu) when its preconditions hold; IVIT_ATTN_TC=0 disables
+    // DeiT path on the tcgen05 tensor cores when the preconditions hold: the pipelined one-CTA-per-SM kernel
+    // (ivit_attn_pipe.cu; IVIT_ATTN_PIPE=0 disables) or round 1's two-CTA kernel (ivit_attn_tc.cu; IVIT_ATTN_TC=0 disables)
     {
         static const char* tc_env = getenv("IVIT_ATTN_TC");
+        static const char* pipe_env = getenv("IVIT_ATTN_PIPE");
         const long long e0 = ((long long)(-ap->x0)) << ap->n;              // largest exponential, E(0)
-        const bool tc = !(tc_env && tc_env[0] == '0') && ap->head_dim == 64 && !swin && p16 && fast && ap->n_tok <= 224 &&
-                        e0 >= (1LL << 15) && e0 < (1LL << 23) && ctx->encode_tiled != nullptr;
+        const bool common = ap->head_dim == 64 && !swin && p16 && fast && ap->n_tok <= 224 && ap->n == 15 &&
+                            ctx->encode_tiled != nullptr;
+        if (common && !(pipe_env && pipe_env[0] == '0') && ap->n_tok >= 49 && e0 < (1LL << 31))
+            return launch_attention_pipe(ctx, qkv, ap, a.half_s, a.half_o, out, s);
+        const bool tc = !(tc_env && tc_env[0] == '0') && common && e0 >= (1LL << 15) && e0 < (1LL << 23);
         if (tc) return launch_attention_tc(ctx, qkv, ap, a.half_s, a.half_o, out, s);
     }
     if (swin && ap->n_tok > 64) return fail(IVIT_ENOTSUP, "ivit_attention_i8: bias/mask path supports n_tok <= 64 (window attention)");

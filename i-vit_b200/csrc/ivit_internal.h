@@ -30,6 +30,9 @@ inline cudaStream_t st(ivit_stream s) { return reinterpret_cast<cudaStream_t>(s)
 // tcgen05 attention (ivit_attn_tc.cu); preconditions are checked by ivit_attention_i8
 int launch_attention_tc(ivit_ctx* ctx, const int8_t* qkv, const ivit_attn_params* ap, long long half_s, long long half_o,
                         int8_t* out, cudaStream_t s);
+// pipelined tcgen05 attention, one persistent CTA per SM (ivit_attn_pipe.cu); same preconditions, 49 <= n_tok <= 224
+int launch_attention_pipe(ivit_ctx* ctx, const int8_t* qkv, const ivit_attn_params* ap, long long half_s, long long half_o,
+                          int8_t* out, cudaStream_t s);
 inline int dtype_size(int dt) {
     switch (dt) {
         case IVIT_I8: case IVIT_U8: return 1;
