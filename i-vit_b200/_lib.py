@@ -45,6 +45,13 @@ class AttnParams(C.Structure):
                 ("mask", C.c_void_p), ("n_win", C.c_int)]
 
 
+class WinAttnParams(C.Structure):
+    _fields_ = [("n_win", C.c_int), ("n_heads", C.c_int), ("n_tok", C.c_int), ("head_dim", C.c_int),
+                ("me_s", Dyadic), ("me_s2", Dyadic), ("x0", C.c_int32), ("n", C.c_int), ("p_bits", C.c_int),
+                ("me_o", Dyadic), ("bias_rq", C.c_void_p), ("mask_bits", C.c_void_p), ("n_win_img", C.c_int),
+                ("mask_add", C.c_int32)]
+
+
 _vp, _i64, _int = C.c_void_p, C.c_int64, C.c_int
 # name -> argtypes (ctx and stream included); all return int except the first three
 SIGNATURES = {
@@ -67,6 +74,9 @@ SIGNATURES = {
     "ivit_quantize_patchify": [_vp, _vp, _vp, _int, _int, _int, _int, _int, _vp, _vp],
     "ivit_quantize_patchify_u8": [_vp, _vp, _vp, _vp, _vp, _int, _int, _int, _int, _int, _vp, _vp],
     "ivit_embed_tokens_fast": [_vp, _vp, _vp, _vp, _int, _int, _int, Dyadic, Dyadic, _vp, _vp],
+    "ivit_window_attention_i8": [_vp, _vp, C.POINTER(WinAttnParams), _vp, _vp],
+    "ivit_layernorm_gather_i16_i8": [_vp, _vp, _i64, _int, _int, _vp, _int, _int, _vp, _vp, _vp, _vp, _vp],
+    "ivit_avgpool_requant_i8": [_vp, _vp, _int, _int, _int, Dyadic, _vp, _vp],
 }
 EXPORTS = ["ivit_version", "ivit_last_error", "ivit_create", "ivit_destroy", "ivit_num_sms"] + sorted(SIGNATURES)
 

@@ -194,6 +194,9 @@ IVIT_PTX void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)[32]) {
         : "r"(taddr)
         : "memory");
 }
+IVIT_PTX void tmem_ld_32x32b_x1(uint32_t taddr, uint32_t& r) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r) : "r"(taddr) : "memory");
+}
 IVIT_PTX void tmem_ld_32x32b_x8(uint32_t taddr, uint32_t (&r)[8]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"

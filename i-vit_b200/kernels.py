@@ -334,3 +334,45 @@ def embed_tokens_fast(pe16, cls32, pos16, B: int, n_tok: int, C: int, me, me_res
     call("ivit_embed_tokens_fast", context(pe16.device), ptr(pe16), ptr(cls32), ptr(pos16), B, n_tok, C,
          Dyadic(int(me[0]), int(me[1])), Dyadic(int(me_res[0]), int(me_res[1])), ptr(out))
     return out
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Swin hot path
+# ---------------------------------------------------------------------------------------------------------------
+def window_attention_i8(qkv: torch.Tensor, n_win: int, n_heads: int, me_s, me_s2, x0: int, me_o, bias_rq: torch.Tensor,
+                        mask_bits: torch.Tensor = None, n_win_img: int = 0, mask_add: int = 0, out=None):
+    """tcgen05 window attention (49 tokens, head_dim 32, 8-bit Shiftmax); raises IvitError(ENOTSUP) outside its domain."""
+    assert qkv.dtype == torch.int8 and qkv.is_contiguous() and qkv.shape == (n_win * 49, 96 * n_heads)
+    assert bias_rq.dtype == torch.int16 and bias_rq.is_contiguous() and bias_rq.shape == (n_heads, 49, 49)
+    if out is None:
+        out = torch.empty((n_win * 49, 32 * n_heads), dtype=torch.int8, device=qkv.device)
+    p = _lib.WinAttnParams()
+    p.n_win, p.n_heads, p.n_tok, p.head_dim = n_win, n_heads, 49, 32
+    p.me_s = Dyadic(int(me_s[0]), int(me_s[1]))
+    p.me_s2 = Dyadic(int(me_s2[0]), int(me_s2[1]))
+    p.x0, p.n, p.p_bits = int(x0), 15, 8
+    p.me_o = Dyadic(int(me_o[0]), int(me_o[1]))
+    p.bias_rq = ptr(bias_rq)
+    p.mask_bits = ptr(mask_bits)
+    p.n_win_img, p.mask_add = int(n_win_img), int(mask_add)
+    call("ivit_window_attention_i8", context(qkv.device), ptr(qkv), C.byref(p), ptr(out))
+    return out
+
+
+def layernorm_gather(x: torch.Tensor, rows_out: int, C_out: int, G: int, rowmap, L_out: int, L_in: int,
+                     bias_int: torch.Tensor, me: torch.Tensor, out=None, xcopy=None):
+    """IntLayerNorm + QuantAct over gathered rows (window permutation, G = 1; 2x2 patch merging, G = 4)."""
+    assert x.dtype == torch.int16 and x.is_contiguous()
+    if out is None:
+        out = torch.empty((rows_out, C_out), dtype=torch.int8, device=x.device)
+    call("ivit_layernorm_gather_i16_i8", context(x.device), ptr(x), rows_out, C_out, G, ptr(rowmap), L_out, L_in,
+         ptr(bias_int), ptr(me), ptr(out), ptr(xcopy))
+    return out
+
+
+def avgpool_requant_i8(x: torch.Tensor, B: int, L: int, Cc: int, me, out=None):
+    assert x.dtype == torch.int8 and x.is_contiguous()
+    if out is None:
+        out = torch.empty((B, Cc), dtype=torch.int8, device=x.device)
+    call("ivit_avgpool_requant_i8", context(x.device), ptr(x), B, L, Cc, Dyadic(int(me[0]), int(me[1])), ptr(out))
+    return out

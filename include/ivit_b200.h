@@ -267,6 +267,52 @@ IVIT_API int ivit_embed_tokens(ivit_ctx*, const int16_t* pe, const int32_t* cls,
                                int B, int n_tok, int C, ivit_dyadic_t me, ivit_dyadic_t me_res,
                                int bits, int16_t* out, ivit_stream stream);
 
+/* ---- Swin hot path (swin_quant.py:121-169, 251-301, 328-349, 539-558) -------------------- */
+
+/* Fused window attention on the tcgen05 tensor cores for the shape every Swin of the reference zoo uses (49-token
+ * windows, head_dim 32, 8-bit Shiftmax): same arithmetic and results as ivit_attention_i8 with relbias / mask, two
+ * windows per 128-row MMA tile.  qkv: int8 [n_win * 49, 3 * 32 * n_heads] (windows contiguous), out: int8
+ * [n_win * 49, 32 * n_heads].
+ *   bias_rq    int16 [n_heads, 49, 49]: the identity branch of qact2 ALREADY requantised, RNE(bias_int8 * mb / 2^eb)
+ *              (static per block: ivit_requant of the gathered relative-position bias, swin_quant.py:142-149)
+ *   mask_bits  optional uint64 [n_win_img, 49]: bit j of entry (w, i) set = key j masked for query i in window w of the
+ *              image (attn_mask != 0, swin_quant.py:223-247); window index = global window % n_win_img
+ *   mask_add   the integer addend of a masked entry, RNE(-100 / s) (App. A.5); only checked: it must saturate Shiftmax
+ * Returns IVIT_ENOTSUP (nothing launched) when a scale is outside the fast-form domain; ivit_attention_i8 covers those. */
+typedef struct ivit_winattn_params {
+    int n_win, n_heads, n_tok, head_dim;
+    ivit_dyadic_t me_s;        /* scores requant (qact_attn1)                     */
+    ivit_dyadic_t me_s2;       /* qact2, scores branch                            */
+    int32_t x0;                /* floor(-1/s_2)                                   */
+    int n;                     /* 15                                              */
+    int p_bits;                /* 8                                               */
+    ivit_dyadic_t me_o;        /* P.V requant (qact3)                             */
+    const int16_t* bias_rq;
+    const uint64_t* mask_bits;
+    int n_win_img;
+    int32_t mask_add;
+} ivit_winattn_params;
+
+IVIT_API int ivit_window_attention_i8(ivit_ctx*, const int8_t* qkv, const ivit_winattn_params* p, int8_t* out,
+                                      ivit_stream stream);
+
+/* IntLayerNorm + per-channel QuantAct (as ivit_layernorm_i16_i8) over GATHERED rows: the window glue of Swin as index
+ * math in the row load.  Images hold L_in input rows and L_out output rows each; output row r of an image is built from
+ *   G == 1: input row rowmap[r] (int32 [L_out]; NULL = identity)  -- torch.roll + window_partition of this block composed
+ *           with window_reverse + roll-back of the previous one (swin_quant.py:259-288).  If xcopy != NULL the gathered
+ *           int16 row is also stored there (the residual stream in the new order);
+ *   G == 4: the concatenation of input rows rowmap[4r .. 4r+3] (int32 [L_out * 4]), each C/4 wide -- PatchMerging's strided
+ *           2x2 gather + cat (swin_quant.py:337-341) feeding norm (:344).
+ * x: int16 [images * L_in, C / G]; out: int8 [rows_out, C]; C % (8 G) == 0, C <= 1536. */
+IVIT_API int ivit_layernorm_gather_i16_i8(ivit_ctx*, const int16_t* x, int64_t rows_out, int C, int G,
+                                          const int32_t* rowmap, int L_out, int L_in, const int32_t* bias_int,
+                                          const ivit_dyadic_t* me, int8_t* out, int16_t* xcopy, ivit_stream stream);
+
+/* Token average + QuantAct (swin_quant.py:554-555): out[b, c] = clamp8(RNE(RNE(sum_t x[b, t, c] / L) * m / 2^e)).
+ * x: int8 [B, L, C], out: int8 [B, C]; C % 4 == 0. */
+IVIT_API int ivit_avgpool_requant_i8(ivit_ctx*, const int8_t* x, int B, int L, int C, ivit_dyadic_t me, int8_t* out,
+                                     ivit_stream stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -620,3 +620,118 @@ def test_layernorm_isqrt_edge_variances(K):
     want = O.layernorm(q, bq)
     got = K.layernorm(dev(q.astype(np.int32)), dev(bq.astype(np.int32)))
     assert_equal(got, want, "layernorm isqrt edge cases")
+
+
+# ------------------------------------------------------------------------------- Swin hot path (round 2)
+def pack_mask_bits(mask01):
+    """[n_win, N, N] 0/1 -> uint64 [n_win, N]: bit j of (w, i) = key j masked for query i (host side of SwinEngine)."""
+    n_win, N, _ = mask01.shape
+    w = (mask01.astype(np.uint64) << np.arange(N, dtype=np.uint64)[None, None, :]).sum(axis=2, dtype=np.uint64)
+    return np.ascontiguousarray(w)
+
+
+@pytest.mark.parametrize("n_seq,n_win,H,with_mask,s_a,s_2", [
+    (8, 4, 3, True, 0.05, 0.043), (2, 1, 6, False, 0.05, 0.043), (32, 16, 2, True, 0.05, 0.043),
+    (5, 1, 1, False, 0.021, 0.017),            # odd number of windows (last pair half empty), one head (pair half empty)
+    (6, 2, 4, True, 0.011, 0.0041),            # e_2 < 32 (s_a / s_2 > 1), fine softmax scale
+    (1300, 4, 3, True, 0.03, 0.2),             # more work units than resident CTAs; coarse softmax scale (x0 = -5)
+    (64, 64, 24, True, 0.05, 0.043)])          # 24 heads (Swin stage 4), 64 windows per image (stage 1)
+def test_window_attention_tc(K, n_seq, n_win, H, with_mask, s_a, s_2):
+    """tcgen05 window attention (two 49-token windows per MMA tile, head pairs per TMA box) against the oracle and,
+    bit for bit, against the general mma.sync kernel.  swin_quant.py:121-164."""
+    n_tok, D = 49, 32
+    rng = np.random.default_rng(100 * n_win + H + n_seq)
+    qkv = rng.integers(-128, 128, (n_seq * n_tok, 3 * H * D)).astype(np.int8)
+    qkv[::5, :H * D] = np.clip(qkv[::5, :H * D].astype(np.int32) * 3, -128, 127).astype(np.int8)
+    bias = rng.integers(-128, 128, (H, n_tok, n_tok)).astype(np.int8)
+    s_a, s_b, s_2 = np.float32(s_a), np.float32(0.004), np.float32(s_2)
+    acc_scale = np.float32(127 * s_a / (D * 127 * 30))
+    m_s, e_s = K.dyadic_host(np.array([acc_scale], np.float32), s_a)
+    m_2, e_2 = K.dyadic_host(np.array([s_a], np.float32), s_2)
+    m_b, e_b = K.dyadic_host(np.array([s_b], np.float32), s_2)
+    x0 = O.x0_of(s_2)
+    m_o, e_o = K.dyadic_host(np.array([2.0 ** -7 * 0.02], np.float32), np.float32(0.02 * 0.9))
+    mask01 = np.zeros((n_win, n_tok, n_tok), np.int64)
+    if with_mask:
+        grp = rng.integers(0, 3, (n_win, n_tok))
+        mask01 = (grp[:, :, None] != grp[:, None, :]).astype(np.int64)
+        mask01[0] = 0
+    add = int(np.rint(np.float64(-100.0) / np.float64(s_2)))
+    me_s, me_2, me_b, me_o = [(int(a[0]), int(b[0])) for a, b in ((m_s, e_s), (m_2, e_2), (m_b, e_b), (m_o, e_o))]
+    bias_rq = K.requant(dev(bias.reshape(-1, 1).astype(np.int32)), me_dev(K, m_b, e_b), 16).reshape(H, n_tok, n_tok).contiguous()
+    assert_equal(bias_rq, O.requant(bias.astype(np.int64), [m_b[0]], [e_b[0]], 16), "bias requant")
+    got = K.window_attention_i8(dev(qkv), n_seq, H, me_s, me_2, x0, me_o, bias_rq,
+                                mask_bits=dev(pack_mask_bits(mask01).view(np.int64)) if with_mask else None,
+                                n_win_img=n_win if with_mask else 0, mask_add=add if with_mask else 0)
+    gen = K.attention_i8(dev(qkv), n_seq, n_tok, H, D, me_s, x0, me_o, p_bits=8, relbias=dev(bias), me_s2=me_2, me_b=me_b,
+                         mask=dev((add * mask01).astype(np.int32)) if with_mask else None, n_win=n_win if with_mask else 0)
+    assert torch.equal(got, gen), "tcgen05 window attention differs from the general kernel: %d elements" % int((got != gen).sum())
+    if n_seq <= 64:                                   # the numpy oracle loop is slow
+        Cc = H * D
+        nb = min(n_seq, 8)
+        want = np.zeros((nb * n_tok, Cc), np.int64)
+        for b in range(nb):
+            blk = qkv[b * n_tok:(b + 1) * n_tok].astype(np.int64)
+            for h in range(H):
+                q, k, v = blk[:, h * D:(h + 1) * D], blk[:, Cc + h * D:Cc + (h + 1) * D], blk[:, 2 * Cc + h * D:2 * Cc + (h + 1) * D]
+                s = O.requant(q @ k.T, [m_s[0]], [e_s[0]], 8)
+                s = O.requant(s, [m_2[0]], [e_2[0]], 8, bias[h].astype(np.int64), [m_b[0]], [e_b[0]])
+                s = s + add * mask01[b % n_win]
+                want[b * n_tok:(b + 1) * n_tok, h * D:(h + 1) * D] = O.requant(O.shiftmax(s, x0, 8) @ v, [m_o[0]], [e_o[0]], 8)
+        assert np.abs(want).max() > 8
+        assert_equal(got[:nb * n_tok], want, "window attention n_win=%d H=%d mask=%s" % (n_win, H, with_mask))
+
+
+def test_window_attention_refuses_scales_outside_its_domain(K):
+    from ivit_b200._lib import IvitError
+    qkv = torch.zeros((2 * 49, 96), dtype=torch.int8, device="cuda")
+    b = torch.zeros((1, 49, 49), dtype=torch.int16, device="cuda")
+    with pytest.raises(IvitError, match="fast-form"):
+        K.window_attention_i8(qkv, 2, 1, (2 ** 30, 20), (2 ** 30, 31), -20, (2 ** 30, 40), b)      # e_s < 32
+    with pytest.raises(IvitError, match="fast-form"):
+        K.window_attention_i8(qkv, 2, 1, (2 ** 30 + 1, 40), (2 ** 30, 31), -20, (2 ** 30 + 1, 40), b)   # qact2: reachable tie
+
+
+@pytest.mark.parametrize("C,G,L_out,mag", [(96, 1, 56, 9000), (192, 1, 28, 20000), (384, 1, 49, 32767), (768, 1, 49, 5000),
+                                           (384, 4, 16, 9000), (768, 4, 49, 30000), (1536, 4, 9, 32767), (48, 1, 5, 300),
+                                           (1024, 4, 4, 700)])
+def test_layernorm_gather(K, C, G, L_out, mag):
+    """IntLayerNorm + QuantAct over rows gathered through a per-image map: window permutation (G = 1, with the permuted
+    int16 copy) and 2 x 2 patch merging (G = 4)."""
+    rng = np.random.default_rng(C + G)
+    B = 5
+    L_in = L_out * G
+    Cs = C // G
+    x = rng.integers(-mag, mag + 1, (B * L_in, Cs)).astype(np.int64)
+    x[1] = 7
+    x[2] = 0
+    x[2, 0] = mag
+    if G == 1:
+        rowmap = rng.permutation(L_out).astype(np.int32)
+        gathered = x.reshape(B, L_in, Cs)[:, rowmap].reshape(B * L_out, C)
+    else:
+        rowmap = rng.permutation(L_in).astype(np.int32).reshape(L_out, 4)
+        gathered = x.reshape(B, L_in, Cs)[:, rowmap.reshape(-1)].reshape(B * L_out, C)
+    bq = rng.integers(-2 ** 24, 2 ** 24, C).astype(np.int64)
+    m, e = rand_me(rng, C, 40, 52, neg_every=5)
+    want = O.requant(O.layernorm(gathered, bq), m, e, 8)
+    xcopy = torch.zeros((B * L_out, C), dtype=torch.int16, device="cuda") if G == 1 else None
+    got = K.layernorm_gather(dev(x.astype(np.int16)), B * L_out, C, G, dev(rowmap.reshape(-1)), L_out, L_in,
+                             dev(bq.astype(np.int32)), me_dev(K, m, e), xcopy=xcopy)
+    assert_equal(got, want, "layernorm_gather C=%d G=%d" % (C, G))
+    if G == 1:
+        assert_equal(xcopy, gathered, "gathered residual copy")
+        ident = K.layernorm_gather(dev(x.astype(np.int16)), B * L_out, C, 1, None, L_out, L_in, dev(bq.astype(np.int32)), me_dev(K, m, e))
+        assert_equal(ident, O.requant(O.layernorm(x, bq), m, e, 8), "identity map")
+
+
+def test_avgpool_requant(K):
+    rng = np.random.default_rng(77)
+    for B, L, C in [(3, 49, 768), (2, 49, 1024), (1, 4, 8), (5, 196, 96)]:
+        x = rng.integers(-128, 128, (B, L, C)).astype(np.int64)
+        x[0, :, 0] = 1                                   # mean exactly 1
+        x[0, :, 1] = np.arange(L) % 2                    # a .5-ish mean
+        m, e = K.dyadic_host(np.array([0.031], np.float32), np.float32(0.027))
+        want = O.requant(O.avgpool_rne(x), [m[0]], [e[0]], 8)
+        got = K.avgpool_requant_i8(dev(x.astype(np.int8)), B, L, C, (int(m[0]), int(e[0])))
+        assert_equal(got, want, "avgpool B=%d L=%d C=%d" % (B, L, C))
