@@ -12,9 +12,12 @@ parameter pack is NCCL-broadcast once from rank 0).  Prints ONE JSON line (rank 
                engine -> D2H logits, every step
   roofline     dominant kernel (tcgen05 INT8 GEMM): algorithmic int-ops / measured launch time vs the
                measured tensor peak (MEASURED_PEAKS.json bf16 x 2)
-  cpu_baseline the oracle port (oracle/, pinned to the reference) timed on this box's host cores
-  --impl reference   the reference's CPU integer path (oracle port; the reference itself is Python
-               and cannot travel to the GPU box) on rank 0 only, same metric / config
+  cpu_baseline the reference's own CPU integer path timed on this box's host cores: the UNMODIFIED reference
+               model(x) (baseline/_ref staged by tools/fetch_ref.py, its own quantization_utils, fp32 carrier, frozen:
+               kind "reference"), or the oracle port when the staged copy is absent (kind "port")
+  configs      the other single-GPU BASELINE.json configs (DeiT-small bs=128, Swin-tiny bs=128), device-timed
+  parity       logits of seeded images: every rank's sha256 all-gathered (N > 1), rank 0 against the CPU oracle
+  --impl reference   that CPU arm alone, on rank 0 only, same metric / config
 """
 from __future__ import annotations
 
@@ -42,6 +45,19 @@ def int_ops_per_image(meta) -> float:
     pe = (N - 1) * C * meta["in_chans"] * meta["patch"] ** 2
     blk = N * C * 3 * C + 2 * H * N * N * D + N * C * C + 2 * N * C * Hd
     return 2.0 * (pe + meta["depth"] * blk + C * meta["num_classes"])
+
+
+def int_ops_per_image_swin(meta) -> float:
+    """Algorithmic integer ops (2 x MAC) per image of a Swin pack (8.98e9 for Swin-tiny)."""
+    C, R = meta["embed_dim"], meta["grid"]
+    mac = R * R * C * meta["in_chans"] * meta["patch"] ** 2
+    for li, depth in enumerate(meta["depths"]):
+        L, N, Hd = R * R, meta["window"][li] ** 2, meta["mlp_hidden"][li]
+        mac += depth * (L * C * 3 * C + 2 * L * N * C + L * C * C + 2 * L * C * Hd)
+        if li + 1 < len(meta["depths"]):
+            mac += (L // 4) * (4 * C) * (2 * C)
+            C, R = 2 * C, R // 2
+    return 2.0 * (mac + C * meta["num_classes"])
 
 
 def gemm_shapes(meta, B):
@@ -131,38 +147,94 @@ def ncu_traffic(kernel_substr):
 
 def build_pack(model_name):
     from ivit_b200.calib import build_synthetic
-    from ivit_b200.pack import export_deit
-    return export_deit(build_synthetic(model_name))
+    from ivit_b200.pack import export_deit, export_swin
+    return (export_swin if model_name.startswith("swin") else export_deit)(build_synthetic(model_name))
+
+
+def make_engine(pack, dev):
+    from ivit_b200.engine import Engine
+    from ivit_b200.swin_engine import SwinEngine
+    return SwinEngine(pack, dev) if pack.meta["arch"] == "swin" else Engine(pack, dev)
+
+
+def pack_int_ops(meta) -> float:
+    return int_ops_per_image_swin(meta) if meta["arch"] == "swin" else int_ops_per_image(meta)
+
+
+# ------------------------------------------------------------------------------------------ CPU arm
+def cpu_reference_run(model_name, pack, n_img, reps_or_seconds, warmup=0):
+    """Time the reference's CPU integer path on this box's host cores.  Preferred: the UNMODIFIED reference model(x)
+    (staged under baseline/_ref, its own quantization_utils, fp32 carrier, frozen ranges from the golden calibration
+    table -- quant_train.py:325-334 call shape), kind "reference".  Fallback: the oracle port, kind "port".
+    reps_or_seconds: int = exactly that many timed forwards; float = repeat until that many seconds have passed.
+    Returns (images/s, kind, cores, sample description, seconds per forward)."""
+    from ivit_b200.synth import synth_images
+    cores = os.cpu_count() or 1
+    x = synth_images(n_img, seed=11)
+    fwd, kind = None, None
+    try:
+        from ivit_b200.calib import apply_calibration, load_calibration
+        from ivit_b200.dropin import cuda_calls_are_noops, load_reference_models
+        from ivit_b200.synth import synth_parameters
+        ref = load_reference_models(mirror=False)
+        cal = load_calibration(model_name)
+        model = getattr(ref, model_name)(pretrained=False).eval()
+        if synth_parameters(model, cal["seed"]) != cal["weights_sha256"]:
+            raise RuntimeError("reference parameter names differ from the calibration table's")
+        apply_calibration(model, cal["ranges"])
+        ref.freeze_model(model)
+        torch.set_num_threads(cores)
+
+        def fwd():
+            with torch.no_grad(), cuda_calls_are_noops():
+                return model(x)
+        kind = "reference"
+        what = "unmodified reference model(x) from baseline/_ref (fp32 carrier, frozen, torch CPU, %d threads)" % cores
+    except FileNotFoundError:
+        import oracle as O
+        import oracle.model as OM
+        O.set_threads(1)                                  # one image per host thread (images are independent)
+        xn = x.numpy()
+        if pack.meta["arch"] == "swin":
+            def fwd():
+                return OM.swin_forward(pack, xn)
+        else:
+            def fwd():
+                return OM.deit_forward_parallel(pack, xn, threads=cores)
+        kind = "port"
+        what = "oracle port (baseline/_ref not staged), one image per host thread (%d threads)" % cores
+    for _ in range(warmup):
+        fwd()
+    t0 = time.perf_counter()
+    reps = 0
+    if isinstance(reps_or_seconds, int):
+        for _ in range(max(reps_or_seconds, 1)):
+            fwd()
+            reps += 1
+    else:
+        while reps < 1 or (time.perf_counter() - t0 < reps_or_seconds and reps < 20):
+            fwd()
+            reps += 1
+    dt = (time.perf_counter() - t0) / reps
+    return n_img / dt, kind, cores, "%d forward(s) of %d images: %s" % (reps, n_img, what), dt
 
 
 # ------------------------------------------------------------------------------------------ reference arm
 def run_reference(args, rank, world):
-    """CPU arm: the oracle port of the reference's integer path (all host threads)."""
+    """CPU arm: the reference's own CPU integer path (all host threads), a bounded sample of the workload per step."""
     if rank != 0:
         return
-    import oracle as O
-    import oracle.model as OM
-    from ivit_b200.synth import synth_images
-    cores = os.cpu_count() or 1
-    O.set_threads(1)                                  # one image per host thread (images are independent)
     pack = build_pack(args.model)
-    imgs_per_step = args.ref_images or min(cores, 128)
-    x = synth_images(imgs_per_step, seed=11).numpy()
-    for _ in range(min(args.warmup, 1)):
-        OM.deit_forward_parallel(pack, x, threads=cores)
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        OM.deit_forward_parallel(pack, x, threads=cores)
-    dt = (time.perf_counter() - t0) / max(args.steps, 1)
-    val = imgs_per_step / dt
-    line = {"metric": METRIC, "value": val, "unit": "images/s", "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": min(args.warmup, 1), "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+    n_img = args.ref_images or 8
+    val, kind, cores, sample, dt = cpu_reference_run(args.model, pack, n_img, int(args.steps), warmup=args.warmup)
+    line = {"metric": METRIC if args.model == MODEL and args.batch == 256 else "images/sec %s INT8 bs=%d" % (args.model, args.batch),
+            "value": val, "unit": "images/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "int8", "data": "synthetic", "impl": "reference",
-            "config": {"workload": "%s frozen INT8 forward, 3x224x224 synthetic, batch 256 per GPU" % args.model,
-                       "note": "reference is pure Python/PyTorch and cannot travel to the GPU box; its CPU integer path "
-                               "is timed through the oracle port (oracle/, bit-pinned to the reference)"},
-            "cpu_baseline": {"value": val, "unit": "images/s", "cores": cores, "kind": "port",
-                             "sample": "%d images of the batch per step, one image per host thread (%d threads)" % (imgs_per_step, cores)},
+            "config": {"workload": "%s frozen INT8 forward, 3x224x224 synthetic fp32 images, batch %d per GPU" % (args.model, args.batch),
+                       "images_per_step": n_img,
+                       "note": "CPU arm: each step is a bounded sample of %d images of the batch (throughput is batch-flat on "
+                               "the CPU); nothing of this repository's kernels or engine is on this path" % n_img},
+            "cpu_baseline": {"value": val, "unit": "images/s", "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": val, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -207,17 +279,53 @@ def time_gemms(eng, B, iters=10):
     return res
 
 
+def device_time(fn, steps, warmup):
+    """Average ms per call of fn on the current stream (CUDA events, synchronise on both sides)."""
+    for _ in range(warmup):
+        fn()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps
+
+
+def other_config(model_name, batch, dev, peaks, steps):
+    """One of the other single-GPU BASELINE.json configs, device-timed (inputs resident, CUDA-graph replay)."""
+    pack = build_pack(model_name)
+    eng = make_engine(pack, dev)
+    g = torch.Generator(device="cpu")
+    g.manual_seed(4321)
+    x = torch.randn((batch, 3, pack.meta["img_size"], pack.meta["img_size"]), generator=g).to(dev)
+    ms = device_time(lambda: eng(x), steps, 5)
+    ops = pack_int_ops(pack.meta) * batch
+    tops = ops / (ms * 1e-3) / 1e12
+    out = {"workload": "%s frozen INT8 forward, batch %d, 1 GPU" % (model_name, batch), "value": batch / (ms * 1e-3),
+           "unit": "images/s", "ms_per_step": ms, "int_ops_per_image": pack_int_ops(pack.meta), "whole_step_int_tops": tops,
+           "frac_of_sustained_tensor_peak": tops / (2.0 * float(peaks["bf16_tflops_sustained"])),
+           "gpu_launches_per_step": eng.launches_per_forward}
+    if hasattr(eng, "attention_fallbacks"):
+        out["attention_fallbacks_to_mma_sync"] = eng.attention_fallbacks
+    del eng, x
+    torch.cuda.empty_cache()
+    return out
+
+
 def run_ours(args, rank, world, local_rank):
+    import hashlib
     import torch.distributed as dist
     from ivit_b200.dist import broadcast_pack
-    from ivit_b200.engine import Engine
     from ivit_b200.synth import synth_images
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     pack = build_pack(args.model) if rank == 0 else None
     if world > 1:
         pack = broadcast_pack(pack, src=0, device=dev)       # one-time NCCL broadcast of the frozen INT8 parameters
-    eng = Engine(pack, dev)
+    eng = make_engine(pack, dev)
+    is_deit = pack.meta["arch"] == "deit"
     B = args.batch
     g = torch.Generator(device="cpu")
     g.manual_seed(1234 + rank)
@@ -242,6 +350,18 @@ def run_ours(args, rank, world, local_rank):
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
+
+    # ---- parity outside the timed region: the same 4 seeded images on every rank (weights arrived over NCCL on ranks > 0)
+    xs = synth_images(4, seed=5)
+    logits4 = eng(xs.to(dev)).float().cpu().numpy().copy()
+    digest = hashlib.sha256(logits4.tobytes()).digest()
+    parity = {"images": 4}
+    if world > 1:
+        mine = torch.tensor(list(digest), dtype=torch.uint8, device=dev)
+        allg = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(allg, mine)
+        parity["ranks_ok"] = bool(all(torch.equal(a, allg[0]) for a in allg))
+        parity["ranks"] = world
 
     def step_resident():
         eng(x)
@@ -280,20 +400,21 @@ def run_ours(args, rank, world, local_rank):
         return step
 
     step_e2e = make_e2e(host)
-    # the same images as decoded uint8 pixels (the engine applies ToTensor + Normalize on the device): 4x fewer H2D bytes
-    host_u8 = torch.randint(0, 256, host.shape, generator=g, dtype=torch.uint8).pin_memory()
-    step_e2e_u8 = make_e2e(host_u8)
-
-    with ClockSampler(local_rank) as clk:                  # sampled from the warm-up to the end of both timed regions
+    e2e_u8_ms = None
+    with ClockSampler(local_rank) as clk:                  # sampled from the warm-up to the end of the timed regions
         for _ in range(max(args.warmup, 3)):
             step_resident()
         total_ms = timed(step_resident, args.steps)
         for _ in range(max(args.warmup, 6)):               # both staging buffers seen often enough to be graph-bound
             step_e2e()
         e2e_ms = timed(step_e2e, args.steps)
-        for _ in range(3):
-            step_e2e_u8()
-        e2e_u8_ms = timed(step_e2e_u8, args.steps)
+        if is_deit:
+            # the same images as decoded uint8 pixels (the engine applies ToTensor + Normalize on the device): 4x fewer H2D bytes
+            host_u8 = torch.randint(0, 256, host.shape, generator=g, dtype=torch.uint8).pin_memory()
+            step_e2e_u8 = make_e2e(host_u8)
+            for _ in range(3):
+                step_e2e_u8()
+            e2e_u8_ms = timed(step_e2e_u8, args.steps)
     clocks = clk.summary()
 
     ms_step = total_ms / args.steps
@@ -302,68 +423,81 @@ def run_ours(args, rank, world, local_rank):
     if rank != 0:
         return
     peaks, peak_src = measured_peaks()
-    # dominant kernel: every tcgen05 GEMM launch of the step timed in place (CUDA events on the launching stream around
-    # each launch of eager forwards), grouped by shape; the isolated L2-warm timing of time_gemms() is kept beside it
-    per_launch = eng.time_gemms(x, forwards=3)
-    groups = {}
-    for name, M_, N_, K_, ms in per_launch:
-        key = "head" if name == "head" else name.split(".")[-1] if name.startswith("blocks.") else "patch_embed"
-        g_ = groups.setdefault(key, {"name": key, "M": M_, "N": N_, "K": K_, "launches": 0, "ms": 0.0})
-        g_["launches"] += 1
-        g_["ms"] += ms
-    gem = []
-    for g_ in groups.values():
-        g_["ms"] /= g_["launches"]
-        g_["tops"] = 2.0 * g_["M"] * g_["N"] * g_["K"] / (g_["ms"] * 1e-3) / 1e12
-        gem.append(g_)
-    iso = {g_["name"]: g_["ms"] for g_ in time_gemms(eng, B)}
-    for g_ in gem:
-        g_["ms_isolated_l2_warm"] = iso.get(g_["name"])
-    ops = sum(2.0 * g_["M"] * g_["N"] * g_["K"] * g_["launches"] for g_ in gem)
-    gms = sum(g_["ms"] * g_["launches"] for g_ in gem)
-    achieved = ops / (gms * 1e-3) / 1e12
-    peak = 2.0 * float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops")))
+    peak_sus = 2.0 * float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops")))
+    peak_burst = 2.0 * float(peaks.get("bf16_tflops", peaks.get("bf16_tflops_sustained")))
+    whole_tops = pack_int_ops(eng.meta) * B / (ms_step * 1e-3) / 1e12
+    roof = {"bound": "tensor", "unit": "TFLOP/s", "peak": peak_sus, "peak_burst": peak_burst,
+            "peak_source": "2 x bf16_tflops_sustained (peak) / 2 x bf16_tflops (peak_burst) of MEASURED_PEAKS.json (%s); "
+                           "int8 tensor rate = 2 x bf16" % peak_src,
+            "whole_step_int_tops": whole_tops, "whole_step_frac": whole_tops / peak_sus,
+            "whole_step_frac_burst": whole_tops / peak_burst}
+    if is_deit:
+        # dominant kernel: every tcgen05 GEMM launch of the step timed in place (CUDA events on the launching stream around
+        # each launch of eager forwards), grouped by shape; the isolated L2-warm timing of time_gemms() is kept beside it
+        per_launch = eng.time_gemms(x, forwards=3)
+        groups = {}
+        for name, M_, N_, K_, ms in per_launch:
+            key = "head" if name == "head" else name.split(".")[-1] if name.startswith("blocks.") else "patch_embed"
+            g_ = groups.setdefault(key, {"name": key, "M": M_, "N": N_, "K": K_, "launches": 0, "ms": 0.0})
+            g_["launches"] += 1
+            g_["ms"] += ms
+        gem = []
+        for g_ in groups.values():
+            g_["ms"] /= g_["launches"]
+            g_["tops"] = 2.0 * g_["M"] * g_["N"] * g_["K"] / (g_["ms"] * 1e-3) / 1e12
+            gem.append(g_)
+        iso = {g_["name"]: g_["ms"] for g_ in time_gemms(eng, B)}
+        for g_ in gem:
+            g_["ms_isolated_l2_warm"] = iso.get(g_["name"])
+        ops = sum(2.0 * g_["M"] * g_["N"] * g_["K"] * g_["launches"] for g_ in gem)
+        gms = sum(g_["ms"] * g_["launches"] for g_ in gem)
+        achieved = ops / (gms * 1e-3) / 1e12
+        nl = sum(g_["launches"] for g_ in gem)
+        traffic, tsrc = ncu_traffic("gemm_i8_tcgen05_kernel")
+        roof.update({"achieved": achieved, "frac": achieved / peak_sus, "frac_burst": achieved / peak_burst,
+                     "traffic": traffic, "traffic_source": tsrc,
+                     "timing": "CUDA events around each GEMM launch inside eager forwards (operands as produced by the preceding "
+                               "kernels): closer to a kernel timed alone than to a long step, so both the sustained (frac) and the "
+                               "burst (frac_burst) peak are stated",
+                     "algorithmic_bytes_per_launch": sum((g_["M"] * g_["K"] + g_["N"] * g_["K"] + g_["M"] * g_["N"] * (1 if g_["name"] in ("qkv", "fc1") else 4))
+                                                         * g_["launches"] for g_ in gem) / nl,
+                     "kernel": "gemm_i8_tcgen05_kernel (all %d GEMM launches of the step)" % nl,
+                     "per_shape": gem, "gemm_share_of_step": gms / ms_step})
+    else:
+        roof.update({"achieved": whole_tops, "frac": whole_tops / peak_sus, "traffic": None,
+                     "kernel": "whole step (Swin: no single dominant kernel; see profiles/launches_swin_r2*.md)"})
     cpu = None
     if not args.no_cpu_baseline:
-        import oracle as O
+        n_img = args.ref_images or 8
+        v, kind, cores, sample, _ = cpu_reference_run(args.model, pack, n_img, 12.0)
+        cpu = {"value": v, "unit": "images/s", "cores": cores, "kind": kind, "sample": sample}
+    # rank 0 against the CPU oracle on the parity images (2 of the 4: the oracle port is slow)
+    if not args.no_cpu_baseline:
         import oracle.model as OM
-        cores = os.cpu_count() or 1
-        O.set_threads(1)
-        n_img = args.ref_images or min(cores, 128)
-        xs = synth_images(n_img, seed=11).numpy()
-        t0 = time.perf_counter()
-        reps = 0
-        while reps < 1 or (time.perf_counter() - t0 < 10.0 and reps < 20):
-            OM.deit_forward_parallel(pack, xs, threads=cores)
-            reps += 1
-        dt = (time.perf_counter() - t0) / reps
-        cpu = {"value": n_img / dt, "unit": "images/s", "cores": cores, "kind": "port",
-               "sample": "%d forward(s) of %d images (same synthetic %s pack), one image per host thread (%d threads)" % (
-                   reps, n_img, args.model, cores)}
-    act_mb = B * eng.meta["n_tok"] * eng.meta["mlp_hidden"] / 1e6
-    line = {"metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
+        want = (OM.deit_forward if is_deit else OM.swin_forward)(pack, xs[:2].numpy())
+        parity["oracle_ok"] = bool(np.array_equal(logits4[:2], want))
+    configs = {}
+    if world == 1 and not args.no_other_configs:
+        for name, b in (("deit_small_patch16_224", 128), ("swin_tiny_patch4_window7_224", 128)):
+            if name != args.model:
+                configs[name] = other_config(name, b, dev, peaks, max(args.steps, 10))
+    img_mb = B * 3 * eng.meta["img_size"] ** 2 * 4 / 1e6
+    e2e = {"value": e2e_val, "unit": "images/s", "h2d_bytes_per_step": int(host.numel() * 4) * world,
+           "d2h_bytes_per_step": int(out_host.numel() * 4) * world, "ms_per_step": e2e_ms / args.steps}
+    if e2e_u8_ms is not None:
+        e2e["uint8_input"] = {"value": world * B / (e2e_u8_ms / args.steps * 1e-3), "unit": "images/s",
+                              "h2d_bytes_per_step": int(host.numel()) * world, "ms_per_step": e2e_u8_ms / args.steps,
+                              "note": "decoded uint8 pixels in, ToTensor + Normalize fused into the stem kernel"}
+    line = {"metric": METRIC if args.model == MODEL and B == 256 else "images/sec %s INT8 bs=%d" % (args.model, B),
+            "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "int8", "data": "synthetic",
             "config": {"workload": "%s frozen INT8 forward, batch %d per GPU, 3x224x224 synthetic fp32 images" % (args.model, B),
                        "global_batch": world * B, "parallelism": "batch sharded dp%d, one-time NCCL weight broadcast" % world,
-                       "l2": "no flush needed: per-step working set (fp32 input %.0f MB + fc1/GELU activations 2 x %.0f MB) exceeds the 126 MB L2" % (
-                           B * 3 * 224 * 224 * 4 / 1e6, act_mb),
-                       "int_ops_per_image": int_ops_per_image(eng.meta)},
-            "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                         "traffic": ncu_traffic("gemm_i8_tcgen05_kernel")[0], "traffic_source": ncu_traffic("gemm_i8_tcgen05_kernel")[1],
-                         "timing": "CUDA events around each GEMM launch inside eager forwards (operands as produced by the preceding kernels)",
-                         "algorithmic_bytes_per_launch": sum((g_["M"] * g_["K"] + g_["N"] * g_["K"] + g_["M"] * g_["N"] * (1 if g_["name"] in ("qkv", "fc1") else 4))
-                                                             * g_["launches"] for g_ in gem) / sum(g_["launches"] for g_ in gem), "kernel": "gemm_i8_tcgen05_kernel (all %d GEMM launches of the step)" % sum(g_["launches"] for g_ in gem),
-                         "peak_source": "2 x bf16_tflops_sustained of MEASURED_PEAKS.json (%s); int8 tensor rate = 2 x bf16" % peak_src,
-                         "per_shape": gem, "gemm_share_of_step": gms / ms_step,
-                         "whole_step_int_tops": int_ops_per_image(eng.meta) * B / (ms_step * 1e-3) / 1e12},
-            "cpu_baseline": cpu,
-            "e2e": {"value": e2e_val, "unit": "images/s", "h2d_bytes_per_step": int(host.numel() * 4) * world,
-                    "d2h_bytes_per_step": int(out_host.numel() * 4) * world, "ms_per_step": e2e_ms / args.steps,
-                    "uint8_input": {"value": world * B / (e2e_u8_ms / args.steps * 1e-3), "unit": "images/s",
-                                    "h2d_bytes_per_step": int(host_u8.numel()) * world, "ms_per_step": e2e_u8_ms / args.steps,
-                                    "note": "decoded uint8 pixels in, ToTensor + Normalize fused into the stem kernel"}},
-            "gpu_launches": (eng.launches_per_forward - 1) * args.steps,
+                       "l2": "no flush needed: per-step working set (fp32 input %.0f MB + activations) exceeds the 126 MB L2" % img_mb,
+                       "int_ops_per_image": pack_int_ops(eng.meta)},
+            "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "parity": parity, "configs": configs,
+            "gpu_launches": eng.launches_per_forward * args.steps,
             "clocks": clocks}
     print(json.dumps(line), flush=True)
 
@@ -376,8 +510,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--model", default=MODEL)
     ap.add_argument("--batch", type=int, default=256, help="images per GPU per step")
-    ap.add_argument("--ref-images", type=int, default=0, help="images per CPU-baseline step (bounded sample; 0 = one per host core, max 128)")
+    ap.add_argument("--ref-images", type=int, default=0, help="images per CPU-baseline step (bounded sample; 0 = 8)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-other-configs", action="store_true", help="skip the DeiT-small / Swin-tiny lines of `configs`")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

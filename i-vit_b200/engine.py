@@ -61,6 +61,7 @@ class Engine:
         self._norm = (torch.tensor([0.485, 0.456, 0.406], dtype=torch.float32, device=self.device),
                       torch.tensor([0.229, 0.224, 0.225], dtype=torch.float32, device=self.device))
         self._gemm_events = None
+        self._cls_map = torch.zeros(1, dtype=torch.int32, device=self.device)      # x[:, 0] as a row map (vit_quant.py:272)
         self.launches_per_forward = 0
 
     # ------------------------------------------------------------------ parameter transport
@@ -155,9 +156,13 @@ class Engine:
             tap(p + "mlp.qact1", b["g8"])
             lin(p + "mlp.fc2", b["g8"], x, p + "mlp.qact2", 16, residual=x2, stage2=p + "qact4"); n += 1
             tap(p + "qact4", x)
-        # final norm on the cls rows only (LayerNorm is row-wise; vit_quant.py:271-273), then the head
-        b["cls16"].copy_(x.view(B, N, C)[:, 0]); n += 1
-        _layernorm_into(b["cls16"], t["norm.bias_integer"], t["qact2.me"], b["cls8"]); n += 1
+        # final norm on the cls rows only (LayerNorm is row-wise; vit_quant.py:271-273), then the head.  The x[:, 0] slice
+        # is the row map of the gathering LayerNorm (one output row per image: token 0 of its N input rows)
+        if C % 8 == 0 and C <= 1536:
+            K.layernorm_gather(x, B, C, 1, self._cls_map, 1, N, t["norm.bias_integer"], t["qact2.me"], out=b["cls8"]); n += 1
+        else:
+            b["cls16"].copy_(x.view(B, N, C)[:, 0])
+            _layernorm_into(b["cls16"], t["norm.bias_integer"], t["qact2.me"], b["cls8"]); n += 1
         tap("qact2", b["cls8"])
         K.gemm_i8(b["cls8"], t["head.weight_integer"], bias=t["head.bias_integer"], mode="carrier",
                   scale=t["head.out_scale"], out=b["logits"]); n += 1
