@@ -81,8 +81,8 @@ attention_pipe_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
     uint32_t* sRedMax = reinterpret_cast<uint32_t*>(smem + AP_RED);                    // [4][128]
     unsigned long long* sRedSum = reinterpret_cast<unsigned long long*>(smem + AP_RED + 4 * 128 * 4);   // [4][128]
     const uint32_t bar = base + AP_BAR;
-    const uint32_t q_full = bar, kv_full = bar + 16, s_full = bar + 32, s_free = bar + 40, p_ready = bar + 48,
-                   o_full = bar + 56, o_free = bar + 64;
+    const uint32_t q_full = bar, k_full = bar + 16, s_full = bar + 32, s_free = bar + 40, p_ready = bar + 48,
+                   o_full = bar + 56, o_free = bar + 64, v_full = bar + 72;
     volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + AP_BAR + 96);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -98,8 +98,10 @@ attention_pipe_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
         ptx::prefetch_tensormap(&tmap_k);
         ptx::mbar_init(q_full, 1);
         ptx::mbar_init(q_full + 8, 1);
-        ptx::mbar_init(kv_full, 1);
-        ptx::mbar_init(kv_full + 8, 1);
+        ptx::mbar_init(k_full, 1);
+        ptx::mbar_init(k_full + 8, 1);
+        ptx::mbar_init(v_full, 1);
+        ptx::mbar_init(v_full + 8, 1);
         ptx::mbar_init(s_full, 1);
         ptx::mbar_init(s_free, AP_SW);
         ptx::mbar_init(p_ready, AP_SW);
@@ -137,12 +139,20 @@ attention_pipe_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
                 b = work / p.H;
                 h = work % p.H;
             };
-            auto load_kv = [&](int it) {
+            // K and V of item `it` go to buffer (it & 1); each has its own barrier so that K of item it+2 can be requested as
+            // soon as the last score MMA of item it has completed, and V once its last P V result has been read
+            auto load_k = [&](int it) {
                 int b, h;
                 item_of(it, b, h);
-                const uint32_t fb = kv_full + 8u * (uint32_t)(it & 1);
-                ptx::mbar_arrive_expect_tx(fb, 2 * AP_KV_BYTES);                    // keys >= n_tok read as zeros
+                const uint32_t fb = k_full + 8u * (uint32_t)(it & 1);
+                ptx::mbar_arrive_expect_tx(fb, AP_KV_BYTES);                        // keys >= n_tok read as zeros
                 ptx::tma_load_3d(sK + (uint32_t)((it & 1) * AP_KV_BYTES), &tmap_k, fb, HD + h * 64, 0, b);
+            };
+            auto load_v = [&](int it) {
+                int b, h;
+                item_of(it, b, h);
+                const uint32_t fb = v_full + 8u * (uint32_t)(it & 1);
+                ptx::mbar_arrive_expect_tx(fb, AP_KV_BYTES);
                 ptx::tma_load_3d(sV + (uint32_t)((it & 1) * AP_KV_BYTES), &tmap_k, fb, 2 * HD + h * 64, 0, b);
             };
             auto load_q = [&](int t) {
@@ -155,7 +165,7 @@ attention_pipe_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
             auto issue_s = [&](int t) {
                 const int it = t / n_mt;
                 ptx::mbar_wait(q_full + 8u * (uint32_t)(t & 1), (uint32_t)(t >> 1) & 1u);
-                if (t % n_mt == 0) ptx::mbar_wait(kv_full + 8u * (uint32_t)(it & 1), (uint32_t)(it >> 1) & 1u);
+                if (t % n_mt == 0) ptx::mbar_wait(k_full + 8u * (uint32_t)(it & 1), (uint32_t)(it >> 1) & 1u);
                 ptx::tc_fence_after();
                 const uint64_t dq = ap_desc_sw64(sQ + (uint32_t)((t & 1) * 8192));
                 const uint64_t dk = ap_desc_sw64(sK + (uint32_t)((it & 1) * AP_KV_BYTES));
@@ -164,21 +174,32 @@ attention_pipe_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
                     ptx::mma_i8_ss(tmem_base, dq + (uint64_t)(2 * k), dk + (uint64_t)(2 * k), idesc_s, k ? 1u : 0u);
                 ptx::mma_commit(s_full);
             };
-            load_kv(0);
+            load_k(0);
             load_q(0);
+            load_v(0);
             if (T > 1) load_q(1);
-            if (n_it > 1) load_kv(1);
+            if (n_it > 1) {
+                load_k(1);
+                load_v(1);
+            }
             issue_s(0);
 #pragma unroll 1
             for (int t = 0; t < T; ++t) {
                 const int it = t / n_mt, mt = t % n_mt;
                 ptx::mbar_wait(s_free, (uint32_t)t & 1u);                           // S(t) is in registers: the columns are free
+                // S(t) has completed: its Q buffer takes tile t+2, and after an item's last score MMA its K buffer takes
+                // the item after next
+                if (mt == n_mt - 1 && it + 2 < n_it) load_k(it + 2);
                 if (t + 1 < T) issue_s(t + 1);
-                if (t + 2 < T) load_q(t + 2);                                       // Q buffer (t & 1): S(t) has completed
+                if (t + 2 < T) load_q(t + 2);
                 ptx::mbar_wait(p_ready, (uint32_t)t & 1u);                          // probabilities of tile t are in shared memory
-                if (t > 0) ptx::mbar_wait(o_free, (uint32_t)(t - 1) & 1u);          // O(t-1) has been read out of TMEM
-                // every MMA of the previous item has completed: its K / V buffers take the item after this one
-                if (mt == 0 && it >= 1 && it + 1 < n_it) load_kv(it + 1);
+                if (t > 0) {
+                    ptx::mbar_wait(o_free, (uint32_t)(t - 1) & 1u);                 // O(t-1) has been read out of TMEM
+                    // ... so P V(t-1) has completed: after an item's last tile its V buffer takes the item after next
+                    const int itp = (t - 1) / n_mt;
+                    if ((t - 1) % n_mt == n_mt - 1 && itp + 2 < n_it) load_v(itp + 2);
+                }
+                if (mt == 0) ptx::mbar_wait(v_full + 8u * (uint32_t)(it & 1), (uint32_t)(it >> 1) & 1u);
                 ptx::tc_fence_after();
                 const uint32_t sVi = sV + (uint32_t)((it & 1) * AP_KV_BYTES);
 #pragma unroll 1

@@ -16,6 +16,11 @@ def pytest_configure(config):
 def pytest_collection_modifyitems(config, items):
     import torch
     if torch.cuda.is_available():
+        # a hung kernel must fail its test, not eat the whole GPU session (pytest-timeout is in the image)
+        if config.pluginmanager.hasplugin("timeout"):
+            for it in items:
+                if "gpu" in it.keywords and it.get_closest_marker("timeout") is None:
+                    it.add_marker(pytest.mark.timeout(600))
         return
     skip = pytest.mark.skip(reason="no CUDA device")
     for it in items:
