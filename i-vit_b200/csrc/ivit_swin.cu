@@ -11,6 +11,9 @@
 //                                      residual epilogue)
 //                               G = 4  out row r <- the concatenation of four in rows map[4r..4r+3]: PatchMerging's
 //                                      strided 2x2 gather + cat (:337-341) feeding its LayerNorm(4C) (:344-345)
+//                               IN8 / OUT16: the patch embedding's norm (layers_quant.py:193-195 + swin_quant.py:546) reads the
+//                                      8-bit qact_before_norm output and applies TWO 16-bit QuantActs in a row
+//                                      (patch_embed.qact per channel, then the model's qact1, scalar) -> int16 stream
 //   avgpool_requant_kernel    token average RNE(sum / L) (AdaptiveAvgPool1d on the carrier, :554) + qact3 (:555)
 #include <stdlib.h>
 
@@ -37,16 +40,25 @@ __device__ __forceinline__ int32_t g_dp2a_lo_ss(uint32_t a, uint32_t b, int32_t 
     return d;
 }
 
+// prmt.b32 in its generic form: selector nibbles with bit 3 set replicate the SIGN of the selected byte (the
+// __byte_perm intrinsic only honours the low three bits of a nibble)
+__device__ __forceinline__ uint32_t g_prmt(uint32_t a, uint32_t b, uint32_t sel) {
+    uint32_t d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+    return d;
+}
+
 constexpr int LNG_MAXC = 1536;      // 4 * 384: the widest merge LayerNorm of the Swin zoo (Swin-B: 4 * 512 takes the general kernel)
 
 // LPR lanes per row (32 / LPR rows per warp), NV 16-byte vectors (8 channels) per lane; C == 8 * NV * LPR when FULL.
 // G source rows per output row (1 or 4), each Cs = C / G channels wide.  Statistics and arithmetic: see
 // layernorm_i16_i8_kernel (one packed pass with IDP.2A, exact 64-bit variance, closed-form integer square root).
-template <int NV, int LPR, bool FULL, int G>
+template <int NV, int LPR, bool FULL, int G, bool IO16 = false>
 __global__ void __launch_bounds__(256, 2)
 layernorm_gather_kernel(const int16_t* __restrict__ x, int64_t rows, int C, const int32_t* __restrict__ rowmap, int L_out,
                         int L_in, const int32_t* __restrict__ bias_int, const ivit_dyadic_t* __restrict__ me,
-                        int8_t* __restrict__ out, int16_t* __restrict__ xcopy) {
+                        int8_t* __restrict__ out, int16_t* __restrict__ xcopy, ivit_dyadic_t me2 = ivit_dyadic_t{0, 0}) {
+    // IO16 (G == 1, no map): x is INT8 [rows, C]; out is INT16 [rows, C] = clamp16(RNE(clamp16(RNE(y*m/2^e)) * m2 / 2^e2))
     constexpr int RPW = 32 / LPR;
     const int lane = threadIdx.x & 31;
     const int sub = lane % LPR, rsel = lane / LPR;
@@ -63,7 +75,20 @@ layernorm_gather_kernel(const int16_t* __restrict__ x, int64_t rows, int C, cons
         const uint32_t img = (uint32_t)row / (uint32_t)L_out;
         const uint32_t r = (uint32_t)row - img * (uint32_t)L_out;
         const int64_t in0 = (int64_t)img * L_in;
-        if constexpr (G == 1) {
+        if constexpr (IO16) {
+            // 8 int8 channels per vector -> four words of two sign-extended int16 (PRMT with sign replication)
+            const uint2* src = reinterpret_cast<const uint2*>(reinterpret_cast<const int8_t*>(x) + (in0 + r) * (int64_t)C);
+#pragma unroll
+            for (int j = 0; j < NV; ++j) {
+                const int vi = sub + LPR * j;
+                w[j] = make_uint4(0, 0, 0, 0);
+                if (FULL || vi < nvec) {
+                    const uint2 v = __ldg(src + vi);
+                    w[j] = make_uint4(g_prmt(v.x, 0u, 0x9180u), g_prmt(v.x, 0u, 0xB3A2u),
+                                      g_prmt(v.y, 0u, 0x9180u), g_prmt(v.y, 0u, 0xB3A2u));
+                }
+            }
+        } else if constexpr (G == 1) {
             const int sr = rowmap ? __ldg(rowmap + r) : (int)r;
             const uint4* src = reinterpret_cast<const uint4*>(x + (in0 + sr) * (int64_t)C);
 #pragma unroll
@@ -103,12 +128,13 @@ layernorm_gather_kernel(const int16_t* __restrict__ x, int64_t rows, int C, cons
     }
     const bool fast = __syncthreads_and(ok) != 0;
     const float inv_c = 1.0f / (float)C;
+    const UniRq rq2 = make_unirq(me2, 16);                       // IO16: the second (scalar) QuantAct on a 16-bit operand
     for (; rbase < rows; rbase += nwarps * RPW) {
         const int64_t row = rbase + rsel;
         const bool row_ok = row < rows;
         const int64_t rnext = rbase + nwarps * RPW;
         if (rnext < rows) load_row(rnext, wn);                   // in flight during this row's arithmetic
-        if (G == 1 && xcopy != nullptr && row_ok) {              // the gathered row in the new order (residual stream)
+        if (!IO16 && G == 1 && xcopy != nullptr && row_ok) {              // the gathered row in the new order (residual stream)
             uint4* dstx = reinterpret_cast<uint4*>(xcopy + row * (int64_t)C);
 #pragma unroll
             for (int j = 0; j < NV; ++j) {
@@ -174,12 +200,23 @@ layernorm_gather_kernel(const int16_t* __restrict__ x, int64_t rows, int C, cons
                         r[u] = requant32_general((int32_t)o, p.m, p.sh + 32);
                     }
                 }
-                uint32_t lo, hi, w0, w1;
-                asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, %3;" : "=r"(hi) : "r"(r[3]), "r"(r[2]), "r"(0));
-                asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, %3;" : "=r"(w0) : "r"(r[1]), "r"(r[0]), "r"(hi));
-                asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, %3;" : "=r"(lo) : "r"(r[7]), "r"(r[6]), "r"(0));
-                asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, %3;" : "=r"(w1) : "r"(r[5]), "r"(r[4]), "r"(lo));
-                dst[vi] = make_uint2(w0, w1);
+                if constexpr (IO16) {
+                    uint32_t ow[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int32_t a = clamp_bits<16>(unirq_apply(rq2, clamp_bits<16>(r[2 * u])));
+                        const int32_t b = clamp_bits<16>(unirq_apply(rq2, clamp_bits<16>(r[2 * u + 1])));
+                        ow[u] = ((uint32_t)a & 0xffffu) | ((uint32_t)b << 16);
+                    }
+                    reinterpret_cast<uint4*>(reinterpret_cast<int16_t*>(out) + (row_ok ? row : rbase) * (int64_t)C)[vi] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+                } else {
+                    uint32_t lo, hi, w0, w1;
+                    asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, %3;" : "=r"(hi) : "r"(r[3]), "r"(r[2]), "r"(0));
+                    asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, %3;" : "=r"(w0) : "r"(r[1]), "r"(r[0]), "r"(hi));
+                    asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, %3;" : "=r"(lo) : "r"(r[7]), "r"(r[6]), "r"(0));
+                    asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, %3;" : "=r"(w1) : "r"(r[5]), "r"(r[4]), "r"(lo));
+                    dst[vi] = make_uint2(w0, w1);
+                }
             }
         }
         if (rnext < rows) {
@@ -251,6 +288,34 @@ int ivit_layernorm_gather_i16_i8(ivit_ctx* ctx, const int16_t* x, int64_t rows_o
 #undef LG_G
 #undef LG_K
     IVIT_LAUNCH_OK("layernorm_gather_kernel");
+    return IVIT_OK;
+}
+
+int ivit_layernorm_i8_i16x2(ivit_ctx* ctx, const int8_t* x, int64_t rows, int C, const int32_t* bias_int,
+                            const ivit_dyadic_t* me, ivit_dyadic_t me2, int16_t* out, ivit_stream stream) {
+    IVIT_REQUIRE(ctx && x && bias_int && me && out && rows > 0 && rows < (1LL << 31), "ivit_layernorm_i8_i16x2: bad arguments");
+    IVIT_REQUIRE(C % 8 == 0 && C >= 8 && C <= LNG_MAXC, "ivit_layernorm_i8_i16x2: C must be a multiple of 8, <= %d", LNG_MAXC);
+    IVIT_REQUIRE(((uintptr_t)x % 8) == 0 && ((uintptr_t)out % 16) == 0, "ivit_layernorm_i8_i16x2: alignment");
+    const int nvec = C / 8;
+    int lpr = 4;
+    while (lpr < 32 && (nvec + lpr - 1) / lpr > 6) lpr *= 2;
+    const int nv = (nvec + lpr - 1) / lpr;
+    IVIT_REQUIRE(nv <= 6, "ivit_layernorm_i8_i16x2: C too wide");
+    const bool full = nv * lpr == nvec;
+    const int rpb = 8 * (32 / lpr);
+    const int64_t want = (rows + rpb - 1) / rpb;
+    const int grid = (int)(want < (int64_t)ctx->num_sms * 2 ? want : (int64_t)ctx->num_sms * 2);
+    const int L = 1;
+#define LQ_K(NV, LPR, FULLV) layernorm_gather_kernel<NV, LPR, FULLV, 1, true><<<grid, 256, 0, st(stream)>>>( \
+        reinterpret_cast<const int16_t*>(x), rows, C, nullptr, L, L, bias_int, me, reinterpret_cast<int8_t*>(out), nullptr, me2)
+#define LQ_F(NV, LPR) do { if (full) LQ_K(NV, LPR, true); else LQ_K(NV, LPR, false); } while (0)
+#define LQ_L(NV) do { switch (lpr) { case 4: LQ_F(NV, 4); break; case 8: LQ_F(NV, 8); break; case 16: LQ_F(NV, 16); break; default: LQ_F(NV, 32); break; } } while (0)
+    switch (nv) { case 1: LQ_L(1); break; case 2: LQ_L(2); break; case 3: LQ_L(3); break; case 4: LQ_L(4); break;
+                  case 5: LQ_L(5); break; default: LQ_L(6); break; }
+#undef LQ_L
+#undef LQ_F
+#undef LQ_K
+    IVIT_LAUNCH_OK("layernorm_gather_kernel (int8 -> int16 x2)");
     return IVIT_OK;
 }
 

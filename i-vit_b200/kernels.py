@@ -376,3 +376,13 @@ def avgpool_requant_i8(x: torch.Tensor, B: int, L: int, Cc: int, me, out=None):
         out = torch.empty((B, Cc), dtype=torch.int8, device=x.device)
     call("ivit_avgpool_requant_i8", context(x.device), ptr(x), B, L, Cc, Dyadic(int(me[0]), int(me[1])), ptr(out))
     return out
+
+
+def layernorm_i8_i16x2(x: torch.Tensor, bias_int: torch.Tensor, me: torch.Tensor, me2, out=None):
+    """IntLayerNorm over int8 rows + two 16-bit QuantActs in a row (Swin patch embedding tail)."""
+    assert x.dtype == torch.int8 and x.is_contiguous() and x.dim() == 2
+    if out is None:
+        out = torch.empty(x.shape, dtype=torch.int16, device=x.device)
+    call("ivit_layernorm_i8_i16x2", context(x.device), ptr(x), x.shape[0], x.shape[1], ptr(bias_int), ptr(me),
+         Dyadic(int(me2[0]), int(me2[1])), ptr(out))
+    return out

@@ -12,8 +12,8 @@ Every QuantAct is fused into the kernel that produces its input, and the window 
   by norm1's row load (``ivit_layernorm_gather_i16_i8``, G = 1), which also writes the permuted int16 stream for the
   residual branch.  PatchMerging's gather + cat is the same kernel with four source rows per output row (G = 4).
 
-    patch embedding      quantize+unfold (4x4) | tcgen05 GEMM (K = 48) + qact_before_norm | LayerNorm + 16-bit QuantAct |
-                         qact1 requant
+    patch embedding      quantize+unfold (4x4) | tcgen05 GEMM (K = 48) + qact_before_norm | LayerNorm + patch_embed.qact
+                         + qact1 (two 16-bit QuantActs) in one pass
     block                norm1+qact1 (gathered rows -> int8, + permuted int16 stream) | qkv GEMM (+attn.qact1) |
                          tcgen05 window attention: scores -> qact_attn1 -> qact2 (+ relative-position bias) -> mask ->
                          8-bit Shiftmax -> P V -> qact3 | proj GEMM (+attn.qact4, + residual QuantAct qact2 in the
@@ -174,10 +174,12 @@ class SwinEngine:
         patches = K.quantize_patchify(img, t["qact_input.scale"], P); n += 1            # swin_quant.py:540, layers_quant.py:190
         x8 = lin("patch_embed.proj", patches, "patch_embed.qact_before_norm", 8); n += 1  # :190 + :193
         tap("patch_embed.qact_before_norm", x8, (B, G * G, C))
-        x = K.layernorm(x8, t["patch_embed.norm.bias_integer"], t["patch_embed.qact.me"], bits=16); n += 1   # :194-195
-        tap("patch_embed.qact", x, (B, G * G, C))
-        x = K.requant(x, t["qact1.me"], 16); n += 1                                     # swin_quant.py:546
-        tap("qact1", x, (B, G * G, C))
+        if taps is not None:                                                            # the two QuantActs one by one (diagnostic launches)
+            x = K.layernorm(x8, t["patch_embed.norm.bias_integer"], t["patch_embed.qact.me"], bits=16)   # :194-195
+            tap("patch_embed.qact", x, (B, G * G, C))
+            tap("qact1", K.requant(x, t["qact1.me"], 16), (B, G * G, C))                # swin_quant.py:546
+        # norm + patch_embed.qact (16 bit, per channel) + the model's qact1 (16 bit) in one pass over the int8 rows
+        x = K.layernorm_i8_i16x2(x8, t["patch_embed.norm.bias_integer"], t["patch_embed.qact.me"], s["qact1.me"]); n += 1
 
         R = G
         for li, depth in enumerate(m["depths"]):

@@ -308,6 +308,12 @@ IVIT_API int ivit_layernorm_gather_i16_i8(ivit_ctx*, const int16_t* x, int64_t r
                                           const int32_t* rowmap, int L_out, int L_in, const int32_t* bias_int,
                                           const ivit_dyadic_t* me, int8_t* out, int16_t* xcopy, ivit_stream stream);
 
+/* Swin patch embedding tail (layers_quant.py:193-195, swin_quant.py:546): IntLayerNorm over the 8-bit qact_before_norm
+ * output followed by TWO 16-bit QuantActs, patch_embed.qact (per channel, me[C]) and the model's qact1 (scalar me2):
+ * out = clamp16(RNE(clamp16(RNE(LN(x) * m[c] / 2^e[c])) * m2 / 2^e2)).  x: int8 [rows, C]; out: int16 [rows, C]. */
+IVIT_API int ivit_layernorm_i8_i16x2(ivit_ctx*, const int8_t* x, int64_t rows, int C, const int32_t* bias_int,
+                                     const ivit_dyadic_t* me, ivit_dyadic_t me2, int16_t* out, ivit_stream stream);
+
 /* Token average + QuantAct (swin_quant.py:554-555): out[b, c] = clamp8(RNE(RNE(sum_t x[b, t, c] / L) * m / 2^e)).
  * x: int8 [B, L, C], out: int8 [B, C]; C % 4 == 0. */
 IVIT_API int ivit_avgpool_requant_i8(ivit_ctx*, const int8_t* x, int B, int L, int C, ivit_dyadic_t me, int8_t* out,

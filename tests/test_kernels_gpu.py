@@ -735,3 +735,20 @@ def test_avgpool_requant(K):
         want = O.requant(O.avgpool_rne(x), [m[0]], [e[0]], 8)
         got = K.avgpool_requant_i8(dev(x.astype(np.int8)), B, L, C, (int(m[0]), int(e[0])))
         assert_equal(got, want, "avgpool B=%d L=%d C=%d" % (B, L, C))
+
+
+@pytest.mark.parametrize("C,rows", [(96, 1000), (128, 77), (192, 64), (40, 33)])
+def test_layernorm_i8_i16x2(K, C, rows):
+    """Swin patch embedding tail: IntLayerNorm over int8 rows + patch_embed.qact (per channel, 16 bit) + qact1 (scalar, 16 bit)."""
+    rng = np.random.default_rng(C)
+    q = rng.integers(-128, 128, (rows, C)).astype(np.int64)
+    q[1] = 7
+    q[2] = 0
+    q[2, 0] = 127
+    bq = rng.integers(-2 ** 24, 2 ** 24, C).astype(np.int64)
+    m, e = rand_me(rng, C, 44, 50, neg_every=5)
+    m2, e2 = K.dyadic_host(np.array([0.00031], np.float32), np.float32(0.00047))
+    want = O.requant(O.requant(O.layernorm(q, bq), m, e, 16), [m2[0]], [e2[0]], 16)
+    got = K.layernorm_i8_i16x2(dev(q.astype(np.int8)), dev(bq.astype(np.int32)), me_dev(K, m, e), (int(m2[0]), int(e2[0])))
+    assert np.abs(want).max() > 1000
+    assert_equal(got, want, "layernorm_i8_i16x2 C=%d" % C)
