@@ -234,10 +234,8 @@ attention_pipe_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
         const uint32_t sE_lane = ptx::smem_u32(sE) + 4u * (uint32_t)lane;
 
         // output of tile tp (its P V MMAs were committed to o_full long ago): (O_hi << 8) + O_lo -> attn.qact2 -> int8
-        auto do_output = [&](int tp) {
-            const int itp = tp / n_mt, mtp = tp % n_mt;
-            const int work = (int)blockIdx.x + itp * (int)gridDim.x;
-            const int b = work / p.H, h = work % p.H;
+        // (no divisions per tile: the (m-tile, output address) of the previous tile is carried along the loop)
+        auto do_output = [&](int mtp, uint32_t obase) {
             const int row = mtp * 128 + trow;
             if ((mtp * 128 + lg * 32) >= n_tok) {          // my 32 rows lie past the sequence: nothing to read
                 __syncwarp();
@@ -264,15 +262,27 @@ attention_pipe_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
                 asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, %3;" : "=r"(hi2) : "r"(o[3]), "r"(o[2]), "r"(0));
                 asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, %3;" : "=r"(ow[w]) : "r"(o[1]), "r"(o[0]), "r"(hi2));
             }
-            if (row < n_tok) {
-                int8_t* dst = out + ((long long)b * n_tok + row) * (long long)HD + h * 64 + 16 * part;
-                *reinterpret_cast<uint4*>(dst) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
-            }
+            if (row < n_tok) *reinterpret_cast<uint4*>(out + obase + (uint32_t)(row * HD)) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
         };
+        // obase(item) = byte offset of (row 0, my 16 channels of the item's head) in `out` (< 2^32: host-checked)
+        auto item_base = [&](int it) -> uint32_t {
+            const int work = (int)blockIdx.x + it * (int)gridDim.x;
+            const int b = work / p.H, h = work - b * p.H;
+            return (uint32_t)(b * n_tok) * (uint32_t)HD + (uint32_t)(h * 64 + 16 * part);
+        };
+        int mt = 0, it_cur = 0;
+        uint32_t ob_cur = item_base(0), ob_prev = ob_cur;
 
 #pragma unroll 1
         for (int t = 0; t < T; ++t) {
-            const int mt = t % n_mt;
+            const int mt_prev = mt;
+            if (t > 0) {                                   // advance (item, m-tile); remember the previous tile for its output
+                ob_prev = ob_cur;
+                if (++mt == n_mt) {
+                    mt = 0;
+                    ob_cur = item_base(++it_cur);
+                }
+            }
             const bool act = (mt * 128 + lg * 32) < n_tok;
             ptx::mbar_wait(s_full, (uint32_t)t & 1u);
             ptx::tc_fence_after();
@@ -287,7 +297,7 @@ attention_pipe_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
                 }
                 __syncwarp();
                 if (lane == 0) ptx::mbar_arrive(p_ready);
-                if (t > 0) do_output(t - 1);
+                if (t > 0) do_output(mt_prev, ob_prev);
                 continue;
             }
             // ---- pass 1: scores -> requant -> saturate to int8, four per register (signed bytes) ----
@@ -395,7 +405,7 @@ attention_pipe_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
 #pragma unroll
             for (int pp = 0; pp < 4; ++pp) S += sRedSum[pp * 128 + trow];
             if (p.dbg != nullptr && part == 0) {
-                const int work = (int)blockIdx.x + (t / n_mt) * (int)gridDim.x;
+                const int work = (int)blockIdx.x + it_cur * (int)gridDim.x;
                 p.dbg[((long long)work * n_mt + mt) * 128 + trow] = ((unsigned long long)mxu << 48) | S;
             }
             const uint32_t S32 = S > 2147483647ULL ? 2147483647u : (uint32_t)S;   // clamp_max_(2**31-1)
@@ -457,12 +467,12 @@ attention_pipe_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
             ptx::fence_proxy_async();                      // P written through the generic proxy -> visible to the MMA
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(p_ready);
-            if (t > 0) do_output(t - 1);
+            if (t > 0) do_output(mt_prev, ob_prev);
         }
         if (T > 0) {
             ptx::mbar_wait(o_full, (uint32_t)(T - 1) & 1u);
             ptx::tc_fence_after();
-            do_output(T - 1);
+            do_output(mt, ob_cur);
         }
     }
     ptx::tc_fence_before();
@@ -510,6 +520,8 @@ int launch_attention_pipe(ivit_ctx* ctx, const int8_t* qkv, const ivit_attn_para
     rc = ap_make_tmap(ctx, &tk, qkv, ap->n_seq, ap->n_tok, ld, 224);
     if (rc) return rc;
     const int items = ap->n_seq * ap->n_heads;
+    if ((long long)ap->n_seq * ap->n_tok * ap->n_heads * 64 >= (1LL << 32))
+        return fail(IVIT_ENOTSUP, "attention (tcgen05, pipelined): output of %d x %d tokens exceeds 4 GiB (32-bit offsets)", ap->n_seq, ap->n_tok);
     const int grid = items < ctx->num_sms ? items : ctx->num_sms;                // persistent: one CTA per SM
     // per-thread partial sums cover at most 56 exponentials: 32-bit while E(0) = |x0| << n < 2^26
     const bool wide = (((long long)(-ap->x0)) << ap->n) >= (1LL << 26);
