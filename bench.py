@@ -467,12 +467,12 @@ def run_ours(args, rank, world, local_rank):
         roof.update({"achieved": whole_tops, "frac": whole_tops / peak_sus, "traffic": None,
                      "kernel": "whole step (Swin: no single dominant kernel; see profiles/launches_swin_r2*.md)"})
     cpu = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:            # the CPU arm is timed at N = 1 only
         n_img = args.ref_images or 8
         v, kind, cores, sample, _ = cpu_reference_run(args.model, pack, n_img, 12.0)
         cpu = {"value": v, "unit": "images/s", "cores": cores, "kind": kind, "sample": sample}
     # rank 0 against the CPU oracle on the parity images (2 of the 4: the oracle port is slow)
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:
         import oracle.model as OM
         want = (OM.deit_forward if is_deit else OM.swin_forward)(pack, xs[:2].numpy())
         parity["oracle_ok"] = bool(np.array_equal(logits4[:2], want))

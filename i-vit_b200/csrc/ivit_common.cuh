@@ -76,7 +76,9 @@ IVIT_DEVINL UniRq make_unirq(ivit_dyadic_t d, int zbits) {
     u.m = d.m; u.e = d.e;
     u.half = (d.e >= 1 && d.e <= 62) ? (1LL << (d.e - 1)) : 0;
     const int tz = __ffs(d.m) - 1;
-    u.fast = (d.e >= 16 && d.e <= 62 && d.m != 0 && (d.e - 1 - tz > zbits)) ? 1 : 0;
+    // no reachable tie: either the tie bit lies above every operand bit (e-1-tz > zbits), or the product has no
+    // fractional bits at all (tz >= e: e.g. the identity ratio m = 2^30, e = 30 of two QuantActs with equal ranges)
+    u.fast = (d.e >= 16 && d.e <= 62 && d.m != 0 && ((d.e - 1 - tz > zbits) || tz >= d.e)) ? 1 : 0;
     return u;
 }
 // out-of-line general form: keeps the (rarely taken) slow path from being inlined at every call site

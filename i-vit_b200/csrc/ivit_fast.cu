@@ -579,11 +579,19 @@ int ivit_layernorm_i16_i8(ivit_ctx* ctx, const int16_t* x, int64_t rows, int C, 
     const int lpr = 16;
     const int rpb = 8 * (32 / lpr);                              // rows per 256-thread block and pass
     const int64_t want = (rows + rpb - 1) / rpb;
-    // persistent grid: two resident 256-thread blocks per SM (126 registers with the prefetched second register set)
-    const int grid = (int)(want < (int64_t)ctx->num_sms * 2 ? want : (int64_t)ctx->num_sms * 2);
+    // persistent grid: two resident 256-thread blocks per SM (126 registers with the prefetched second register set).
+    // IVIT_LN_VARIANT (experiments, tools/rowops_bench.py): 1 = three blocks per SM (<= 80 registers, no prefetch set),
+    // 2 = four blocks per SM (<= 64 registers, no prefetch set)
+    static const char* var_env = getenv("IVIT_LN_VARIANT");
+    const int variant = var_env ? atoi(var_env) : 0;
+    const int bps = variant == 1 ? 3 : (variant == 2 ? 4 : 2);
+    const int grid = (int)(want < (int64_t)ctx->num_sms * bps ? want : (int64_t)ctx->num_sms * bps);
     const int nv = (nvec + lpr - 1) / lpr;
     const bool full = (nv * lpr == nvec);
-#define LNK(NV, LPR, FULLV) layernorm_i16_i8_kernel<NV, LPR, FULLV, 2, true><<<grid, 256, 0, st(stream)>>>(x, rows, C, bias_int, me, out)
+#define LNK(NV, LPR, FULLV) do { \
+        if (variant == 1) layernorm_i16_i8_kernel<NV, LPR, FULLV, 3, false><<<grid, 256, 0, st(stream)>>>(x, rows, C, bias_int, me, out); \
+        else if (variant == 2) layernorm_i16_i8_kernel<NV, LPR, FULLV, 4, false><<<grid, 256, 0, st(stream)>>>(x, rows, C, bias_int, me, out); \
+        else layernorm_i16_i8_kernel<NV, LPR, FULLV, 2, true><<<grid, 256, 0, st(stream)>>>(x, rows, C, bias_int, me, out); } while (0)
 #define LNF(NV, LPR) do { if (full) LNK(NV, LPR, true); else LNK(NV, LPR, false); } while (0)
     switch (nv) { case 1: LNF(1, 16); break; case 2: LNF(2, 16); break; case 3: LNF(3, 16); break; case 4: LNF(4, 16); break;
                   case 5: LNF(5, 16); break; case 6: LNF(6, 16); break; case 7: LNF(7, 16); break; default: LNF(8, 16); break; }
