@@ -48,7 +48,7 @@ __device__ __forceinline__ uint32_t g_prmt(uint32_t a, uint32_t b, uint32_t sel)
     return d;
 }
 
-constexpr int LNG_MAXC = 1536;      // 4 * 384: the widest merge LayerNorm of the Swin zoo (Swin-B: 4 * 512 takes the general kernel)
+constexpr int LNG_MAXC = 2048;      // 4 * 512: the widest merge LayerNorm of the Swin zoo (Swin-B, stage 3 -> 4)
 
 // LPR lanes per row (32 / LPR rows per warp), NV 16-byte vectors (8 channels) per lane; C == 8 * NV * LPR when FULL.
 // G source rows per output row (1 or 4), each Cs = C / G channels wide.  Statistics and arithmetic: see
@@ -272,7 +272,7 @@ int ivit_layernorm_gather_i16_i8(ivit_ctx* ctx, const int16_t* x, int64_t rows_o
     int lpr = 4;
     while (lpr < 32 && (nvec + lpr - 1) / lpr > 6) lpr *= 2;
     const int nv = (nvec + lpr - 1) / lpr;
-    IVIT_REQUIRE(nv <= 6, "ivit_layernorm_gather_i16_i8: C too wide");
+    IVIT_REQUIRE(nv <= 8, "ivit_layernorm_gather_i16_i8: C too wide");
     const bool full = nv * lpr == nvec;
     const int rpb = 8 * (32 / lpr);
     const int64_t want = (rows_out + rpb - 1) / rpb;
@@ -282,7 +282,8 @@ int ivit_layernorm_gather_i16_i8(ivit_ctx* ctx, const int16_t* x, int64_t rows_o
 #define LG_F(NV, LPR) do { if (full) LG_G(NV, LPR, true); else LG_G(NV, LPR, false); } while (0)
 #define LG_L(NV) do { switch (lpr) { case 4: LG_F(NV, 4); break; case 8: LG_F(NV, 8); break; case 16: LG_F(NV, 16); break; default: LG_F(NV, 32); break; } } while (0)
     switch (nv) { case 1: LG_L(1); break; case 2: LG_L(2); break; case 3: LG_L(3); break; case 4: LG_L(4); break;
-                  case 5: LG_L(5); break; default: LG_L(6); break; }
+                  case 5: LG_L(5); break; case 6: LG_L(6); break;
+                  case 7: LG_F(7, 32); break; default: LG_F(8, 32); break; }      // C > 1536: one row per warp
 #undef LG_L
 #undef LG_F
 #undef LG_G

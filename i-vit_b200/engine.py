@@ -158,7 +158,7 @@ class Engine:
             tap(p + "qact4", x)
         # final norm on the cls rows only (LayerNorm is row-wise; vit_quant.py:271-273), then the head.  The x[:, 0] slice
         # is the row map of the gathering LayerNorm (one output row per image: token 0 of its N input rows)
-        if C % 8 == 0 and C <= 1536:
+        if C % 8 == 0 and C <= 2048:
             K.layernorm_gather(x, B, C, 1, self._cls_map, 1, N, t["norm.bias_integer"], t["qact2.me"], out=b["cls8"]); n += 1
         else:
             b["cls16"].copy_(x.view(B, N, C)[:, 0])

@@ -303,7 +303,7 @@ IVIT_API int ivit_window_attention_i8(ivit_ctx*, const int8_t* qkv, const ivit_w
  *           int16 row is also stored there (the residual stream in the new order);
  *   G == 4: the concatenation of input rows rowmap[4r .. 4r+3] (int32 [L_out * 4]), each C/4 wide -- PatchMerging's strided
  *           2x2 gather + cat (swin_quant.py:337-341) feeding norm (:344).
- * x: int16 [images * L_in, C / G]; out: int8 [rows_out, C]; C % (8 G) == 0, C <= 1536. */
+ * x: int16 [images * L_in, C / G]; out: int8 [rows_out, C]; C % (8 G) == 0, C <= 2048. */
 IVIT_API int ivit_layernorm_gather_i16_i8(ivit_ctx*, const int16_t* x, int64_t rows_out, int C, int G,
                                           const int32_t* rowmap, int L_out, int L_in, const int32_t* bias_int,
                                           const ivit_dyadic_t* me, int8_t* out, int16_t* xcopy, ivit_stream stream);

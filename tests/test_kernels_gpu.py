@@ -694,7 +694,7 @@ def test_window_attention_refuses_scales_outside_its_domain(K):
 
 @pytest.mark.parametrize("C,G,L_out,mag", [(96, 1, 56, 9000), (192, 1, 28, 20000), (384, 1, 49, 32767), (768, 1, 49, 5000),
                                            (384, 4, 16, 9000), (768, 4, 49, 30000), (1536, 4, 9, 32767), (48, 1, 5, 300),
-                                           (1024, 4, 4, 700)])
+                                           (1024, 4, 4, 700), (2048, 4, 7, 12000), (1792, 1, 3, 900)])
 def test_layernorm_gather(K, C, G, L_out, mag):
     """IntLayerNorm + QuantAct over rows gathered through a per-image map: window permutation (G = 1, with the permuted
     int16 copy) and 2 x 2 patch merging (G = 4)."""

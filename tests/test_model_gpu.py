@@ -178,3 +178,25 @@ def test_operator_level_calibration_pass_runs(tiny):
         y2 = m(synth_images(2, seed=5).cuda())
     assert torch.equal(y1, y2) and torch.isfinite(y1).all()
     assert float(torch.as_tensor(m.blocks[3].qact2.max_val)) > 0
+
+
+def test_vit_large_fused_engine_matches_reference_digests():
+    """ViT-large (C = 1024, 16 heads, 24 blocks) through the fused engine against the digests of the reference's own run
+    (tests/golden/vit_large_b1.npz) -- no oracle involved."""
+    from ivit_b200.calib import build_synthetic
+    from ivit_b200.engine import Engine
+    from ivit_b200.pack import export_deit
+    from ivit_b200.synth import synth_images
+    gold = np.load(os.path.join(GOLDEN, "vit_large_b1.npz"))
+    want = dict(zip(gold["names"].tolist(), gold["digests"].tolist()))
+    eng = Engine(export_deit(build_synthetic("vit_large_patch16_224")), "cuda")
+    x = synth_images(int(gold["batch"]), seed=int(gold["seed_images"])).cuda()
+    taps = eng.forward_taps(x)
+    checked = 0
+    for name, t in taps.items():
+        if name in want and name != "qact_input":
+            assert digest(t.cpu().numpy().astype(np.int64)) == want[name], "Engine (ViT-large) diverges from the reference at %s" % name
+            checked += 1
+    assert checked >= 24 * 8 + 2, checked
+    y = eng(x).cpu().numpy()
+    assert np.abs(y.astype(np.float64) - gold["logits"].astype(np.float64)).max() <= 2e-6 * np.abs(gold["logits"]).max()

@@ -83,3 +83,26 @@ def test_swin_fused_engine_matches_oracle_at_every_fused_boundary():
     err = np.abs(want.astype(np.float64)).max()
     assert err > 0
 
+
+
+def test_swin_base_fused_engine_matches_reference_digests():
+    """Swin-base (C = 128 ... 1024, heads 4 / 8 / 16 / 32, merge LayerNorms up to 4 * 512 = 2048 channels) through the fused
+    SwinEngine against the digests of the reference's own run (tests/golden/swin_base_b1.npz) -- no oracle involved."""
+    from ivit_b200.calib import build_synthetic
+    from ivit_b200.pack import export_swin
+    from ivit_b200.swin_engine import SwinEngine
+    from ivit_b200.synth import synth_images
+    gold = np.load(os.path.join(GOLDEN, "swin_base_b1.npz"))
+    want = dict(zip(gold["names"].tolist(), gold["digests"].tolist()))
+    eng = SwinEngine(export_swin(build_synthetic("swin_base_patch4_window7_224")), "cuda")
+    x = synth_images(int(gold["batch"]), seed=int(gold["seed_images"])).cuda()
+    taps = eng.forward_taps(x)
+    checked = 0
+    for name, t in taps.items():
+        if name in want:
+            assert digest(t.cpu().numpy().astype(np.int64)) == want[name], "SwinEngine (Swin-base) diverges from the reference at %s" % name
+            checked += 1
+    assert checked >= 24 * 9 + 3 * 2 + 4, checked
+    y = eng(x).cpu().numpy()
+    assert np.abs(y.astype(np.float64) - gold["logits"].astype(np.float64)).max() <= 2e-6 * np.abs(gold["logits"]).max()
+    assert eng.attention_fallbacks == 0
