@@ -133,7 +133,8 @@ def ncu_traffic(kernel_substr):
     """Average DRAM bytes per launch of a kernel from the newest committed ncu --set full summary
     (profiles/ncu_full_*.json, written by tools/summarize_ncu.py); None if there is none."""
     import glob
-    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "ncu_full_*.json")))
+    # the newest DeiT capture (ncu_full_r<round><tag>.json; the Swin captures are ncu_full_swin_*.json)
+    files = sorted(f for f in glob.glob(os.path.join(ROOT, "profiles", "ncu_full_r*.json")))
     if not files:
         return None, None
     d = json.load(open(files[-1]))

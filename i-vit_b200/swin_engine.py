@@ -151,6 +151,15 @@ class SwinEngine:
                                   me_s2=s[p + "attn.qact2.me"], me_b=s[p + "attn.qact2.me_res"], mask=self.mask_i32.get(p),
                                   n_win=(n_win_img if masked else 0))
 
+    @staticmethod
+    def _ln8(x, bias_int, me):
+        """norm + QuantAct, int16 -> int8.  Narrow rows (C <= 384) take the gather kernel with the identity map: it packs up
+        to eight rows into a warp (4 lanes per row at C = 96), where the DeiT-tuned kernel spends 16 lanes on a row."""
+        rows, C = x.shape
+        if C <= 384:
+            return K.layernorm_gather(x, rows, C, 1, None, 1, 1, bias_int, me)
+        return K.layernorm_i16_i8(x, bias_int, me)
+
     def _run(self, img: torch.Tensor, taps: dict = None):
         m, t, s = self.meta, self.t, self.s
         B = img.shape[0]
@@ -193,7 +202,7 @@ class SwinEngine:
                 rmap = self.rowmap[p]
                 if rmap is None:                                                        # stream already in this block's order
                     x1 = x
-                    ln8 = K.layernorm_i16_i8(x1, t[p + "norm1.bias_integer"], t[p + "qact1.me"]); n += 1   # :256-257
+                    ln8 = self._ln8(x1, t[p + "norm1.bias_integer"], t[p + "qact1.me"]); n += 1   # :256-257
                 else:                                                                   # :256-271 + :278-288 of the previous block
                     x1 = torch.empty_like(x)
                     ln8 = K.layernorm_gather(x, B * L, C, 1, rmap, L, L, t[p + "norm1.bias_integer"], t[p + "qact1.me"], xcopy=x1); n += 1
@@ -207,7 +216,7 @@ class SwinEngine:
                 x2 = lin(p + "attn.proj", ao8, p + "attn.qact4", 16, two_stage=True, me2=s[p + "qact2.me"],
                          residual=x1, res_me=s[p + "qact2.me_res"]); n += 1               # :166-167 + residual QuantAct :293
                 tap(p + "qact2", x2, (B, L, C), order)
-                ln8 = K.layernorm_i16_i8(x2, t[p + "norm2.bias_integer"], t[p + "qact3.me"]); n += 1   # :295-296
+                ln8 = self._ln8(x2, t[p + "norm2.bias_integer"], t[p + "qact3.me"]); n += 1   # :295-296
                 tap(p + "qact3", ln8, (B, L, C), order)
                 h8 = lin(p + "mlp.fc1", ln8, p + "mlp.qact_gelu", 8); n += 1             # layers_quant.py:145-146
                 tap(p + "mlp.qact_gelu", h8, (B, L, -1), order)

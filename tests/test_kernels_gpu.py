@@ -438,6 +438,25 @@ def test_attention(K, n_seq, n_tok, H, D, p_bits):
     assert_equal(got, want, "attention n_tok=%d H=%d D=%d P%d" % (n_tok, H, D, p_bits))
 
 
+@pytest.mark.parametrize("s_attn", [0.3, 0.11, 0.0122, 0.0039, 0.001, 0.00031, 2.1e-5])
+def test_attention_over_softmax_scales(K, s_attn):
+    """DeiT attention over Shiftmax input scales 0.3 ... 2e-5 (x0 = -4 ... -47619): the pipelined tcgen05 kernel covers all of
+    them (round 1's needed a scale above 1/256), with 64-bit row sums below ~5e-4.  Bit-exact against the oracle."""
+    n_seq, n_tok, H, D = 3, 197, 2, 64
+    rng = np.random.default_rng(int(s_attn * 1e7))
+    qkv = rng.integers(-128, 128, (n_seq * n_tok, 3 * H * D)).astype(np.int8)
+    qkv[::7, :H * D] = np.clip(qkv[::7, :H * D].astype(np.int32) * 3, -128, 127).astype(np.int8)
+    s_attn = np.float32(s_attn)
+    acc_scale = np.float32(127 * s_attn / (D * 127 * 40))
+    m_s, e_s = K.dyadic_host(np.array([acc_scale], np.float32), s_attn)
+    x0 = O.x0_of(s_attn)
+    m_o, e_o = K.dyadic_host(np.array([2.0 ** -15 * 0.02], np.float32), np.float32(0.02 * 1.3))
+    me_s, me_o = (int(m_s[0]), int(e_s[0])), (int(m_o[0]), int(e_o[0]))
+    want = oracle_attention(qkv, n_seq, n_tok, H, D, me_s, x0, me_o, 16)
+    got = K.attention_i8(dev(qkv), n_seq, n_tok, H, D, me_s, x0, me_o, p_bits=16)
+    assert_equal(got, want, "attention s=%g x0=%d" % (float(s_attn), x0))
+
+
 @pytest.mark.parametrize("n_win,H,with_mask", [(4, 3, True), (1, 6, False), (16, 2, True)])
 def test_attention_swin_bias_and_mask(K, n_win, H, with_mask):
     """Window attention of Swin in the fused kernel (swin_quant.py:135-164): scores -> qact_attn1 -> qact2 with the
