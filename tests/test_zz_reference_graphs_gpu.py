@@ -167,6 +167,18 @@ def test_reference_calibration_pass_on_the_mirror_tracks_the_golden_ranges(ref):
     print("calibration on the mirror: %d QuantActs executed, %d bit-identical to the reference's, worst relative "
           "deviation %.3g at %s" % (executed, exact, worst[0], worst[1]))
     assert executed > 100
+    # ... and BIT FOR BIT the ranges of the oracle's exact-integer calibration forward (oracle/calib.py), itself checked
+    # against the reference's table in tests/test_calib_oracle.py: the mirror's calibration pass is pinned, not just bounded
+    from test_calib_oracle import oracle_ranges
+    _, want = oracle_ranges(name)
+    diff = []
+    for n, mod in model.named_modules():
+        if type(mod) is ref.QuantAct and n in want:
+            mn = np.float32(float(torch.as_tensor(mod.min_val).float().reshape(-1)[0]))
+            mx = np.float32(float(torch.as_tensor(mod.max_val).float().reshape(-1)[0]))
+            if mn != np.float32(want[n][0]) or mx != np.float32(want[n][1]):
+                diff.append((n, float(mn), want[n][0], float(mx), want[n][1]))
+    assert not diff, "mirror calibration differs from the oracle's at %d QuantActs, first: %r" % (len(diff), diff[0])
     for n in ("qact_input", "patch_embed.qact", "qact_pos"):         # upstream of every integer operator: exact
         mod = dict(model.named_modules())[n]
         assert np.float32(float(torch.as_tensor(mod.max_val).float().reshape(-1)[0])) == np.float32(cal["ranges"][n][1]), n
