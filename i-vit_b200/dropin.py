@@ -52,15 +52,23 @@ def _tkinter_stub():
 _loaded = {}
 
 
-def load_reference_models(path: str = None, package: str = None, mirror: bool = True):
+def load_reference_models(path: str = None, package: str = None, mirror: bool = True, auto_accelerate: bool = False):
     """Import the reference ``models`` package from ``path`` (see ``find_reference_models``) as ``package`` and return
     the module: ``m.deit_tiny_patch16_224``, ``m.swin_tiny_patch4_window7_224``, ``m.freeze_model``, ...
 
     mirror=True   its ``quantization_utils`` is this package's sm_100a-backed mirror (the drop-in);
-    mirror=False  the reference's own quantization_utils (CPU baseline only)."""
+    mirror=False  the reference's own quantization_utils (CPU baseline only).
+    auto_accelerate=True  (mirror only) the package's ``freeze_model`` / ``unfreeze_model`` -- the names
+                  ``quant_train.py`` calls around its validation loop (:325-326, :273) -- additionally switch a whole
+                  VisionTransformer / SwinTransformer that lives on a CUDA device to the fused engine
+                  (``engine.accelerate``) and back: the reference's evaluation code then runs the fused path without
+                  a single edit.  Freezing a sub-module, or a model on the CPU, behaves exactly as in the reference."""
     models_dir = find_reference_models(path)
-    package = package or ("ivit_ref_models" if mirror else "ivit_ref_models_literal")
-    key = (os.path.realpath(models_dir), package, mirror)
+    if auto_accelerate and not mirror:
+        raise ValueError("auto_accelerate needs the mirror")
+    if package is None:
+        package = ("ivit_ref_models" if mirror else "ivit_ref_models_literal") + ("_auto" if auto_accelerate else "")
+    key = (os.path.realpath(models_dir), package, mirror, auto_accelerate)
     if key in _loaded:
         return _loaded[key]
     if package in sys.modules:
@@ -84,8 +92,41 @@ def load_reference_models(path: str = None, package: str = None, mirror: bool = 
     if mirror:
         mod.quantization_utils = qu
         assert mod.QuantAct is qu.QuantAct and sys.modules[package + ".vit_quant"].QuantLinear is qu.QuantLinear
+        if auto_accelerate:
+            _install_auto_accelerate(mod, package)
     _loaded[key] = mod
     return mod
+
+
+def _install_auto_accelerate(mod, package):
+    """Wrap the reference's freeze_model / unfreeze_model (model_utils.py:5-40) in the loaded package's namespace."""
+    from .engine import accelerate
+    mu = sys.modules[package + ".model_utils"]
+    ref_freeze, ref_unfreeze = mu.freeze_model, mu.unfreeze_model
+    roots = (sys.modules[package + ".vit_quant"].VisionTransformer, sys.modules[package + ".swin_quant"].SwinTransformer)
+
+    def _restore(model):
+        if hasattr(model, "_ivit_forward_operator_level"):
+            model.forward = model._ivit_forward_operator_level
+            del model._ivit_forward_operator_level
+            model._ivit_engine = None
+
+    def freeze_model(model):
+        ref_freeze(model)
+        if isinstance(model, roots):
+            _restore(model)                                   # weights / ranges may have changed since the last freeze
+            p = next(model.parameters(), None)
+            if p is not None and p.is_cuda:
+                accelerate(model, p.device)
+
+    def unfreeze_model(model):
+        if isinstance(model, roots):
+            _restore(model)
+        ref_unfreeze(model)
+
+    freeze_model.__doc__, unfreeze_model.__doc__ = ref_freeze.__doc__, ref_unfreeze.__doc__
+    for ns in (mod, mu):
+        ns.freeze_model, ns.unfreeze_model = freeze_model, unfreeze_model
 
 
 @contextlib.contextmanager

@@ -210,3 +210,36 @@ def test_engine_from_the_checkpoint_of_a_gpu_run(ref):
         assert np.array_equal(pack.arrays[k], live.arrays[k]), k
     got = Engine(pack, "cuda")(x.cuda()).cpu().numpy()
     assert np.array_equal(got, OM.deit_forward(pack, x.numpy()))
+
+
+def test_auto_accelerate_makes_the_reference_validation_loop_run_fused():
+    """dropin.load_reference_models(auto_accelerate=True): the package's freeze_model / unfreeze_model (what quant_train.py
+    calls around its validation loop, :325-326 / :273) switch a whole model to the fused engine and back -- the
+    reference's evaluation code runs the fused path without an edit.  Logits == CPU oracle; unfreezing restores the
+    operator-by-operator forward."""
+    import oracle.model as OM
+    from ivit_b200.calib import apply_calibration, load_calibration
+    from ivit_b200.dropin import load_reference_models
+    from ivit_b200.pack import export_swin
+    from ivit_b200.synth import synth_images, synth_parameters
+    refa = load_reference_models(auto_accelerate=True)
+    name = "swin_tiny_patch4_window7_224"
+    cal = load_calibration(name)
+    model = getattr(refa, name)(pretrained=False).eval()
+    synth_parameters(model, cal["seed"])
+    apply_calibration(model, cal["ranges"])
+    model = model.cuda()
+    x = synth_images(2, seed=29)
+    refa.freeze_model(model.patch_embed)                   # a sub-module: plain reference behaviour
+    assert getattr(model, "_ivit_engine", None) is None
+    refa.freeze_model(model)                               # quant_train.py:325-326
+    assert model._ivit_engine is not None and model._ivit_engine.meta["arch"] == "swin"
+    with torch.no_grad():
+        fast = model(x.cuda()).cpu().numpy()               # quant_train.py:334
+    want = OM.swin_forward(export_swin(model), x.numpy())
+    assert np.array_equal(fast, want)
+    refa.unfreeze_model(model)                             # quant_train.py:273: back to the operator classes, ranges live again
+    assert model._ivit_engine is None and all(m.running_stat for m in model.modules() if type(m) is refa.QuantAct)
+    refa.freeze_model(model)
+    with torch.no_grad():
+        assert np.array_equal(model(x.cuda()).cpu().numpy(), want)
