@@ -77,6 +77,7 @@ SIGNATURES = {
     "ivit_window_attention_i8": [_vp, _vp, C.POINTER(WinAttnParams), _vp, _vp],
     "ivit_layernorm_gather_i16_i8": [_vp, _vp, _i64, _int, _int, _vp, _int, _int, _vp, _vp, _vp, _vp, _vp],
     "ivit_avgpool_requant_i8": [_vp, _vp, _int, _int, _int, Dyadic, _vp, _vp],
+    "ivit_widen_i8_i16": [_vp, _vp, _i64, _vp, _vp],
     "ivit_layernorm_i8_i16x2": [_vp, _vp, _i64, _int, _vp, _vp, Dyadic, _vp, _vp],
 }
 EXPORTS = ["ivit_version", "ivit_last_error", "ivit_create", "ivit_destroy", "ivit_num_sms"] + sorted(SIGNATURES)

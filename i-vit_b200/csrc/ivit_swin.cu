@@ -252,11 +252,37 @@ __global__ void avgpool_requant_kernel(const int8_t* __restrict__ x, int B, int 
     reinterpret_cast<uint32_t*>(out + (int64_t)b * C)[c4] = o;
 }
 
+// int8 -> int16, 16 values per thread: the 8-bit output of PatchMerging's qact2 (swin_quant.py:347) enters the int16 residual stream
+__global__ void widen_i8_i16_kernel(const uint4* __restrict__ x, int64_t n16, uint4* __restrict__ out) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (int64_t)gridDim.x * blockDim.x) {
+        const uint4 v = __ldg(x + i);
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+        uint32_t o[8];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            o[2 * k] = g_prmt(w[k], 0u, 0x9180u);
+            o[2 * k + 1] = g_prmt(w[k], 0u, 0xB3A2u);
+        }
+        out[2 * i] = make_uint4(o[0], o[1], o[2], o[3]);
+        out[2 * i + 1] = make_uint4(o[4], o[5], o[6], o[7]);
+    }
+}
+
 }  // namespace ivit
 
 using namespace ivit;
 
 extern "C" {
+
+int ivit_widen_i8_i16(ivit_ctx* ctx, const int8_t* x, int64_t n, int16_t* out, ivit_stream stream) {
+    IVIT_REQUIRE(ctx && x && out && n > 0 && n % 16 == 0, "ivit_widen_i8_i16: n must be a positive multiple of 16");
+    IVIT_REQUIRE(((uintptr_t)x % 16) == 0 && ((uintptr_t)out % 16) == 0, "ivit_widen_i8_i16: 16-byte alignment");
+    const int64_t n16 = n / 16, blocks = (n16 + 255) / 256;
+    const int grid = (int)(blocks < (int64_t)ctx->num_sms * 16 ? blocks : (int64_t)ctx->num_sms * 16);
+    widen_i8_i16_kernel<<<grid, 256, 0, st(stream)>>>(reinterpret_cast<const uint4*>(x), n16, reinterpret_cast<uint4*>(out));
+    IVIT_LAUNCH_OK("widen_i8_i16_kernel");
+    return IVIT_OK;
+}
 
 int ivit_layernorm_gather_i16_i8(ivit_ctx* ctx, const int16_t* x, int64_t rows_out, int C, int G, const int32_t* rowmap,
                                  int L_out, int L_in, const int32_t* bias_int, const ivit_dyadic_t* me, int8_t* out,

@@ -386,3 +386,12 @@ def layernorm_i8_i16x2(x: torch.Tensor, bias_int: torch.Tensor, me: torch.Tensor
     call("ivit_layernorm_i8_i16x2", context(x.device), ptr(x), x.shape[0], x.shape[1], ptr(bias_int), ptr(me),
          Dyadic(int(me2[0]), int(me2[1])), ptr(out))
     return out
+
+
+def widen_i8_i16(x: torch.Tensor, out=None):
+    """int8 -> int16 storage, values unchanged (PatchMerging output entering the int16 residual stream)."""
+    assert x.dtype == torch.int8 and x.is_contiguous() and x.numel() % 16 == 0
+    if out is None:
+        out = torch.empty(x.shape, dtype=torch.int16, device=x.device)
+    call("ivit_widen_i8_i16", context(x.device), ptr(x), x.numel(), ptr(out))
+    return out

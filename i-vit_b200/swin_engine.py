@@ -82,8 +82,6 @@ class SwinEngine:
                 name = k[:-len(".weight_integer")]
                 bound = int(v.shape[1]) * 128 * 128 + int(np.abs(pack.arrays[name + ".bias_integer"].astype(np.int64)).max()) + 1
                 self.acc_bits[name] = min(31, int(bound).bit_length())
-        # identity dyadic (m / 2^e = 1): widens the 8-bit output of a patch merging to the int16 residual stream
-        self._ident = K.dyadic_table([1 << 30], [30], self.device)
         # static per-block tables: ShiftGELU table, requantised relative-position bias, mask bits, row permutations
         self.gelu_lut, self.bias_rq, self.mask_bits, self.mask_add, self.mask_i32 = {}, {}, {}, {}, {}
         self.rowmap, self.order, self.merge_map = {}, {}, {}
@@ -235,7 +233,7 @@ class SwinEngine:
                 C *= 2
                 x8 = lin(d + "reduction", ln8, d + "qact2", 8); n += 1                   # :346-347
                 tap(d + "qact2", x8, (B, L, C), self.order[d])
-                x = K.requant(x8, self._ident, 16); n += 1                               # the residual stream is carried as int16
+                x = K.widen_i8_i16(x8); n += 1                                           # the residual stream is carried as int16
 
         L = R * R
         ln8 = K.layernorm_i16_i8(x, t["norm.bias_integer"], t["qact2.me"]); n += 1        # :552-553

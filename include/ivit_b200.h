@@ -314,6 +314,10 @@ IVIT_API int ivit_layernorm_gather_i16_i8(ivit_ctx*, const int16_t* x, int64_t r
 IVIT_API int ivit_layernorm_i8_i16x2(ivit_ctx*, const int8_t* x, int64_t rows, int C, const int32_t* bias_int,
                                      const ivit_dyadic_t* me, ivit_dyadic_t me2, int16_t* out, ivit_stream stream);
 
+/* int8 -> int16 storage (values unchanged): the 8-bit output of PatchMerging's qact2 (swin_quant.py:347) entering the int16
+ * residual stream of the next stage.  n % 16 == 0. */
+IVIT_API int ivit_widen_i8_i16(ivit_ctx*, const int8_t* x, int64_t n, int16_t* out, ivit_stream stream);
+
 /* Token average + QuantAct (swin_quant.py:554-555): out[b, c] = clamp8(RNE(RNE(sum_t x[b, t, c] / L) * m / 2^e)).
  * x: int8 [B, L, C], out: int8 [B, C]; C % 4 == 0. */
 IVIT_API int ivit_avgpool_requant_i8(ivit_ctx*, const int8_t* x, int B, int L, int C, ivit_dyadic_t me, int8_t* out,

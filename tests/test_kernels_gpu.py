@@ -773,3 +773,9 @@ def test_layernorm_i8_i16x2(K, C, rows):
     got = K.layernorm_i8_i16x2(dev(q.astype(np.int8)), dev(bq.astype(np.int32)), me_dev(K, m, e), (int(m2[0]), int(e2[0])))
     assert np.abs(want).max() > 1000
     assert_equal(got, want, "layernorm_i8_i16x2 C=%d" % C)
+
+
+def test_widen_i8_i16(K):
+    rng = np.random.default_rng(3)
+    x = rng.integers(-128, 128, (37, 48)).astype(np.int8)
+    assert_equal(K.widen_i8_i16(dev(x)), x.astype(np.int64), "widen")
