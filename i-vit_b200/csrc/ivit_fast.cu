@@ -584,6 +584,17 @@ int ivit_layernorm_i16_i8(ivit_ctx* ctx, const int16_t* x, int64_t rows, int C, 
     // 2 = four blocks per SM (<= 64 registers, no prefetch set)
     static const char* var_env = getenv("IVIT_LN_VARIANT");
     const int variant = var_env ? atoi(var_env) : 0;
+    // 3 / 4 (C == 768 only): eight lanes per row (four rows per warp: the per-row scalar work -- reductions, mean, integer
+    // square root, reciprocal -- is amortised over twice as many rows), 12 vectors per lane, without / with the prefetch set
+    if ((variant == 3 || variant == 4) && C == 768) {
+        const int rpb8 = 8 * 4;
+        const int64_t want8 = (rows + rpb8 - 1) / rpb8;
+        const int grid8 = (int)(want8 < (int64_t)ctx->num_sms * 2 ? want8 : (int64_t)ctx->num_sms * 2);
+        if (variant == 3) layernorm_i16_i8_kernel<12, 8, true, 2, false><<<grid8, 256, 0, st(stream)>>>(x, rows, C, bias_int, me, out);
+        else layernorm_i16_i8_kernel<12, 8, true, 1, true><<<grid8 / 2 > 0 ? grid8 / 2 : 1, 256, 0, st(stream)>>>(x, rows, C, bias_int, me, out);
+        IVIT_LAUNCH_OK("layernorm_i16_i8_kernel");
+        return IVIT_OK;
+    }
     const int bps = variant == 1 ? 3 : (variant == 2 ? 4 : 2);
     const int grid = (int)(want < (int64_t)ctx->num_sms * bps ? want : (int64_t)ctx->num_sms * bps);
     const int nv = (nvec + lpr - 1) / lpr;
