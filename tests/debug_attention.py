@@ -1,4 +1,6 @@
-"""Localise mismatches of the fused attention kernel against the oracle (which rows / heads / channel quarters)."""
+"""Debug helper (not collected by pytest): localise mismatches of the fused attention kernel against the oracle (which
+rows / heads / channel quarters), and dump per-row (max, sum) through IVIT_ATTN_DBG_PTR.  Lives under tests/ because it
+uses the oracle:  python tests/debug_attention.py"""
 import os
 import sys
 
