@@ -1,6 +1,7 @@
 // Context, error reporting and driver entry points of libivit_b200.so.
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "ivit_internal.h"
 
@@ -14,6 +15,11 @@ int fail(int code, const char* fmt, ...) {
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
     return code;
+}
+
+bool pdl_enabled() {
+    static const int on = [] { const char* e = getenv("IVIT_PDL"); return (e && e[0] == '1') ? 1 : 0; }();
+    return on != 0;
 }
 
 int fail_cuda(cudaError_t e, const char* what) {

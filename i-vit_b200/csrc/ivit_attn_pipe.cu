@@ -113,6 +113,7 @@ attention_pipe_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
         ptx::tmem_alloc(ptx::smem_u32(const_cast<uint32_t*>(tmem_ptr_smem)), 512);
         ptx::tmem_relinquish();
     }
+    ptx::grid_dep_wait();                                  // qkv is the predecessor's output (programmatic dependent launch)
     // exponent table: sE[k][copy] = int_exp_shift(-k), k = max - q in [0, 255]; copy = lane -> every lane reads its own bank
     if (tid < 512) {
         const int k = tid & 255;
@@ -533,8 +534,8 @@ int launch_attention_pipe(ivit_ctx* ctx, const int8_t* qkv, const ivit_attn_para
             IVIT_CUDA_OK(cudaFuncSetAttribute(attention_pipe_kernel<N, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AP_SMEM));  \
             attr_set[ctx->device] = 1;                                                                                 \
         }                                                                                                              \
-        if (wide) attention_pipe_kernel<N, true><<<grid, AP_THREADS, AP_SMEM, s>>>(tq, tk, a, out);                    \
-        else attention_pipe_kernel<N, false><<<grid, AP_THREADS, AP_SMEM, s>>>(tq, tk, a, out);                        \
+        if (wide) IVIT_CUDA_OK(launch_k(attention_pipe_kernel<N, true>, dim3(grid), dim3(AP_THREADS), AP_SMEM, s, tq, tk, a, out)); \
+        else IVIT_CUDA_OK(launch_k(attention_pipe_kernel<N, false>, dim3(grid), dim3(AP_THREADS), AP_SMEM, s, tq, tk, a, out));     \
     } break;
     switch ((ap->n_tok + 15) >> 4) {
         AP_CASE(4) AP_CASE(5) AP_CASE(6) AP_CASE(7) AP_CASE(8) AP_CASE(9) AP_CASE(10) AP_CASE(11) AP_CASE(12) AP_CASE(13) AP_CASE(14)

@@ -17,6 +17,7 @@
 
 #include "ivit_common.cuh"
 #include "ivit_internal.h"
+#include "ivit_ptx.cuh"
 
 namespace ivit {
 
@@ -54,6 +55,7 @@ __global__ void __launch_bounds__(256)
 gelu_lut_apply_kernel(const int8_t* __restrict__ q, int64_t rows, int cols, const int8_t* __restrict__ lut,
                       int8_t* __restrict__ out) {
     __shared__ __align__(256) uint8_t s_lut[8][256];
+    ptx::grid_dep_wait();
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int nvec = cols >> 4;
     const int64_t warp0 = (int64_t)blockIdx.x * 8 + w;
@@ -180,6 +182,7 @@ __global__ void __launch_bounds__(256, MINB)
 layernorm_i16_i8_kernel(const int16_t* __restrict__ x, int64_t rows, int C, const int32_t* __restrict__ bias_int,
                         const ivit_dyadic_t* __restrict__ me, int8_t* __restrict__ out) {
     constexpr int RPW = 32 / LPR;                                // rows per warp
+    ptx::grid_dep_wait();
     const int lane = threadIdx.x & 31;
     const int sub = lane % LPR, rsel = lane / LPR;
     const int nvec = C >> 3;                                     // vectors of 8 int16
@@ -433,6 +436,7 @@ __device__ __forceinline__ int32_t emb_rq(const EmbRq& u, int32_t z) {
 __global__ void embed_tokens_fast_kernel(const int16_t* __restrict__ pe, const int32_t* __restrict__ cls,
                                          const int16_t* __restrict__ pos, int B, int n_tok, int C, EmbRq rq, EmbRq rqp,
                                          ivit_dyadic_t me, int16_t* __restrict__ out) {
+    ptx::grid_dep_wait();
     const int C8 = C >> 3;
     const int64_t n8 = (int64_t)B * n_tok * C8;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (int64_t)gridDim.x * blockDim.x) {
@@ -511,7 +515,7 @@ int ivit_shiftgelu_lut(ivit_ctx* ctx, const int8_t* q, int64_t rows, int cols, c
         int& bps = bps_dev[ctx->device];                                                                                 \
         if (!bps) IVIT_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, gelu_lut_apply_kernel<MAXV>, 256, 0)); \
         const int64_t want = (rows + 7) / 8, cap = (int64_t)ctx->num_sms * (bps > 0 ? bps : 1);                          \
-        gelu_lut_apply_kernel<MAXV><<<(int)(want < cap ? want : cap), 256, 0, st(stream)>>>(q, rows, cols, lut, out);     \
+        IVIT_CUDA_OK(launch_k(gelu_lut_apply_kernel<MAXV>, dim3((unsigned)(want < cap ? want : cap)), dim3(256), 0, st(stream), q, rows, cols, lut, out)); \
     } while (0)
     if (nv <= 2) GL(2); else if (nv <= 4) GL(4); else if (nv <= 6) GL(6); else GL(8);
 #undef GL
@@ -564,7 +568,7 @@ int ivit_embed_tokens_fast(ivit_ctx* ctx, const int16_t* pe, const int32_t* cls,
     const int64_t n8 = (int64_t)B * n_tok * (C / 8);
     const int64_t blocks = (n8 + 255) / 256;
     const int grid = (int)(blocks < (int64_t)ctx->num_sms * 16 ? blocks : (int64_t)ctx->num_sms * 16);
-    embed_tokens_fast_kernel<<<grid, 256, 0, st(stream)>>>(pe, cls, pos, B, n_tok, C, rq, rqp, me, out);
+    IVIT_CUDA_OK(launch_k(embed_tokens_fast_kernel, dim3(grid), dim3(256), 0, st(stream), pe, cls, pos, B, n_tok, C, rq, rqp, me, out));
     IVIT_LAUNCH_OK("embed_tokens_fast_kernel");
     return IVIT_OK;
 }
@@ -602,7 +606,7 @@ int ivit_layernorm_i16_i8(ivit_ctx* ctx, const int16_t* x, int64_t rows, int C, 
 #define LNK(NV, LPR, FULLV) do { \
         if (variant == 1) layernorm_i16_i8_kernel<NV, LPR, FULLV, 3, false><<<grid, 256, 0, st(stream)>>>(x, rows, C, bias_int, me, out); \
         else if (variant == 2) layernorm_i16_i8_kernel<NV, LPR, FULLV, 4, false><<<grid, 256, 0, st(stream)>>>(x, rows, C, bias_int, me, out); \
-        else layernorm_i16_i8_kernel<NV, LPR, FULLV, 2, true><<<grid, 256, 0, st(stream)>>>(x, rows, C, bias_int, me, out); } while (0)
+        else IVIT_CUDA_OK(launch_k(layernorm_i16_i8_kernel<NV, LPR, FULLV, 2, true>, dim3(grid), dim3(256), 0, st(stream), x, rows, C, bias_int, me, out)); } while (0)
 #define LNF(NV, LPR) do { if (full) LNK(NV, LPR, true); else LNK(NV, LPR, false); } while (0)
     switch (nv) { case 1: LNF(1, 16); break; case 2: LNF(2, 16); break; case 3: LNF(3, 16); break; case 4: LNF(4, 16); break;
                   case 5: LNF(5, 16); break; case 6: LNF(6, 16); break; case 7: LNF(7, 16); break; default: LNF(8, 16); break; }

@@ -416,6 +416,7 @@ gemm_i8_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
     volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + STAGES * S::STAGE_BYTES + S::OUT_BYTES + S::RES_BYTES + S::PARAM_BYTES + 8 * (2 * STAGES + 8));
     int* fast_flag = reinterpret_cast<int*>(const_cast<uint32_t*>(tmem_ptr_smem) + 2);   // [2] one per accumulator stage
 
+    ptx::grid_dep_wait();                             // A / residual are the predecessor's outputs (programmatic dependent launch)
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
 
@@ -887,16 +888,28 @@ static int launch_gemm(ivit_ctx* ctx, const CUtensorMap& ta, const CUtensorMap& 
     cfg.blockDim = dim3(gemm_threads(MODE));
     cfg.dynamicSmemBytes = S::TOTAL;
     cfg.stream = s;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = CS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cudaLaunchAttribute attr[2];
+    int na = 0;
+    if (CS > 1) {
+        attr[na].id = cudaLaunchAttributeClusterDimension;
+        attr[na].val.clusterDim.x = CS; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1;
+        ++na;
+    }
+    const int na_cluster = na;
+    if (pdl_enabled()) {
+        attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[na].val.programmaticStreamSerializationAllowed = 1;
+        ++na;
+    }
     cfg.attrs = attr;
-    cfg.numAttrs = (CS > 1) ? 1 : 0;
+    cfg.numAttrs = na;
     if (!attr_set) {
         IVIT_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
         if (CS > 1) {
             cfg.gridDim = dim3(CS * ctx->num_sms);
+            cfg.numAttrs = na_cluster;                           // the occupancy query takes the cluster attribute only
             IVIT_CUDA_OK(cudaOccupancyMaxActiveClusters(&max_clusters, kern, &cfg));
+            cfg.numAttrs = na;
             if (max_clusters < 1) return fail(IVIT_ECUDA, "gemm: no co-resident cluster of %d CTAs fits", CS);
         }
         attr_set = 1;

@@ -24,6 +24,23 @@ struct PerDevice {
     int v[kMaxDevices] = {};
     int& operator[](int dev) { return v[(unsigned)dev % kMaxDevices]; }
 };
+// Launch with (IVIT_PDL=1) or without the programmatic-stream-serialization attribute: the grid may be scheduled while
+// its predecessor in the stream drains; every kernel launched this way starts with ptx::grid_dep_wait().
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
 int fail(int code, const char* fmt, ...);
 int fail_cuda(cudaError_t e, const char* what);
 inline cudaStream_t st(ivit_stream s) { return reinterpret_cast<cudaStream_t>(s); }

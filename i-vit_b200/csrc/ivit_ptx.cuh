@@ -13,6 +13,11 @@ namespace ptx {
 
 IVIT_PTX uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// ---- programmatic dependent launch -----------------------------------------------------
+// Wait until every grid this one depends on has completed and its memory is visible.  A no-op when the kernel was
+// launched without the programmatic-serialization attribute (ivit::launch_k, IVIT_PDL=1).
+IVIT_PTX void grid_dep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ---- mbarrier ----------------------------------------------------------------------
 IVIT_PTX void mbar_init(uint32_t bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");

@@ -19,6 +19,7 @@
 
 #include "ivit_common.cuh"
 #include "ivit_internal.h"
+#include "ivit_ptx.cuh"
 
 namespace ivit {
 
@@ -60,6 +61,7 @@ layernorm_gather_kernel(const int16_t* __restrict__ x, int64_t rows, int C, cons
                         int8_t* __restrict__ out, int16_t* __restrict__ xcopy, ivit_dyadic_t me2 = ivit_dyadic_t{0, 0}) {
     // IO16 (G == 1, no map): x is INT8 [rows, C]; out is INT16 [rows, C] = clamp16(RNE(clamp16(RNE(y*m/2^e)) * m2 / 2^e2))
     constexpr int RPW = 32 / LPR;
+    ptx::grid_dep_wait();
     const int lane = threadIdx.x & 31;
     const int sub = lane % LPR, rsel = lane / LPR;
     const int nvec = C >> 3;
@@ -303,7 +305,7 @@ int ivit_layernorm_gather_i16_i8(ivit_ctx* ctx, const int16_t* x, int64_t rows_o
     const int rpb = 8 * (32 / lpr);
     const int64_t want = (rows_out + rpb - 1) / rpb;
     const int grid = (int)(want < (int64_t)ctx->num_sms * 2 ? want : (int64_t)ctx->num_sms * 2);
-#define LG_K(NV, LPR, FULLV, GV) layernorm_gather_kernel<NV, LPR, FULLV, GV><<<grid, 256, 0, st(stream)>>>(x, rows_out, C, rowmap, L_out, L_in, bias_int, me, out, xcopy)
+#define LG_K(NV, LPR, FULLV, GV) IVIT_CUDA_OK(launch_k(layernorm_gather_kernel<NV, LPR, FULLV, GV, false>, dim3(grid), dim3(256), 0, st(stream), x, rows_out, C, rowmap, L_out, L_in, bias_int, me, out, xcopy, ivit_dyadic_t{0, 0}))
 #define LG_G(NV, LPR, FULLV) do { if (G == 1) LG_K(NV, LPR, FULLV, 1); else LG_K(NV, LPR, FULLV, 4); } while (0)
 #define LG_F(NV, LPR) do { if (full) LG_G(NV, LPR, true); else LG_G(NV, LPR, false); } while (0)
 #define LG_L(NV) do { switch (lpr) { case 4: LG_F(NV, 4); break; case 8: LG_F(NV, 8); break; case 16: LG_F(NV, 16); break; default: LG_F(NV, 32); break; } } while (0)
