@@ -178,7 +178,7 @@ class Engine:
         torch.cuda.current_stream(self.device).wait_stream(side)
         torch.cuda.synchronize(self.device)
         g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
+        with torch.cuda.graph(g, stream=side):      # explicit stream: torch's default capture stream is global and may live on another device
             self._run(b, B, img=img)
         return g
 
@@ -194,6 +194,14 @@ class Engine:
 
     @torch.no_grad()
     def forward(self, images: torch.Tensor) -> torch.Tensor:
+        """See ``_forward``.  Runs with the engine's device current (torch captures CUDA graphs on the CURRENT device: an
+        engine on cuda:1 driven from a process whose current device is cuda:0 would otherwise capture nothing)."""
+        if torch.cuda.current_device() == (self.device.index if self.device.index is not None else torch.cuda.current_device()):
+            return self._forward(images)
+        with torch.cuda.device(self.device):
+            return self._forward(images)
+
+    def _forward(self, images: torch.Tensor) -> torch.Tensor:
         """images: fp32 [B, 3, H, W] (already normalised, as the reference's models take them) or uint8 [B, 3, H, W]
         (decoded pixels: ToTensor + Normalize of the reference's eval transform are applied on the device, bit-identical
         to torchvision's fp32 arithmetic) on this engine's device -> fp32 logits [B, classes]

@@ -249,6 +249,13 @@ class SwinEngine:
     # ------------------------------------------------------------------ public API
     @torch.no_grad()
     def forward(self, images: torch.Tensor) -> torch.Tensor:
+        """See ``_forward``; runs with the engine's device current (torch captures CUDA graphs on the current device)."""
+        if torch.cuda.current_device() == (self.device.index if self.device.index is not None else torch.cuda.current_device()):
+            return self._forward(images)
+        with torch.cuda.device(self.device):
+            return self._forward(images)
+
+    def _forward(self, images: torch.Tensor) -> torch.Tensor:
         """images: fp32 [B, 3, H, W] on this engine's device -> fp32 logits [B, classes] (a view of an internal buffer,
         valid until the next call with the same batch size)."""
         if images.device != self.device and not (images.is_cuda and self.device.index is None):
@@ -268,7 +275,7 @@ class SwinEngine:
             torch.cuda.current_stream(self.device).wait_stream(side)
             torch.cuda.synchronize(self.device)
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
+            with torch.cuda.graph(g, stream=side):      # explicit stream: torch's default capture stream is global and may live on another device
                 out = self._run(static_in)
             plan = self._plans[B] = {"in": static_in, "graph": g, "out": out}
         plan["in"].copy_(images, non_blocking=True)

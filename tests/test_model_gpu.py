@@ -200,3 +200,19 @@ def test_vit_large_fused_engine_matches_reference_digests():
     assert checked >= 24 * 8 + 2, checked
     y = eng(x).cpu().numpy()
     assert np.abs(y.astype(np.float64) - gold["logits"].astype(np.float64)).max() <= 2e-6 * np.abs(gold["logits"]).max()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs in one process")
+def test_two_devices_in_one_process(tiny):
+    """one process driving two GPUs -- launches go to the context's device and stream whatever torch's current
+    device is, ivit_create leaves the current device alone, and the per-kernel attributes are set per device."""
+    from ivit_b200.engine import Engine
+    assert torch.cuda.current_device() == 0
+    eng1 = Engine(tiny["pack"], "cuda:1")
+    assert torch.cuda.current_device() == 0                 # ivit_create restored it
+    x = tiny["x"]
+    y1 = eng1(x.to("cuda:1")).cpu().numpy()                  # current device is still 0
+    y0 = tiny["eng"](x.to("cuda:0")).cpu().numpy()
+    assert np.array_equal(y1, tiny["logits"]) and np.array_equal(y0, tiny["logits"])
+    with torch.cuda.device(1):
+        assert np.array_equal(tiny["eng"](x.to("cuda:0")).cpu().numpy(), tiny["logits"])   # engine on 0 while 1 is current
