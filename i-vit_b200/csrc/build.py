@@ -29,7 +29,7 @@ def build(force: bool = False, verbose: bool = False, diag: bool = False) -> str
     """diag: compile the GEMM's IVIT_GEMM_DEBUG diagnostics in (tools/gemm_bench.py experiments; slower production path)."""
     if not (force or stale()):
         return OUT
-    flags = FLAGS + (["-DIVIT_GEMM_DIAG"] if diag else [])
+    flags = FLAGS + (["-DIVIT_GEMM_DIAG"] if diag else []) + os.environ.get("IVIT_NVCC_EXTRA", "").split()   # e.g. -DIVIT_ATTN_TRACE
     objs = []
     procs = []
     for s in SRCS:

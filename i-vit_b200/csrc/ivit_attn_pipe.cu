@@ -31,6 +31,19 @@
 
 namespace ivit {
 
+// -DIVIT_ATTN_TRACE (tools/attn_trace.py): CTA 0 stamps clock64() at the phase boundaries of its first 64 tiles into the
+// IVIT_ATTN_DBG_PTR buffer, [warp 17][tile 64][event 8]; the row statistics normally written there are off in that build
+#ifdef IVIT_ATTN_TRACE
+#define AP_TR(ev)                                                                                                      \
+    do {                                                                                                               \
+        if (blockIdx.x == 0 && lane == 0 && p.dbg != nullptr && t < 64) p.dbg[(warp * 64 + t) * 8 + (ev)] = (unsigned long long)clock64(); \
+    } while (0)
+#define AP_ROWSTATS 0
+#else
+#define AP_TR(ev) do {} while (0)
+#define AP_ROWSTATS 1
+#endif
+
 struct AttnPipeArgs {
     int n_seq, n_tok, H;
     int32_t m_s, sh_s, m_o, sh_o;  // FAST requants: hi32(z*m + half) >> sh
@@ -54,6 +67,7 @@ constexpr int AP_BAR = AP_RED + 4 * 128 * 4 + 4 * 128 * 8;
 constexpr int AP_SMEM = AP_BAR + 128 + 1024;      // barriers + tmem pointer, + alignment slack
 static_assert(AP_SP % 1024 == 0 && AP_SV % 1024 == 0 && AP_KV_BYTES % 1024 == 0, "swizzle atoms need 1024-byte alignment");
 static_assert(AP_SMEM <= 227 * 1024, "shared memory budget");
+constexpr uint32_t AP_MAGIC = 0x4B000000u;        // bits of the float 2^23
 constexpr int AP_TM_O = 256;                      // first TMEM column of O_hi (O_lo follows 64 columns later)
 
 __device__ __forceinline__ uint64_t ap_desc_sw64(uint32_t smem_addr) {
@@ -69,7 +83,8 @@ __device__ __forceinline__ uint64_t ap_desc_sw64(uint32_t smem_addr) {
 }
 
 // NS16 = ceil(n_tok / 16) in [4, 14]; WIDE: 64-bit partial row sums (exponentials up to 2^31: |x0| >= 2048)
-template <int NS16, bool WIDE>
+// FP3: pass 3 on the FP32 pipe (exponentials below 2^23, see the table fill and `pw` below)
+template <int NS16, bool WIDE, bool FP3>
 __global__ void __launch_bounds__(AP_THREADS, 1)
 attention_pipe_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                       const AttnPipeArgs p, int8_t* __restrict__ out) {
@@ -117,7 +132,8 @@ attention_pipe_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
     // exponent table: sE[k][copy] = int_exp_shift(-k), k = max - q in [0, 255]; copy = lane -> every lane reads its own bank
     if (tid < 512) {
         const int k = tid & 255;
-        const uint32_t e = (uint32_t)shiftexp(-k, p.x0, p.inv_x0, p.n);
+        // FP3: the entry is the float 2^23 + E bit for bit (E < 2^23), see pass 3
+        const uint32_t e = (uint32_t)shiftexp(-k, p.x0, p.inv_x0, p.n) + (FP3 ? AP_MAGIC : 0u);
         const int c0 = (tid >> 8) * 16;
 #pragma unroll
         for (int j = 0; j < 16; ++j) sE[k * 32 + c0 + j] = e;
@@ -188,12 +204,15 @@ attention_pipe_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
             for (int t = 0; t < T; ++t) {
                 const int it = t / n_mt, mt = t % n_mt;
                 ptx::mbar_wait(s_free, (uint32_t)t & 1u);                           // S(t) is in registers: the columns are free
+                AP_TR(0);
                 // S(t) has completed: its Q buffer takes tile t+2, and after an item's last score MMA its K buffer takes
                 // the item after next
                 if (mt == n_mt - 1 && it + 2 < n_it) load_k(it + 2);
                 if (t + 1 < T) issue_s(t + 1);
                 if (t + 2 < T) load_q(t + 2);
+                AP_TR(1);
                 ptx::mbar_wait(p_ready, (uint32_t)t & 1u);                          // probabilities of tile t are in shared memory
+                AP_TR(2);
                 if (t > 0) {
                     ptx::mbar_wait(o_free, (uint32_t)(t - 1) & 1u);                 // O(t-1) has been read out of TMEM
                     // ... so P V(t-1) has completed: after an item's last tile its V buffer takes the item after next
@@ -201,6 +220,7 @@ attention_pipe_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
                     if ((t - 1) % n_mt == n_mt - 1 && itp + 2 < n_it) load_v(itp + 2);
                 }
                 if (mt == 0) ptx::mbar_wait(v_full + 8u * (uint32_t)(it & 1), (uint32_t)(it >> 1) & 1u);
+                AP_TR(3);
                 ptx::tc_fence_after();
                 const uint32_t sVi = sV + (uint32_t)((it & 1) * AP_KV_BYTES);
 #pragma unroll 1
@@ -213,6 +233,7 @@ attention_pipe_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
                     }
                 }
                 ptx::mma_commit(o_full);
+                AP_TR(4);
             }
         }
     } else {
@@ -287,6 +308,7 @@ attention_pipe_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
             const bool act = (mt * 128 + lg * 32) < n_tok;
             ptx::mbar_wait(s_full, (uint32_t)t & 1u);
             ptx::tc_fence_after();
+            AP_TR(0);
             if (!act) {
                 // rows past the sequence (upper lane groups of an item's last m-tile): keep the barrier protocol, compute
                 // nothing; the MMA reads whatever is in their P rows and nobody stores the result
@@ -332,6 +354,7 @@ attention_pipe_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
             ptx::tc_fence_before();                        // my tcgen05.ld of S(t) are complete (wait::ld)
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(s_free);       // -> the control warp may overwrite the S columns with S(t+1)
+            AP_TR(1);
             // padding columns [n_tok, NS) (at most 15, all in the last two chunks of the last part): forced to -128 so
             // that they never raise the max; their exponentials are taken out of the sum; their P meets zero V rows
             int npad = 0;
@@ -360,6 +383,7 @@ attention_pipe_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
             asm volatile("bar.sync %0, 128;" ::"r"(lg_bar) : "memory");
 #pragma unroll
             for (int pp = 0; pp < 4; ++pp) mxu = max(mxu, sRedMax[pp * 128 + trow]);
+            AP_TR(2);
             // ---- pass 2: exponentials E(max - q) from the table, row sum ----
             // address = table + 128 * (max - q) + 4 * lane: ONE dot-product instruction per element (IDP.4A, FMA pipe; the
             // selector holds -128 in byte i)
@@ -392,37 +416,57 @@ attention_pipe_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
                 asm("ld.shared.u32 %0, [%1];" : "=r"(epad) : "r"(pEq + 128 * 128));
                 sum -= (decltype(sum))npad * epad;
             }
+            if constexpr (FP3) sum -= (uint32_t)(8 * nch - npad) * AP_MAGIC;      // every remaining term carries 2^23's bits (mod 2^32: the true sum is < 2^29)
             if (part == 3) {                                                       // P of a padding column is zero by definition
 #pragma unroll
                 for (int j = BASE - 2; j < BASE; ++j) {
 #pragma unroll
                     for (int i = 0; i < 8; ++i)
-                        if (c_begin + 8 * j + i >= n_tok) E[8 * j + i] = 0;
+                        if (c_begin + 8 * j + i >= n_tok) E[8 * j + i] = FP3 ? AP_MAGIC : 0u;
                 }
             }
+            AP_TR(3);
             sRedSum[part * 128 + trow] = (unsigned long long)sum;
             asm volatile("bar.sync %0, 128;" ::"r"(lg_bar) : "memory");
             unsigned long long S = 0;
 #pragma unroll
             for (int pp = 0; pp < 4; ++pp) S += sRedSum[pp * 128 + trow];
-            if (p.dbg != nullptr && part == 0) {
+            if (AP_ROWSTATS && p.dbg != nullptr && part == 0) {
                 const int work = (int)blockIdx.x + it_cur * (int)gridDim.x;
                 p.dbg[((long long)work * n_mt + mt) * 128 + trow] = ((unsigned long long)mxu << 48) | S;
             }
             const uint32_t S32 = S > 2147483647ULL ? 2147483647u : (uint32_t)S;   // clamp_max_(2**31-1)
             const uint32_t F = 2147483647u / (S32 ? S32 : 1u);                    // <= 65535 (E(0) >= 2^15)
             const uint32_t Fs = F << 16;                                          // P = (E*F) >> 16 == umulhi(E, F << 16)
+            // FP3: IMAD.HI issues at a quarter of the FFMA rate (tools/ubench/pipes.cu: 4 vs 2 cycles per warp instruction
+            // and scheduler).  With t = 2^23 + E (the table entry read as a float), f = F / 2^16 and c = 2^23 - 2^7 F, all
+            // three exact in fp32, the fused t f + c = E F / 2^16 + 2^23 is rounded once, toward zero, at unit spacing:
+            // the mantissa of the result IS floor(E F / 2^16) = P < 2^16
+            const float Ff = __uint2float_rn(F) * (1.0f / 65536.0f);
+            const float Cf = __uint2float_rn(8388608u - 128u * F);
             // ---- pass 3: probabilities, byte planes -> A operand tiles.  P V of tile t-1 must have consumed them ----
+            AP_TR(4);
             if (t > 0) {
                 ptx::mbar_wait(o_full, (uint32_t)(t - 1) & 1u);
                 ptx::tc_fence_after();
             }
+            AP_TR(5);
             auto pw = [&](int j, int w, uint32_t& lo, uint32_t& hi) {
-                // P < 2^16: two of them share a word through one multiply-add, then one byte permute per plane
-                const uint32_t P01 = __umulhi(E[8 * j + 4 * w + 1], Fs) * 65536u + __umulhi(E[8 * j + 4 * w], Fs);
-                const uint32_t P23 = __umulhi(E[8 * j + 4 * w + 3], Fs) * 65536u + __umulhi(E[8 * j + 4 * w + 2], Fs);
-                lo = __byte_perm(P01, P23, 0x6420);
-                hi = __byte_perm(P01, P23, 0x7531);
+                if constexpr (FP3) {
+                    uint32_t r[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) r[i] = __float_as_uint(__fmaf_rz(__uint_as_float(E[8 * j + 4 * w + i]), Ff, Cf));
+                    const uint32_t a01 = __byte_perm(r[0], r[1], 0x5140);         // bytes {P0 lo, P1 lo, P0 hi, P1 hi}
+                    const uint32_t a23 = __byte_perm(r[2], r[3], 0x5140);
+                    lo = __byte_perm(a01, a23, 0x5410);
+                    hi = __byte_perm(a01, a23, 0x7632);
+                } else {
+                    // P < 2^16: two of them share a word through one multiply-add, then one byte permute per plane
+                    const uint32_t P01 = __umulhi(E[8 * j + 4 * w + 1], Fs) * 65536u + __umulhi(E[8 * j + 4 * w], Fs);
+                    const uint32_t P23 = __umulhi(E[8 * j + 4 * w + 3], Fs) * 65536u + __umulhi(E[8 * j + 4 * w + 2], Fs);
+                    lo = __byte_perm(P01, P23, 0x6420);
+                    hi = __byte_perm(P01, P23, 0x7531);
+                }
             };
             auto p_off = [&](int j) -> uint32_t {          // byte offset of the 8 keys of my chunk j inside a plane
                 const uint32_t key0 = (uint32_t)(c_begin + 8 * j);
@@ -468,7 +512,9 @@ attention_pipe_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
             ptx::fence_proxy_async();                      // P written through the generic proxy -> visible to the MMA
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(p_ready);
+            AP_TR(6);
             if (t > 0) do_output(mt_prev, ob_prev);
+            AP_TR(7);
         }
         if (T > 0) {
             ptx::mbar_wait(o_full, (uint32_t)(T - 1) & 1u);
@@ -526,16 +572,21 @@ int launch_attention_pipe(ivit_ctx* ctx, const int8_t* qkv, const ivit_attn_para
     const int grid = items < ctx->num_sms ? items : ctx->num_sms;                // persistent: one CTA per SM
     // per-thread partial sums cover at most 56 exponentials: 32-bit while E(0) = |x0| << n < 2^26
     const bool wide = (((long long)(-ap->x0)) << ap->n) >= (1LL << 26);
+    // exponentials below 2^23 (|x0| < 256, i.e. a softmax input scale above 1/256): pass 3 on the FP32 pipe
+    static const bool fp3_on = [] { const char* e = getenv("IVIT_ATTN_FP3"); return e == nullptr || e[0] != '0'; }();
+    const bool fp3 = fp3_on && (((long long)(-ap->x0)) << ap->n) < (1LL << 23);
 #define AP_CASE(N)                                                                                                     \
     case N: {                                                                                                          \
         static PerDevice attr_set;                                                                                     \
         if (!attr_set[ctx->device]) {                                                                                  \
-            IVIT_CUDA_OK(cudaFuncSetAttribute(attention_pipe_kernel<N, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AP_SMEM)); \
-            IVIT_CUDA_OK(cudaFuncSetAttribute(attention_pipe_kernel<N, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AP_SMEM));  \
+            IVIT_CUDA_OK(cudaFuncSetAttribute(attention_pipe_kernel<N, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AP_SMEM)); \
+            IVIT_CUDA_OK(cudaFuncSetAttribute(attention_pipe_kernel<N, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AP_SMEM));  \
+            IVIT_CUDA_OK(cudaFuncSetAttribute(attention_pipe_kernel<N, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AP_SMEM));  \
             attr_set[ctx->device] = 1;                                                                                 \
         }                                                                                                              \
-        if (wide) IVIT_CUDA_OK(launch_k(attention_pipe_kernel<N, true>, dim3(grid), dim3(AP_THREADS), AP_SMEM, s, tq, tk, a, out)); \
-        else IVIT_CUDA_OK(launch_k(attention_pipe_kernel<N, false>, dim3(grid), dim3(AP_THREADS), AP_SMEM, s, tq, tk, a, out));     \
+        if (fp3) IVIT_CUDA_OK(launch_k(attention_pipe_kernel<N, false, true>, dim3(grid), dim3(AP_THREADS), AP_SMEM, s, tq, tk, a, out));      \
+        else if (wide) IVIT_CUDA_OK(launch_k(attention_pipe_kernel<N, true, false>, dim3(grid), dim3(AP_THREADS), AP_SMEM, s, tq, tk, a, out)); \
+        else IVIT_CUDA_OK(launch_k(attention_pipe_kernel<N, false, false>, dim3(grid), dim3(AP_THREADS), AP_SMEM, s, tq, tk, a, out));         \
     } break;
     switch ((ap->n_tok + 15) >> 4) {
         AP_CASE(4) AP_CASE(5) AP_CASE(6) AP_CASE(7) AP_CASE(8) AP_CASE(9) AP_CASE(10) AP_CASE(11) AP_CASE(12) AP_CASE(13) AP_CASE(14)
