@@ -13,7 +13,8 @@ import threading
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "csrc", "libivit_b200.so")
+# IVIT_B200_SO: a differently built copy of the same library (kernel A/B experiments under tools/)
+SO_PATH = os.environ.get("IVIT_B200_SO") or os.path.join(_HERE, "csrc", "libivit_b200.so")
 
 I8, I16, I32, F32, U8, F64 = 0, 1, 2, 3, 4, 5
 EPI_RAW_I32, EPI_REQUANT, EPI_CARRIER = 0, 1, 2
@@ -79,6 +80,9 @@ SIGNATURES = {
     "ivit_avgpool_requant_i8": [_vp, _vp, _int, _int, _int, Dyadic, _vp, _vp],
     "ivit_widen_i8_i16": [_vp, _vp, _i64, _vp, _vp],
     "ivit_layernorm_i8_i16x2": [_vp, _vp, _i64, _int, _vp, _vp, Dyadic, _vp, _vp],
+    "ivit_tvm_softmax": [_vp, _vp, _i64, _int, C.c_int32, _int, _vp, _vp],
+    "ivit_tvm_gelu": [_vp, _vp, _i64, _int, C.c_int32, _int, _vp, _vp],
+    "ivit_tvm_layernorm": [_vp, _vp, _i64, _int, _vp, _vp, _vp],
 }
 EXPORTS = ["ivit_version", "ivit_last_error", "ivit_create", "ivit_destroy", "ivit_num_sms"] + sorted(SIGNATURES)
 

@@ -10,7 +10,7 @@ import subprocess
 import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SRCS = ["ivit_api.cu", "ivit_ops.cu", "ivit_fast.cu", "ivit_gemm.cu", "ivit_attn.cu", "ivit_attn_tc.cu", "ivit_attn_pipe.cu", "ivit_swin.cu", "ivit_attn_win.cu"]
+SRCS = ["ivit_api.cu", "ivit_ops.cu", "ivit_fast.cu", "ivit_gemm.cu", "ivit_attn.cu", "ivit_attn_tc.cu", "ivit_attn_pipe.cu", "ivit_swin.cu", "ivit_attn_win.cu", "ivit_tvm.cu"]
 HDRS = ["ivit_common.cuh", "ivit_internal.h", "ivit_ptx.cuh", "../../include/ivit_b200.h"]
 OUT = os.path.join(HERE, "libivit_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")

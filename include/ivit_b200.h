@@ -323,6 +323,22 @@ IVIT_API int ivit_widen_i8_i16(ivit_ctx*, const int8_t* x, int64_t n, int16_t* o
 IVIT_API int ivit_avgpool_requant_i8(ivit_ctx*, const int8_t* x, int B, int L, int C, ivit_dyadic_t me, int8_t* out,
                                      ivit_stream stream);
 
+/* ---- TVM-semantics compatibility mode -------------------------------------------------------
+ * The integer row operators as the reference's DEPLOYMENT tree states them in Relay, for cross-checking against the
+ * authors' deployed numerics: int32 wrapping arithmetic, truncating divisions, `(r >> 1) - x0` exponent, no clamp of the
+ * sums.  They differ numerically from ivit_shiftmax / ivit_shiftgelu / ivit_layernorm above (which follow
+ * models/quantization_utils/quant_modules.py) and are never used by the engines.  x0 = int(-1 / input_scale - 1)
+ * (layers.py:357; for GELU input_scale * 1.702, layers.py:394), computed by the caller.
+ *   ivit_tvm_softmax   replaces TVM_benchmark/models/layers.py:372-386 quantized_softmax (n = 16): int32 [rows, cols] -> int8
+ *   ivit_tvm_gelu      replaces TVM_benchmark/models/layers.py:389-404 quantized_gelu (n = 23): int32 -> int32 (pre * sigmoid_int)
+ *   ivit_tvm_layernorm replaces TVM_benchmark/models/layers.py:329-350 quantized_layernorm: int32 [rows, C] + bias_int[C] -> int32 */
+IVIT_API int ivit_tvm_softmax(ivit_ctx*, const int32_t* x, int64_t rows, int cols, int32_t x0, int n, int8_t* out,
+                              ivit_stream stream);
+IVIT_API int ivit_tvm_gelu(ivit_ctx*, const int32_t* x, int64_t rows, int cols, int32_t x0, int n, int32_t* out,
+                           ivit_stream stream);
+IVIT_API int ivit_tvm_layernorm(ivit_ctx*, const int32_t* x, int64_t rows, int C, const int32_t* bias_int, int32_t* out,
+                                ivit_stream stream);
+
 #ifdef __cplusplus
 }
 #endif
