@@ -15,7 +15,7 @@ import ivit_b200.kernels as K  # noqa: E402
 
 def main():
     dev = torch.device("cuda")
-    n_seq, n_tok, H, D = int(os.environ.get("NSEQ", "256")), 197, 12, 64
+    n_seq, n_tok, H, D = int(os.environ.get("NSEQ", "256")), 197, int(os.environ.get("HEADS", "12")), 64
     qkv = torch.randint(-128, 128, (n_seq * n_tok, 3 * H * D), dtype=torch.int8, device=dev)
     s_attn = np.float32(0.031)
     acc_scale = np.float32(127 * s_attn / (D * 127 * 40))
