@@ -307,6 +307,215 @@ layernorm_i16_i8_kernel(const int16_t* __restrict__ x, int64_t rows, int C, cons
 }
 
 // ------------------------------------------------------------------------------------
+// Four rows per warp, every lane a 1/32 slice of EACH row (C = 256 * NVL): the per-channel constants -- one 16-byte
+// shared-memory load per channel -- serve four rows instead of one (the 16-lane kernel above spends 47 % of the
+// shared-memory data pipe on them), and each group of 8 lanes computes the row scalars (mean, integer square root,
+// reciprocal) of ONE of the four rows after a transposing butterfly (18 shuffles), so that the scalar work per row is
+// halved as well.  No second register set: a vector of the next four rows is requested the moment the current one has
+// been consumed (rolling prefetch).  Same integers as layernorm_i16_i8_kernel.
+// ------------------------------------------------------------------------------------
+template <int NVL>
+__global__ void __launch_bounds__(256, 2)
+layernorm_i16_i8_r4_kernel(const int16_t* __restrict__ x, int64_t rows, int C, const int32_t* __restrict__ bias_int,
+                           const ivit_dyadic_t* __restrict__ me, int8_t* __restrict__ out) {
+    constexpr int R = 4;
+    ptx::grid_dep_wait();
+    const int lane = threadIdx.x & 31;
+    const int nvec = C >> 3;                                     // == 32 * NVL
+    const int64_t warp0 = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int64_t nwarps = (int64_t)gridDim.x * 8;
+    __shared__ LnCol s_c[256 * 4];
+    __shared__ int32_t s_b[256 * 4];
+    uint4 w[R][NVL];
+    // rows [rb, rb + 4) of vector j; rows past the end re-read the last row (their results are never stored)
+    auto load_vec = [&](int64_t rb, int j) {
+        if (rb + R <= rows) {                                    // warp-uniform: the common case has no per-row index math
+            const uint4* src = reinterpret_cast<const uint4*>(x + rb * (int64_t)C) + lane + 32 * j;
+#pragma unroll
+            for (int r = 0; r < R; ++r) w[r][j] = __ldg(src + r * nvec);
+        } else {
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const int64_t row = rb + r < rows ? rb + r : rows - 1;
+                w[r][j] = __ldg(reinterpret_cast<const uint4*>(x + row * (int64_t)C) + lane + 32 * j);
+            }
+        }
+    };
+    int64_t rbase = warp0 * R;
+    if (rbase < rows) {
+#pragma unroll
+        for (int j = 0; j < NVL; ++j) load_vec(rbase, j);
+    }
+    int ok = 1;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        const int32_t b = bias_int[c];
+        const ivit_dyadic_t d = me[c];
+        const int tz = __ffs(d.m) - 1;
+        const bool f = (d.e >= 32 && d.e <= 62) && (d.e - 1 - tz > 31) && (b > -(1 << 30)) && (b < (1 << 30));
+        ok &= f ? 1 : 0;
+        LnCol p;
+        p.m = d.m; p.sh = d.e - 32;
+        p.c = (d.e >= 1 && d.e <= 62) ? ((long long)b * (long long)d.m + (1LL << (d.e - 1))) : 0;
+        s_c[(c & 7) * nvec + (c >> 3)] = p;                      // channel 8*vi + u at [u][vi]: lanes read consecutive entries
+        s_b[(c & 7) * nvec + (c >> 3)] = b;
+    }
+    const bool fast = __syncthreads_and(ok) != 0;
+    const float inv_c = 1.0f / (float)C;
+    const LnCol* sc_lane = s_c + lane;
+    const int32_t* sb_lane = s_b + lane;
+    for (; rbase < rows; rbase += nwarps * R) {
+        const int64_t rnext = rbase + nwarps * R;
+        const bool more = rnext < rows;
+        // ---- statistics: per-lane partial sums of the four rows ----
+        // (vector by vector: the vector requested last -- at the end of the previous iteration -- is touched last)
+        int32_t sum[R], sqh[R], sql[R];
+        long long ssq[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) { sum[r] = 0; sqh[r] = 0; sql[r] = 0; }
+#pragma unroll
+        for (int j = 0; j < NVL; ++j) {
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const uint32_t tw[4] = {w[r][j].x, w[r][j].y, w[r][j].z, w[r][j].w};
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    sum[r] = dp2a_lo_ss(tw[u], 0x0101u, sum[r]);
+                    sqh[r] = dp2a_lo_ss(tw[u], __byte_perm(tw[u], 0u, 0x4431), sqh[r]);
+                    sql[r] = dp2a_lo_su(tw[u], __byte_perm(tw[u], 0u, 0x4420), sql[r]);
+                }
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < R; ++r) ssq[r] = (long long)sqh[r] * 256 + (long long)sql[r];
+        // transposing butterfly: after xor 16 a lane holds two rows, after xor 8 one (row (lane >> 3) & 3), then a plain reduction
+        int32_t s1[2];
+        long long q1[2];
+        {
+            const bool hi = (lane & 16) != 0;
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const int32_t keep_s = hi ? sum[2 + i] : sum[i], send_s = hi ? sum[i] : sum[2 + i];
+                const long long keep_q = hi ? ssq[2 + i] : ssq[i], send_q = hi ? ssq[i] : ssq[2 + i];
+                s1[i] = keep_s + __shfl_xor_sync(0xffffffffu, send_s, 16);
+                q1[i] = keep_q + __shfl_xor_sync(0xffffffffu, send_q, 16);
+            }
+        }
+        int32_t rs;
+        long long rq;
+        {
+            const bool hi = (lane & 8) != 0;
+            const int32_t keep_s = hi ? s1[1] : s1[0], send_s = hi ? s1[0] : s1[1];
+            const long long keep_q = hi ? q1[1] : q1[0], send_q = hi ? q1[0] : q1[1];
+            rs = keep_s + __shfl_xor_sync(0xffffffffu, send_s, 8);
+            rq = keep_q + __shfl_xor_sync(0xffffffffu, send_q, 8);
+        }
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) {
+            rs += __shfl_xor_sync(0xffffffffu, rs, o);
+            rq += __shfl_xor_sync(0xffffffffu, rq, o);
+        }
+        // ---- row scalars of my group's row (as in layernorm_i16_i8_kernel) ----
+        int32_t qd = (int32_t)floorf((float)rs * inv_c), rem = rs - qd * C;
+#pragma unroll
+        for (int t = 0; t < 3; ++t) {
+            if (rem < 0) { qd -= 1; rem += C; }
+            if (rem >= C) { qd += 1; rem -= C; }
+        }
+        if (2 * rem > C || (2 * rem == C && (qd & 1))) qd += 1;
+        const long long Vs = rq - (long long)qd * (2LL * (long long)rs - (long long)C * (long long)qd);
+        const unsigned long long k = ln_isqrt10((unsigned long long)Vs);
+        const int32_t Fm = (int32_t)(k <= 0xffffffffULL ? (2147483647u / (uint32_t)k) : 0u);
+        int32_t nmu[R], F[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            nmu[r] = -__shfl_sync(0xffffffffu, qd, 8 * r);
+            F[r] = __shfl_sync(0xffffffffu, Fm, 8 * r);
+        }
+        // ---- normalise + per-channel requant: one constant load per channel, four rows ----
+        const bool whole = rbase + R <= rows;                    // warp-uniform
+        uint2* dst = reinterpret_cast<uint2*>(out + rbase * (int64_t)C) + lane;
+        auto word_of = [&](int r, int j, int u) -> uint32_t {
+            return (u >> 1) == 0 ? w[r][j].x : ((u >> 1) == 1 ? w[r][j].y : ((u >> 1) == 2 ? w[r][j].z : w[r][j].w));
+        };
+        auto store_vec = [&](int j, const uint32_t (&pk)[R][2]) {
+            if (whole) {
+#pragma unroll
+                for (int r = 0; r < R; ++r) dst[r * nvec + 32 * j] = make_uint2(pk[r][0], pk[r][1]);
+            } else {
+#pragma unroll
+                for (int r = 0; r < R; ++r)
+                    if (rbase + r < rows) dst[r * nvec + 32 * j] = make_uint2(pk[r][0], pk[r][1]);
+            }
+        };
+        auto pack4 = [&](const int32_t (&v)[4]) -> uint32_t {
+            uint32_t hi2, lo2;
+            asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, %3;" : "=r"(hi2) : "r"(v[3]), "r"(v[2]), "r"(0));
+            asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, %3;" : "=r"(lo2) : "r"(v[1]), "r"(v[0]), "r"(hi2));
+            return lo2;
+        };
+        if (fast) {
+#pragma unroll
+            for (int j = 0; j < NVL; ++j) {
+                uint32_t pk[R][2];
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {                    // channels 4h .. 4h+3 of the vector
+                    int32_t res[R][4];
+#pragma unroll
+                    for (int uu = 0; uu < 4; ++uu) {
+                        const int u = 4 * h + uu;
+                        const int4 pw = *reinterpret_cast<const int4*>(sc_lane + u * nvec + 32 * j);   // {m, sh, c}
+                        const long long pc = (long long)(((unsigned long long)(uint32_t)pw.w << 32) | (uint32_t)pw.z);
+#pragma unroll
+                        for (int r = 0; r < R; ++r) {
+                            const int32_t y = dp2a_lo_ss(word_of(r, j, u), (u & 1) ? 0x0100u : 0x0001u, nmu[r]);   // x - mu
+                            int32_t z = (int32_t)(mul_wide_s32(y, F[r]) >> 1);                                    // floor(y F / 2)
+                            asm("" : "+r"(z));
+                            res[r][uu] = (int32_t)(((long long)z * (long long)pw.x + pc) >> 32) >> pw.y;
+                        }
+                    }
+#pragma unroll
+                    for (int r = 0; r < R; ++r) pk[r][h] = pack4(res[r]);
+                }
+                store_vec(j, pk);
+                if (more) load_vec(rnext, j);                    // this vector of the next four rows: in flight from here on
+            }
+        } else {
+            // general requants (a column outside the fast form): same structure, out-of-line arithmetic; fully unrolled so
+            // that the packed rows stay in registers
+#pragma unroll
+            for (int j = 0; j < NVL; ++j) {
+                uint32_t pk[R][2];
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    int32_t res[R][4];
+#pragma unroll
+                    for (int uu = 0; uu < 4; ++uu) {
+                        const int u = 4 * h + uu;
+                        const LnCol p = sc_lane[u * nvec + 32 * j];
+                        const int32_t b = sb_lane[u * nvec + 32 * j];
+#pragma unroll
+                        for (int r = 0; r < R; ++r) {
+                            const int32_t y = dp2a_lo_ss(word_of(r, j, u), (u & 1) ? 0x0100u : 0x0001u, nmu[r]);
+                            const int32_t z = (int32_t)(mul_wide_s32(y, F[r]) >> 1);
+                            long long o = (long long)z + (long long)b;
+                            o = o > 2147483647LL ? 2147483647LL : (o < -2147483648LL ? -2147483648LL : o);
+                            res[r][uu] = requant32_general((int32_t)o, p.m, p.sh + 32);
+                        }
+                    }
+#pragma unroll
+                    for (int r = 0; r < R; ++r) pk[r][h] = pack4(res[r]);
+                }
+                store_vec(j, pk);
+            }
+            if (more) {
+#pragma unroll
+                for (int j = 0; j < NVL; ++j) load_vec(rnext, j);
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------
 // Stem: input QuantAct (fp32 -> int8, vit_quant.py:257) fused with the patch unfold of QuantConv2d
 // (kernel == stride, layers_quant.py:190): one pass over the fp32 image, no int8 image round trip.
 //   out[(b*Hp + y/p)*Wp + x/p, (c*p + y%p)*p + x%p] = clamp8(RNE(fp32(1/s) * img[b,c,y,x]))
@@ -597,6 +806,20 @@ int ivit_layernorm_i16_i8(ivit_ctx* ctx, const int16_t* x, int64_t rows, int C, 
         if (variant == 3) layernorm_i16_i8_kernel<12, 8, true, 2, false><<<grid8, 256, 0, st(stream)>>>(x, rows, C, bias_int, me, out);
         else layernorm_i16_i8_kernel<12, 8, true, 1, true><<<grid8 / 2 > 0 ? grid8 / 2 : 1, 256, 0, st(stream)>>>(x, rows, C, bias_int, me, out);
         IVIT_LAUNCH_OK("layernorm_i16_i8_kernel");
+        return IVIT_OK;
+    }
+    // C a multiple of 256 (DeiT-B 768, ViT-L 1024, 512): four rows per warp, one constant load per channel and four rows
+    // (IVIT_LN_VARIANT=9: the 16-lane kernel below, for A/B timing)
+    if (variant == 0 && C % 256 == 0) {
+        const int64_t want4 = (rows + 31) / 32;
+        const int grid4 = (int)(want4 < (int64_t)ctx->num_sms * 2 ? want4 : (int64_t)ctx->num_sms * 2);
+        switch (C / 256) {
+            case 1: IVIT_CUDA_OK(launch_k(layernorm_i16_i8_r4_kernel<1>, dim3(grid4), dim3(256), 0, st(stream), x, rows, C, bias_int, me, out)); break;
+            case 2: IVIT_CUDA_OK(launch_k(layernorm_i16_i8_r4_kernel<2>, dim3(grid4), dim3(256), 0, st(stream), x, rows, C, bias_int, me, out)); break;
+            case 3: IVIT_CUDA_OK(launch_k(layernorm_i16_i8_r4_kernel<3>, dim3(grid4), dim3(256), 0, st(stream), x, rows, C, bias_int, me, out)); break;
+            default: IVIT_CUDA_OK(launch_k(layernorm_i16_i8_r4_kernel<4>, dim3(grid4), dim3(256), 0, st(stream), x, rows, C, bias_int, me, out)); break;
+        }
+        IVIT_LAUNCH_OK("layernorm_i16_i8_r4_kernel");
         return IVIT_OK;
     }
     const int bps = variant == 1 ? 3 : (variant == 2 ? 4 : 2);
