@@ -28,6 +28,10 @@ __device__ __forceinline__ void step(uint32_t (&a)[8], uint32_t b, uint32_t c, u
         if constexpr (OP == 13) a[i] = (uint32_t)(((unsigned long long)a[i] * b) >> 16);   // 64-bit product, funnel shift
         if constexpr (OP == 14) a[i] = __umul24(a[i], b) + c;                              // 24-bit multiply
         if constexpr (OP == 15) a[i] = (uint32_t)__float2uint_rz(__uint2float_rz(a[i]) * __uint_as_float(b));   // I2F, FMUL, F2I
+        if constexpr (OP == 16) asm volatile("dp2a.lo.s32.s32 %0, %0, %1, %2;" : "+r"(a[i]) : "r"(b), "r"(c));          // IDP.2A
+        if constexpr (OP == 17) a[i] = (uint32_t)(((long long)(int32_t)a[i] * (long long)(int32_t)b) >> 1);            // IMAD.WIDE + SHF.R.U64 (LayerNorm y F / 2)
+        if constexpr (OP == 18) a[i] = __float_as_uint(__fmaf_rz(__uint_as_float(a[i]), __uint_as_float(b), __uint_as_float(c)));   // FFMA
+        if constexpr (OP == 19) a[i] = (uint32_t)max(min((int32_t)a[i] + (int32_t)b, 127), -128);                      // IADD + clamp (VIMNMX3)
     }
 }
 
@@ -98,7 +102,7 @@ __global__ void bench_ldtm(uint32_t* out, long long* cyc, int x16) {
 
 static const char* NAMES[] = {"IMAD.HI.U32 (umulhi)", "IMAD.HI + 64-bit addend", "IMAD", "SHF.R.S32", "PRMT", "I2IP (cvt.pack.sat)", "IDP.4A",
                               "LDS (dependent, conflict-free)", "LOP3", "IADD3", "vmaxs2", "umulhi + IMAD pair", "IMAD.HI + SHF pair",
-                              "mul.wide >> 16", "umul24 + add", "I2F + FMUL + F2I"};
+                              "mul.wide >> 16", "umul24 + add", "I2F + FMUL + F2I", "IDP.2A", "IMAD.WIDE + SHF.R.U64 pair", "FFMA", "IADD + clamp"};
 
 template <int OP>
 void run(uint32_t* out, long long* cyc, int per_instr) {
@@ -123,6 +127,7 @@ int main() {
     run<0>(out, cyc, 1); run<1>(out, cyc, 1); run<2>(out, cyc, 1); run<3>(out, cyc, 1); run<4>(out, cyc, 1); run<5>(out, cyc, 1);
     run<6>(out, cyc, 1); run<7>(out, cyc, 1); run<8>(out, cyc, 1); run<9>(out, cyc, 1); run<10>(out, cyc, 1); run<11>(out, cyc, 2);
     run<12>(out, cyc, 2); run<13>(out, cyc, 1); run<14>(out, cyc, 1); run<15>(out, cyc, 3);
+    run<16>(out, cyc, 1); run<17>(out, cyc, 2); run<18>(out, cyc, 1); run<19>(out, cyc, 2);
     for (int x16 = 0; x16 < 2; ++x16)
         for (int W : {1, 2, 4}) {
             bench_ldtm<<<1, 128 * W>>>(out, cyc, x16);
