@@ -158,6 +158,12 @@ __device__ __forceinline__ int32_t dp2a_lo_su(uint32_t a, uint32_t b, int32_t c)
     asm("dp2a.lo.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
     return d;
 }
+// dp2a with signed 16-bit halves of a and signed bytes 2, 3 of b:  a.lo * b.b2 + a.hi * b.b3 + c
+__device__ __forceinline__ int32_t dp2a_hi_ss(uint32_t a, uint32_t b, int32_t c) {
+    int32_t d;
+    asm("dp2a.hi.s32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
 __device__ __forceinline__ int32_t dp2a_lo_ss(uint32_t a, uint32_t b, int32_t c) {
     int32_t d;
     asm("dp2a.lo.s32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
@@ -236,8 +242,9 @@ layernorm_i16_i8_kernel(const int16_t* __restrict__ x, int64_t rows, int C, cons
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 sum = dp2a_lo_ss(tw[u], 0x0101u, sum);
-                sh = dp2a_lo_ss(tw[u], __byte_perm(tw[u], 0u, 0x4431), sh);     // bytes {xh0, xh1}
-                sl = dp2a_lo_su(tw[u], __byte_perm(tw[u], 0u, 0x4420), sl);     // bytes {xl0, xl1}
+                const uint32_t hl = __byte_perm(tw[u], 0u, 0x3120);            // bytes {xl0, xl1, xh0, xh1}
+                sh = dp2a_hi_ss(tw[u], hl, sh);
+                sl = dp2a_lo_su(tw[u], hl, sl);
             }
         }
         long long ssq = (long long)sh * 256 + (long long)sl;
@@ -268,7 +275,7 @@ layernorm_i16_i8_kernel(const int16_t* __restrict__ x, int64_t rows, int C, cons
 #pragma unroll
                 for (int u = 0; u < 8; ++u) {
                     const int32_t y = dp2a_lo_ss(tw[u >> 1], (u & 1) ? 0x0100u : 0x0001u, -mu);   // x - mu, |.| <= 65535
-                    z[u] = (int32_t)(mul_wide_s32(y, F) >> 1);                             // floor(y * F / 2), |.| <= 2^30
+                    z[u] = ((y * F) >> 1);                             // floor(y * F / 2), |.| <= 2^30
                     asm("" : "+r"(z[u]));                                                  // a plain 32-bit value from here on
                 }
                 if (fast) {
@@ -380,8 +387,9 @@ layernorm_i16_i8_r4_kernel(const int16_t* __restrict__ x, int64_t rows, int C, c
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
                     sum[r] = dp2a_lo_ss(tw[u], 0x0101u, sum[r]);
-                    sqh[r] = dp2a_lo_ss(tw[u], __byte_perm(tw[u], 0u, 0x4431), sqh[r]);
-                    sql[r] = dp2a_lo_su(tw[u], __byte_perm(tw[u], 0u, 0x4420), sql[r]);
+                    const uint32_t hl = __byte_perm(tw[u], 0u, 0x3120);            // bytes {xl0, xl1, xh0, xh1}
+                    sqh[r] = dp2a_hi_ss(tw[u], hl, sqh[r]);
+                    sql[r] = dp2a_lo_su(tw[u], hl, sql[r]);
                 }
             }
         }
@@ -468,7 +476,10 @@ layernorm_i16_i8_r4_kernel(const int16_t* __restrict__ x, int64_t rows, int C, c
 #pragma unroll
                         for (int r = 0; r < R; ++r) {
                             const int32_t y = dp2a_lo_ss(word_of(r, j, u), (u & 1) ? 0x0100u : 0x0001u, nmu[r]);   // x - mu
-                            int32_t z = (int32_t)(mul_wide_s32(y, F[r]) >> 1);                                    // floor(y F / 2)
+                            // floor(y F / 2) from the 32-bit product: k >= floor(sqrt(V)) >= |y| for every element of
+                            // the row (V is the sum of the y^2), so |y F| <= k floor((2^31 - 1) / k) < 2^31 -- IMAD + SHF
+                            // instead of IMAD.WIDE (twice the pipe time, tools/ubench/pipes.cu) + 64-bit shift
+                            int32_t z = ((y * F[r]) >> 1);
                             asm("" : "+r"(z));
                             res[r][uu] = (int32_t)(((long long)z * (long long)pw.x + pc) >> 32) >> pw.y;
                         }
@@ -496,7 +507,7 @@ layernorm_i16_i8_r4_kernel(const int16_t* __restrict__ x, int64_t rows, int C, c
 #pragma unroll
                         for (int r = 0; r < R; ++r) {
                             const int32_t y = dp2a_lo_ss(word_of(r, j, u), (u & 1) ? 0x0100u : 0x0001u, nmu[r]);
-                            const int32_t z = (int32_t)(mul_wide_s32(y, F[r]) >> 1);
+                            const int32_t z = ((y * F[r]) >> 1);
                             long long o = (long long)z + (long long)b;
                             o = o > 2147483647LL ? 2147483647LL : (o < -2147483648LL ? -2147483648LL : o);
                             res[r][uu] = requant32_general((int32_t)o, p.m, p.sh + 32);

@@ -35,6 +35,12 @@ __device__ __forceinline__ int32_t g_dp2a_lo_su(uint32_t a, uint32_t b, int32_t 
     asm("dp2a.lo.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
     return d;
 }
+// dp2a with signed 16-bit halves of a and signed bytes 2, 3 of b:  a.lo * b.b2 + a.hi * b.b3 + c
+__device__ __forceinline__ int32_t g_dp2a_hi_ss(uint32_t a, uint32_t b, int32_t c) {
+    int32_t d;
+    asm("dp2a.hi.s32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
 __device__ __forceinline__ int32_t g_dp2a_lo_ss(uint32_t a, uint32_t b, int32_t c) {
     int32_t d;
     asm("dp2a.lo.s32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
@@ -151,8 +157,9 @@ layernorm_gather_kernel(const int16_t* __restrict__ x, int64_t rows, int C, cons
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 sum = g_dp2a_lo_ss(tw[u], 0x0101u, sum);
-                sh = g_dp2a_lo_ss(tw[u], __byte_perm(tw[u], 0u, 0x4431), sh);     // bytes {xh0, xh1}
-                sl = g_dp2a_lo_su(tw[u], __byte_perm(tw[u], 0u, 0x4420), sl);     // bytes {xl0, xl1}
+                const uint32_t hl = __byte_perm(tw[u], 0u, 0x3120);            // bytes {xl0, xl1, xh0, xh1}
+                sh = g_dp2a_hi_ss(tw[u], hl, sh);
+                sl = g_dp2a_lo_su(tw[u], hl, sl);
             }
         }
         long long ssq = (long long)sh * 256 + (long long)sl;
@@ -183,7 +190,7 @@ layernorm_gather_kernel(const int16_t* __restrict__ x, int64_t rows, int C, cons
 #pragma unroll
                 for (int u = 0; u < 8; ++u) {
                     const int32_t y = g_dp2a_lo_ss(tw[u >> 1], (u & 1) ? 0x0100u : 0x0001u, -mu);   // x - mu
-                    z[u] = (int32_t)(g_mul_wide_s32(y, F) >> 1);                                     // floor(y * F / 2)
+                    z[u] = ((y * F) >> 1);                                     // floor(y * F / 2)
                     asm("" : "+r"(z[u]));
                 }
                 if (fast) {

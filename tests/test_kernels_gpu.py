@@ -538,6 +538,28 @@ def test_layernorm_i16_i8_fast(K, C, mag):
     assert_equal(got, want, "layernorm_i16_i8 C=%d" % C)
 
 
+@pytest.mark.parametrize("C,rows,mag", [(256, 1, 3000), (256, 7, 32767), (512, 3, 12000), (512, 4, 500), (768, 5, 32767),
+                                        (768, 9, 40), (1024, 2, 32767), (768, 1031, 9000)])
+def test_layernorm_i16_i8_four_rows_per_warp(K, C, rows, mag):
+    """C a multiple of 256 takes the four-rows-per-warp kernel: row counts around the group of four, extreme magnitudes
+    (|x - mu| close to the integer square root of the variance: the 32-bit y * F product is at its bound), constant rows."""
+    rng = np.random.default_rng(C + rows)
+    q = rng.integers(-mag, mag + 1, (rows, C)).astype(np.int64)
+    q[0, :] = -mag
+    q[0, C // 3] = mag                                 # one element carries almost all of the variance
+    if rows > 1:
+        q[1] = mag                                     # zero variance at the top of the range
+    if rows > 2:
+        q[2, ::2] = mag
+        q[2, 1::2] = -mag                              # maximal variance
+    bq = rng.integers(-2 ** 24, 2 ** 24, C).astype(np.int64)
+    z = O.layernorm(q, bq)
+    m, e = rand_me(rng, C, 40, 52, neg_every=3)
+    want = O.requant(z, m, e, 8)
+    got = K.layernorm_i16_i8(dev(q.astype(np.int16)), dev(bq.astype(np.int32)), me_dev(K, m, e))
+    assert_equal(got, want, "layernorm_i16_i8 (four rows per warp) C=%d rows=%d" % (C, rows))
+
+
 def test_quantize_patchify_fused(K):
     rng = np.random.default_rng(21)
     for (B, Cin, H, W, p) in [(2, 3, 32, 48, 16), (3, 3, 16, 16, 4), (1, 3, 224, 224, 16)]:
