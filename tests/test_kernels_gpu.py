@@ -316,7 +316,10 @@ def test_gemm_requant_i8(K, M, N, K_, e_lo, e_hi):
     assert_equal(got, want, "gemm rq8 acc_bits=%d %dx%dx%d" % (bits, M, N, K_))
 
 
-@pytest.mark.parametrize("M,N,K_", [(197, 192, 768), (300, 768, 3072), (128, 256, 128), (1411, 768, 768), (1024, 1280, 384)])
+@pytest.mark.parametrize("M,N,K_", [(197, 192, 768), (300, 768, 3072), (128, 256, 128), (1411, 768, 768), (1024, 1280, 384),
+                                    # 128-wide un-paired tiles (N = 384: DeiT-small, Swin stage 3): several tiles per CTA,
+                                    # an M tail, one n-tile, a long K, a short K
+                                    (20000, 384, 384), (1411, 384, 1536), (130, 128, 256), (6272, 384, 96)])
 @pytest.mark.parametrize("variant", ["plain", "residual", "two_stage"])
 def test_gemm_requant_i16(K, M, N, K_, variant):
     rng = np.random.default_rng(M + N + K_ + len(variant))
