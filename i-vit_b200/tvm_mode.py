@@ -9,8 +9,11 @@ and argument meaning of ``layers.py`` -- tensors instead of Relay expressions --
 (``csrc/ivit_tvm.cu``) through the C ABI; there is no CPU fallback.  They exist to cross-check a deployed TVM build's
 intermediate tensors against this library's; the engines never call them.
 
-TVM itself is not available in this image, so these operators are checked against ``oracle/tvm_semantics.py`` (a numpy
-restatement of the same Relay expressions) only -- "parity unpinned" in the sense of DESIGN.md section 0.
+TVM itself is not available in this image.  The operators are checked against ``oracle/tvm_semantics.py`` and against
+``tests/golden/tvm_ops.npz`` -- vectors produced by the reference's own ``layers.py`` (unmodified) executed on a numpy
+stand-in for the relay primitives (``tests/golden/relay_shim.py``): the structure of each operator is pinned to the
+reference source, the integer semantics of the relay primitives (wrap, truncating division, ...) are taken from Relay's
+documentation and are not pinned to a TVM run.
 """
 from __future__ import annotations
 

@@ -1,9 +1,12 @@
 """CPU restatement (numpy) of the TVM-semantics integer row operators.  TEST INFRASTRUCTURE: imported by tests/ only.
 
-PARITY UNPINNED: the reference states these operators as TVM Relay expressions
-(/root/reference/TVM_benchmark/models/layers.py:329-404); TVM is not installed in this image and the reference ships no
-golden vectors for them, so this file restates the Relay expressions under Relay's documented integer semantics and is
-checked against nothing executable:
+PARITY: PINNED TO THE REFERENCE'S EXPRESSIONS, NOT TO A TVM RUN.  The reference states these operators as TVM Relay
+expressions (/root/reference/TVM_benchmark/models/layers.py:329-404); TVM is not installed in this image and the reference
+ships no vectors for them.  tests/golden/tvm_ops.npz holds the outputs of the reference's own layers.py, loaded unmodified
+and executed on a numpy stand-in for the dozen relay primitives it uses (tests/golden/relay_shim.py, generator
+make_tvm_golden.py); this file reproduces those vectors bit for bit (tests/test_tvm_oracle.py), so the STRUCTURE of every
+operator is the reference's.  What remains unpinned is the meaning of the primitives themselves, which both this file and
+the stand-in take from Relay's documented integer semantics:
 
   * int32 tensors, two's-complement wrap on add / sub / mul (Relay arithmetic lowers to LLVM integer ops);
   * ``a / b`` on integers is truncating division (``relay.divide`` -> ``tir.truncdiv``);

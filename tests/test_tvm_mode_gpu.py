@@ -1,5 +1,5 @@
 """TVM-semantics compatibility mode: the sm_100a kernels behind ivit_b200.tvm_mode against
-oracle/tvm_semantics.py, bit for bit.  The oracle itself is unpinned (no TVM here), see its header."""
+oracle/tvm_semantics.py and against vectors of the reference's own expressions (tests/golden/tvm_ops.npz), bit for bit."""
 import numpy as np
 import pytest
 import torch
@@ -58,3 +58,19 @@ def test_layernorm(M, rows, C, mag):
 def test_refuses_cpu_tensors(M):
     with pytest.raises(RuntimeError):
         M.quantized_softmax(torch.zeros(2, 8, dtype=torch.int32), 0.1)
+
+
+def test_kernels_equal_the_reference_expressions(M):
+    """The CUDA kernels against tests/golden/tvm_ops.npz: vectors produced by the reference's own layers.py (unmodified)
+    executed on the numpy stand-in for the relay primitives (tests/golden/make_tvm_golden.py)."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "tvm_ops.npz"))
+    for i in range(3):
+        got = M.quantized_softmax(torch.from_numpy(g["sm%d_x" % i]).cuda(), float(g["sm%d_s" % i])).cpu().numpy()
+        assert np.array_equal(got, g["sm%d_y" % i]), "softmax %d" % i
+    for i in range(4):
+        got = M.quantized_gelu(torch.from_numpy(g["ge%d_x" % i]).cuda(), float(g["ge%d_s" % i])).cpu().numpy()
+        assert np.array_equal(got, g["ge%d_y" % i]), "gelu %d" % i
+    for i in range(4):
+        got = M.quantized_layernorm(torch.from_numpy(g["ln%d_x" % i]).cuda(), torch.from_numpy(g["ln%d_b" % i]).cuda()).cpu().numpy()
+        assert np.array_equal(got, g["ln%d_y" % i]), "layernorm %d" % i

@@ -1,6 +1,6 @@
-"""CPU checks of the TVM-semantics oracle (oracle/tvm_semantics.py).  TVM is absent from this image and the reference
-holds no vectors for TVM_benchmark/models/layers.py:329-404, so the restatement is UNPINNED; what can be checked here is
-that it is the stated arithmetic (hand-computed cases) and that it approximates the functions it stands for."""
+"""CPU checks of the TVM-semantics oracle (oracle/tvm_semantics.py): hand-computed cases, closeness to the functions the
+operators stand for, and bit-equality with vectors produced by the reference's own TVM_benchmark/models/layers.py executed
+on a numpy stand-in for the relay primitives (TVM itself is absent from this image)."""
 import numpy as np
 
 from oracle import tvm_semantics as T
@@ -57,3 +57,50 @@ def test_layernorm_close_to_float_layernorm_and_truncating_mean():
     f = (2 ** 31 - 1) // std
     want = np.array([int(np.trunc(f * v / 2)) for v in d[0]])
     assert np.array_equal(out[0], want)
+
+
+# ---- the reference's OWN Relay expressions, executed on a numpy stand-in for the relay primitives ----------------------
+import os  # noqa: E402
+
+import pytest  # noqa: E402
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "tvm_ops.npz")
+
+
+def test_oracle_equals_the_reference_expressions():
+    """tests/golden/tvm_ops.npz was produced by loading TVM_benchmark/models/layers.py unmodified on
+    tests/golden/relay_shim.py (make_tvm_golden.py): the structure of every operator is the reference's."""
+    g = np.load(GOLD)
+    for i in range(3):
+        assert np.array_equal(T.quantized_softmax(g["sm%d_x" % i], float(g["sm%d_s" % i])), g["sm%d_y" % i]), i
+    for i in range(4):
+        assert np.array_equal(T.quantized_gelu(g["ge%d_x" % i], float(g["ge%d_s" % i])), g["ge%d_y" % i]), i
+    for i in range(4):
+        assert np.array_equal(T.quantized_layernorm(g["ln%d_x" % i], g["ln%d_b" % i]), g["ln%d_y" % i]), i
+    for i in range(3):
+        y = T.shift_exp(g["se%d_d" % i], T.x0_of(float(g["se%d_s" % i])), int(g["se%d_n" % i]))
+        assert np.array_equal(y, g["se%d_y" % i]), i
+    assert np.abs(g["ge2_y"]).max() > 0 and g["ln2_y"].dtype == np.int32
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/TVM_benchmark/models/layers.py"), reason="reference checkout absent")
+def test_golden_vectors_regenerate_from_the_reference_source():
+    import importlib.util
+    import sys
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    sys.path.insert(0, here)
+    try:
+        spec = importlib.util.spec_from_file_location("make_tvm_golden", os.path.join(here, "make_tvm_golden.py"))
+        mk = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mk)
+        L = mk.load_layers()
+        import relay_shim as R
+        g = np.load(GOLD)
+        y = L.quantized_softmax(R.Expr(g["sm0_x"].astype(np.int64), "int8"), float(g["sm0_s"]))
+        assert np.array_equal(y.v.astype(np.int8), g["sm0_y"])
+        y = L.quantized_layernorm(R.Expr(g["ln1_x"].astype(np.int64), "int32"), R.Expr(g["ln1_b"].astype(np.int64), "int32"))
+        assert np.array_equal(y.v.astype(np.int32), g["ln1_y"])
+    finally:
+        sys.path.remove(here)
+        for m in ("tvm", "tvm.relay", "tvm.relay.op", "tvm.relay.op.tensor"):
+            sys.modules.pop(m, None)
