@@ -592,9 +592,9 @@ def test_quantize_patchify_u8_matches_reference_transform(K):
         assert np.array_equal(got, want), (B, H, W)
 
 
-def test_embed_tokens_fast_matches_general(K):
-    rng = np.random.default_rng(22)
-    B, N, C = 3, 17, 64
+@pytest.mark.parametrize("B,N,C", [(3, 17, 64), (2, 197, 768), (5, 50, 192)])
+def test_embed_tokens_fast_matches_general(K, B, N, C):
+    rng = np.random.default_rng(22 + C)
     pe = rng.integers(-32768, 32768, (B * (N - 1), C)).astype(np.int16)
     cls = rng.integers(-200000, 200000, C).astype(np.int32)        # the cls token is not clamped to 16 bits
     pos = rng.integers(-32768, 32768, (N, C)).astype(np.int16)
