@@ -314,37 +314,44 @@ layernorm_i16_i8_kernel(const int16_t* __restrict__ x, int64_t rows, int C, cons
 }
 
 // ------------------------------------------------------------------------------------
-// Four rows per warp, every lane a 1/32 slice of EACH row (C = 256 * NVL): the per-channel constants -- one 16-byte
-// shared-memory load per channel -- serve four rows instead of one (the 16-lane kernel above spends 47 % of the
-// shared-memory data pipe on them), and each group of 8 lanes computes the row scalars (mean, integer square root,
-// reciprocal) of ONE of the four rows after a transposing butterfly (18 shuffles), so that the scalar work per row is
-// halved as well.  No second register set: a vector of the next four rows is requested the moment the current one has
-// been consumed (rolling prefetch).  Same integers as layernorm_i16_i8_kernel.
+// Four rows per warp.  The warp is split into groups of LPG lanes (32, 16 or 8); a group holds RPL = LPG / 8 of the four
+// rows and every lane of it a 1/LPG slice of EACH of them (C = 8 * NVL * LPG: 768 = 3 x 32, 384 = 3 x 16, 192 = 3 x 8, ...),
+// so one 16-byte shared-memory load of the per-channel constants serves RPL rows (the 16-lane kernel above spends 47 % of
+// the shared-memory data pipe on them); a transposing butterfly inside the group leaves each run of 8 lanes with the sums
+// of ONE of the four rows, whose scalars (mean, integer square root, reciprocal) it computes and hands to the lanes that
+// need them -- half the scalar work per row of the 16-lane kernel.  The fast / general requant decision is hoisted out of
+// the row loop, whole groups of rows use one base pointer and immediate offsets, and there is no second register set:
+// a vector of the next rows is requested the moment the current one has been consumed (rolling prefetch).
+// Same integers as layernorm_i16_i8_kernel.
 // ------------------------------------------------------------------------------------
-template <int NVL>
+template <int NVL, int LPG>
 __global__ void __launch_bounds__(256, 2)
 layernorm_i16_i8_r4_kernel(const int16_t* __restrict__ x, int64_t rows, int C, const int32_t* __restrict__ bias_int,
                            const ivit_dyadic_t* __restrict__ me, int8_t* __restrict__ out) {
-    constexpr int R = 4;
+    static_assert(LPG == 32 || LPG == 16 || LPG == 8, "lanes per row group");
+    constexpr int R = 4;                                         // rows per warp
+    constexpr int RPL = LPG / 8;                                 // rows per lane (= rows per group)
     ptx::grid_dep_wait();
     const int lane = threadIdx.x & 31;
-    const int nvec = C >> 3;                                     // == 32 * NVL
+    const int sub = lane % LPG, grp = lane / LPG;
+    const int nvec = C >> 3;                                     // == LPG * NVL
     const int64_t warp0 = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
     const int64_t nwarps = (int64_t)gridDim.x * 8;
     __shared__ LnCol s_c[256 * 4];
     __shared__ int32_t s_b[256 * 4];
-    uint4 w[R][NVL];
-    // rows [rb, rb + 4) of vector j; rows past the end re-read the last row (their results are never stored)
+    uint4 w[RPL][NVL];
+    // my group's rows [rb + grp * RPL, + RPL) of vector j; rows past the end re-read the last row (never stored)
     auto load_vec = [&](int64_t rb, int j) {
         if (rb + R <= rows) {                                    // warp-uniform: the common case has no per-row index math
-            const uint4* src = reinterpret_cast<const uint4*>(x + rb * (int64_t)C) + lane + 32 * j;
+            const uint4* src = reinterpret_cast<const uint4*>(x + (rb + grp * RPL) * (int64_t)C) + sub + LPG * j;
 #pragma unroll
-            for (int r = 0; r < R; ++r) w[r][j] = __ldg(src + r * nvec);
+            for (int r = 0; r < RPL; ++r) w[r][j] = __ldg(src + r * nvec);
         } else {
 #pragma unroll
-            for (int r = 0; r < R; ++r) {
-                const int64_t row = rb + r < rows ? rb + r : rows - 1;
-                w[r][j] = __ldg(reinterpret_cast<const uint4*>(x + row * (int64_t)C) + lane + 32 * j);
+            for (int r = 0; r < RPL; ++r) {
+                const int64_t want = rb + grp * RPL + r;
+                const int64_t row = want < rows ? want : rows - 1;
+                w[r][j] = __ldg(reinterpret_cast<const uint4*>(x + row * (int64_t)C) + sub + LPG * j);
             }
         }
     };
@@ -368,21 +375,21 @@ layernorm_i16_i8_r4_kernel(const int16_t* __restrict__ x, int64_t rows, int C, c
     }
     const bool fast = __syncthreads_and(ok) != 0;
     const float inv_c = 1.0f / (float)C;
-    const LnCol* sc_lane = s_c + lane;
-    const int32_t* sb_lane = s_b + lane;
+    const LnCol* sc_lane = s_c + sub;
+    const int32_t* sb_lane = s_b + sub;
     for (; rbase < rows; rbase += nwarps * R) {
         const int64_t rnext = rbase + nwarps * R;
         const bool more = rnext < rows;
-        // ---- statistics: per-lane partial sums of the four rows ----
+        // ---- statistics: per-lane partial sums of my rows
         // (vector by vector: the vector requested last -- at the end of the previous iteration -- is touched last)
-        int32_t sum[R], sqh[R], sql[R];
-        long long ssq[R];
+        int32_t sum[RPL], sqh[RPL], sql[RPL];
+        long long ssq[RPL];
 #pragma unroll
-        for (int r = 0; r < R; ++r) { sum[r] = 0; sqh[r] = 0; sql[r] = 0; }
+        for (int r = 0; r < RPL; ++r) { sum[r] = 0; sqh[r] = 0; sql[r] = 0; }
 #pragma unroll
         for (int j = 0; j < NVL; ++j) {
 #pragma unroll
-            for (int r = 0; r < R; ++r) {
+            for (int r = 0; r < RPL; ++r) {
                 const uint32_t tw[4] = {w[r][j].x, w[r][j].y, w[r][j].z, w[r][j].w};
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
@@ -394,35 +401,39 @@ layernorm_i16_i8_r4_kernel(const int16_t* __restrict__ x, int64_t rows, int C, c
             }
         }
 #pragma unroll
-        for (int r = 0; r < R; ++r) ssq[r] = (long long)sqh[r] * 256 + (long long)sql[r];
-        // transposing butterfly: after xor 16 a lane holds two rows, after xor 8 one (row (lane >> 3) & 3), then a plain reduction
-        int32_t s1[2];
-        long long q1[2];
-        {
-            const bool hi = (lane & 16) != 0;
+        for (int r = 0; r < RPL; ++r) ssq[r] = (long long)sqh[r] * 256 + (long long)sql[r];
+        // transposing butterfly inside the group: every exchange halves the rows a lane holds, until each run of 8 lanes
+        // holds one row (row (lane >> 3) & 3 of the warp's four), then a plain reduction over the 8 lanes
+        int32_t rs;
+        long long rq;
+        if constexpr (RPL == 4) {
+            int32_t s1[2];
+            long long q1[2];
+            const bool hi16 = (lane & 16) != 0;
 #pragma unroll
             for (int i = 0; i < 2; ++i) {
-                const int32_t keep_s = hi ? sum[2 + i] : sum[i], send_s = hi ? sum[i] : sum[2 + i];
-                const long long keep_q = hi ? ssq[2 + i] : ssq[i], send_q = hi ? ssq[i] : ssq[2 + i];
+                const int32_t keep_s = hi16 ? sum[2 + i] : sum[i], send_s = hi16 ? sum[i] : sum[2 + i];
+                const long long keep_q = hi16 ? ssq[2 + i] : ssq[i], send_q = hi16 ? ssq[i] : ssq[2 + i];
                 s1[i] = keep_s + __shfl_xor_sync(0xffffffffu, send_s, 16);
                 q1[i] = keep_q + __shfl_xor_sync(0xffffffffu, send_q, 16);
             }
-        }
-        int32_t rs;
-        long long rq;
-        {
-            const bool hi = (lane & 8) != 0;
-            const int32_t keep_s = hi ? s1[1] : s1[0], send_s = hi ? s1[0] : s1[1];
-            const long long keep_q = hi ? q1[1] : q1[0], send_q = hi ? q1[0] : q1[1];
-            rs = keep_s + __shfl_xor_sync(0xffffffffu, send_s, 8);
-            rq = keep_q + __shfl_xor_sync(0xffffffffu, send_q, 8);
+            const bool hi8 = (lane & 8) != 0;
+            rs = (hi8 ? s1[1] : s1[0]) + __shfl_xor_sync(0xffffffffu, hi8 ? s1[0] : s1[1], 8);
+            rq = (hi8 ? q1[1] : q1[0]) + __shfl_xor_sync(0xffffffffu, hi8 ? q1[0] : q1[1], 8);
+        } else if constexpr (RPL == 2) {
+            const bool hi8 = (lane & 8) != 0;
+            rs = (hi8 ? sum[1] : sum[0]) + __shfl_xor_sync(0xffffffffu, hi8 ? sum[0] : sum[1], 8);
+            rq = (hi8 ? ssq[1] : ssq[0]) + __shfl_xor_sync(0xffffffffu, hi8 ? ssq[0] : ssq[1], 8);
+        } else {
+            rs = sum[0];
+            rq = ssq[0];
         }
 #pragma unroll
         for (int o = 4; o > 0; o >>= 1) {
             rs += __shfl_xor_sync(0xffffffffu, rs, o);
             rq += __shfl_xor_sync(0xffffffffu, rq, o);
         }
-        // ---- row scalars of my group's row (as in layernorm_i16_i8_kernel) ----
+        // ---- row scalars of my run's row (as in layernorm_i16_i8_kernel) ----
         int32_t qd = (int32_t)floorf((float)rs * inv_c), rem = rs - qd * C;
 #pragma unroll
         for (int t = 0; t < 3; ++t) {
@@ -433,26 +444,26 @@ layernorm_i16_i8_r4_kernel(const int16_t* __restrict__ x, int64_t rows, int C, c
         const long long Vs = rq - (long long)qd * (2LL * (long long)rs - (long long)C * (long long)qd);
         const unsigned long long k = ln_isqrt10((unsigned long long)Vs);
         const int32_t Fm = (int32_t)(k <= 0xffffffffULL ? (2147483647u / (uint32_t)k) : 0u);
-        int32_t nmu[R], F[R];
+        int32_t nmu[RPL], F[RPL];                                // of MY rows: warp row grp * RPL + r lives in lanes 8 * (...)
 #pragma unroll
-        for (int r = 0; r < R; ++r) {
-            nmu[r] = -__shfl_sync(0xffffffffu, qd, 8 * r);
-            F[r] = __shfl_sync(0xffffffffu, Fm, 8 * r);
+        for (int r = 0; r < RPL; ++r) {
+            nmu[r] = -__shfl_sync(0xffffffffu, qd, 8 * (grp * RPL + r));
+            F[r] = __shfl_sync(0xffffffffu, Fm, 8 * (grp * RPL + r));
         }
-        // ---- normalise + per-channel requant: one constant load per channel, four rows ----
+        // ---- normalise + per-channel requant: one constant load per channel and RPL rows ----
         const bool whole = rbase + R <= rows;                    // warp-uniform
-        uint2* dst = reinterpret_cast<uint2*>(out + rbase * (int64_t)C) + lane;
+        uint2* dst = reinterpret_cast<uint2*>(out + (rbase + grp * RPL) * (int64_t)C) + sub;
         auto word_of = [&](int r, int j, int u) -> uint32_t {
             return (u >> 1) == 0 ? w[r][j].x : ((u >> 1) == 1 ? w[r][j].y : ((u >> 1) == 2 ? w[r][j].z : w[r][j].w));
         };
-        auto store_vec = [&](int j, const uint32_t (&pk)[R][2]) {
+        auto store_vec = [&](int j, const uint32_t (&pk)[RPL][2]) {
             if (whole) {
 #pragma unroll
-                for (int r = 0; r < R; ++r) dst[r * nvec + 32 * j] = make_uint2(pk[r][0], pk[r][1]);
+                for (int r = 0; r < RPL; ++r) dst[r * nvec + LPG * j] = make_uint2(pk[r][0], pk[r][1]);
             } else {
 #pragma unroll
-                for (int r = 0; r < R; ++r)
-                    if (rbase + r < rows) dst[r * nvec + 32 * j] = make_uint2(pk[r][0], pk[r][1]);
+                for (int r = 0; r < RPL; ++r)
+                    if (rbase + grp * RPL + r < rows) dst[r * nvec + LPG * j] = make_uint2(pk[r][0], pk[r][1]);
             }
         };
         auto pack4 = [&](const int32_t (&v)[4]) -> uint32_t {
@@ -464,17 +475,17 @@ layernorm_i16_i8_r4_kernel(const int16_t* __restrict__ x, int64_t rows, int C, c
         if (fast) {
 #pragma unroll
             for (int j = 0; j < NVL; ++j) {
-                uint32_t pk[R][2];
+                uint32_t pk[RPL][2];
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {                    // channels 4h .. 4h+3 of the vector
-                    int32_t res[R][4];
+                    int32_t res[RPL][4];
 #pragma unroll
                     for (int uu = 0; uu < 4; ++uu) {
                         const int u = 4 * h + uu;
-                        const int4 pw = *reinterpret_cast<const int4*>(sc_lane + u * nvec + 32 * j);   // {m, sh, c}
+                        const int4 pw = *reinterpret_cast<const int4*>(sc_lane + u * nvec + LPG * j);   // {m, sh, c}
                         const long long pc = (long long)(((unsigned long long)(uint32_t)pw.w << 32) | (uint32_t)pw.z);
 #pragma unroll
-                        for (int r = 0; r < R; ++r) {
+                        for (int r = 0; r < RPL; ++r) {
                             const int32_t y = dp2a_lo_ss(word_of(r, j, u), (u & 1) ? 0x0100u : 0x0001u, nmu[r]);   // x - mu
                             // floor(y F / 2) from the 32-bit product: k >= floor(sqrt(V)) >= |y| for every element of
                             // the row (V is the sum of the y^2), so |y F| <= k floor((2^31 - 1) / k) < 2^31 -- IMAD + SHF
@@ -485,27 +496,27 @@ layernorm_i16_i8_r4_kernel(const int16_t* __restrict__ x, int64_t rows, int C, c
                         }
                     }
 #pragma unroll
-                    for (int r = 0; r < R; ++r) pk[r][h] = pack4(res[r]);
+                    for (int r = 0; r < RPL; ++r) pk[r][h] = pack4(res[r]);
                 }
                 store_vec(j, pk);
-                if (more) load_vec(rnext, j);                    // this vector of the next four rows: in flight from here on
+                if (more) load_vec(rnext, j);                    // this vector of the next rows: in flight from here on
             }
         } else {
             // general requants (a column outside the fast form): same structure, out-of-line arithmetic; fully unrolled so
             // that the packed rows stay in registers
 #pragma unroll
             for (int j = 0; j < NVL; ++j) {
-                uint32_t pk[R][2];
+                uint32_t pk[RPL][2];
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
-                    int32_t res[R][4];
+                    int32_t res[RPL][4];
 #pragma unroll
                     for (int uu = 0; uu < 4; ++uu) {
                         const int u = 4 * h + uu;
-                        const LnCol p = sc_lane[u * nvec + 32 * j];
-                        const int32_t b = sb_lane[u * nvec + 32 * j];
+                        const LnCol p = sc_lane[u * nvec + LPG * j];
+                        const int32_t b = sb_lane[u * nvec + LPG * j];
 #pragma unroll
-                        for (int r = 0; r < R; ++r) {
+                        for (int r = 0; r < RPL; ++r) {
                             const int32_t y = dp2a_lo_ss(word_of(r, j, u), (u & 1) ? 0x0100u : 0x0001u, nmu[r]);
                             const int32_t z = ((y * F[r]) >> 1);
                             long long o = (long long)z + (long long)b;
@@ -514,7 +525,7 @@ layernorm_i16_i8_r4_kernel(const int16_t* __restrict__ x, int64_t rows, int C, c
                         }
                     }
 #pragma unroll
-                    for (int r = 0; r < R; ++r) pk[r][h] = pack4(res[r]);
+                    for (int r = 0; r < RPL; ++r) pk[r][h] = pack4(res[r]);
                 }
                 store_vec(j, pk);
             }
@@ -824,19 +835,30 @@ int ivit_layernorm_i16_i8(ivit_ctx* ctx, const int16_t* x, int64_t rows, int C, 
         IVIT_LAUNCH_OK("layernorm_i16_i8_kernel");
         return IVIT_OK;
     }
-    // C a multiple of 256 (DeiT-B 768, ViT-L 1024, 512): four rows per warp, one constant load per channel and four rows
+    // four rows per warp, C = 8 * NVL * LPG with LPG = 32 / 16 / 8 lanes per row group and NVL <= 4 vectors per lane:
+    // 768 = 3 x 32 (DeiT-B), 1024 = 4 x 32 (ViT-L), 384 = 3 x 16 (DeiT-S), 192 = 3 x 8 (DeiT-T), 512, 256, 128, 64
     // (IVIT_LN_VARIANT=9: the 16-lane kernel below, for A/B timing)
-    if (variant == 0 && C % 256 == 0) {
+    if (variant == 0 && C % 64 == 0) {
         const int64_t want4 = (rows + 31) / 32;
         const int grid4 = (int)(want4 < (int64_t)ctx->num_sms * 2 ? want4 : (int64_t)ctx->num_sms * 2);
-        switch (C / 256) {
-            case 1: IVIT_CUDA_OK(launch_k(layernorm_i16_i8_r4_kernel<1>, dim3(grid4), dim3(256), 0, st(stream), x, rows, C, bias_int, me, out)); break;
-            case 2: IVIT_CUDA_OK(launch_k(layernorm_i16_i8_r4_kernel<2>, dim3(grid4), dim3(256), 0, st(stream), x, rows, C, bias_int, me, out)); break;
-            case 3: IVIT_CUDA_OK(launch_k(layernorm_i16_i8_r4_kernel<3>, dim3(grid4), dim3(256), 0, st(stream), x, rows, C, bias_int, me, out)); break;
-            default: IVIT_CUDA_OK(launch_k(layernorm_i16_i8_r4_kernel<4>, dim3(grid4), dim3(256), 0, st(stream), x, rows, C, bias_int, me, out)); break;
+#define LN4(NVLV, LPGV) IVIT_CUDA_OK(launch_k(layernorm_i16_i8_r4_kernel<NVLV, LPGV>, dim3(grid4), dim3(256), 0, st(stream), x, rows, C, bias_int, me, out))
+        bool done = true;
+        switch (C) {
+            case 1024: LN4(4, 32); break;
+            case 768: LN4(3, 32); break;
+            case 512: LN4(2, 32); break;
+            case 256: LN4(1, 32); break;
+            case 384: LN4(3, 16); break;
+            case 192: LN4(3, 8); break;
+            case 128: LN4(2, 8); break;
+            case 64: LN4(1, 8); break;
+            default: done = false; break;
         }
-        IVIT_LAUNCH_OK("layernorm_i16_i8_r4_kernel");
-        return IVIT_OK;
+#undef LN4
+        if (done) {
+            IVIT_LAUNCH_OK("layernorm_i16_i8_r4_kernel");
+            return IVIT_OK;
+        }
     }
     const int bps = variant == 1 ? 3 : (variant == 2 ? 4 : 2);
     const int grid = (int)(want < (int64_t)ctx->num_sms * bps ? want : (int64_t)ctx->num_sms * bps);

@@ -542,9 +542,12 @@ def test_layernorm_i16_i8_fast(K, C, mag):
 
 
 @pytest.mark.parametrize("C,rows,mag", [(256, 1, 3000), (256, 7, 32767), (512, 3, 12000), (512, 4, 500), (768, 5, 32767),
-                                        (768, 9, 40), (1024, 2, 32767), (768, 1031, 9000)])
+                                        (768, 9, 40), (1024, 2, 32767), (768, 1031, 9000),
+                                        # 16 and 8 lanes per row group (two rows / one row per lane)
+                                        (384, 1, 32767), (384, 6, 9000), (384, 1027, 20000), (192, 3, 32767), (192, 1030, 700),
+                                        (128, 5, 32767), (64, 9, 1000), (64, 2, 32767)])
 def test_layernorm_i16_i8_four_rows_per_warp(K, C, rows, mag):
-    """C a multiple of 256 takes the four-rows-per-warp kernel: row counts around the group of four, extreme magnitudes
+    """The four-rows-per-warp kernel (32 / 16 / 8 lanes per row group): row counts around the group of four, extreme magnitudes
     (|x - mu| close to the integer square root of the variance: the 32-bit y * F product is at its bound), constant rows."""
     rng = np.random.default_rng(C + rows)
     q = rng.integers(-mag, mag + 1, (rows, C)).astype(np.int64)
