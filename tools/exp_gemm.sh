@@ -1,5 +1,5 @@
 #!/bin/bash
-# TMA residual tile for the 128-wide un-paired GEMM tiles: parity, then DeiT-small / Swin-tiny step time with / without
+# TMA residual tile of the residual-block GEMMs (IVIT_GEMM_RTMA=1 default / 0): parity, then the step time of the three configs
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 {
